@@ -1,0 +1,351 @@
+"""CPU ORACLE -- test infrastructure only, never the product path.
+
+A stage-wise restatement, in plain PyTorch **CPU** fp32 ops, of the reference's per-ray render hot
+path (``render()`` of ``run_S_eS_eN_alter_trt.py``).  It exists so that every CUDA kernel in
+``pronerf_b200/csrc`` can be checked on *identical inputs* against each intermediate of the
+reference algorithm.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module.
+
+Parity status: **pinned** -- ``oracle/make_golden.py`` executes the reference's own functions
+(imported from ``/root/reference`` with stub modules) on seeded inputs and
+stores their outputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this
+restatement against those vectors (bit-exact for the sort permutation, the projected pixel
+coordinates and the bilinear tap indices; <=1e-6 for floating-point stages).  The reference has no
+tests or golden vectors of its own.
+
+Every function cites the reference lines it follows.  Paths are relative to ``/root/reference``;
+``trt.py`` = ``run_S_eS_eN_alter_trt.py``, ``helpers.py`` = ``run_nerf_helpers.py``, ``iw.py`` =
+``inverse_warp.py``.
+
+Arithmetic notes that matter for bit-exact integers (all verified against torch 2.11 CPU):
+* ``torch.bmm`` of [B,3,4]x[B,4,N] on CPU (MKL) is a sequential FMA chain over k:
+  ``acc = m0*w0; acc = fma(m1,w1,acc); acc = fma(m2,w2,acc); acc = fma(m3,w3,acc)``
+  (0 mismatches on 18 M elements).  ``bmm_k4`` below restates that without calling bmm.
+* tensor / python-scalar is a true IEEE division on CPU.
+* ``grid_sample`` (bilinear, zeros, align_corners=True) un-normalises as ``(x+1)*((W-1)/2)``,
+  takes ``floor``, and weights taps with ``w = x - floor(x)``, ``e = 1 - w``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ORACLE_KIND = "port"          # a restatement ("port"), not the reference binary itself
+
+
+def _t(x, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.detach().to("cpu", dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+# ----------------------------------------------------------------------------- A.1 per-view prep
+def get_rays(H, W, K, c2w):
+    """helpers.py:2705-2714.  K is a numpy float64 3x3, c2w a float32 tensor [3,4]."""
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i = i.t()
+    j = j.t()
+    dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """helpers.py:2776-2793."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
+    o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
+    o2 = 1. + 2. * near / rays_o[..., 2]
+    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
+    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
+    d2 = -2. * near / rays_o[..., 2]
+    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+
+
+def pluecker(rays_o, rays_d):
+    """helpers.py:629-632 (Pluecker.forward): [normalize(d), o x normalize(d)]."""
+    d = F.normalize(rays_d, p=2.0, dim=-1)
+    m = torch.cross(rays_o, d, dim=-1)
+    return torch.cat([d, m], dim=-1)
+
+
+def query_points_linear(rays_o, rays_d, near, far, n):
+    """trt.py:546-562 compute_query_points_from_rays."""
+    depth_values = torch.linspace(near, far, n).to(rays_o).unsqueeze(0)
+    return rays_o[..., None, :] + rays_d[..., None, :] * depth_values[..., :, None], depth_values
+
+
+def embed(x, L):
+    """helpers.py:654, 666-671: [x, sin(x*2^0), cos(x*2^0), ..., sin(x*2^(L-1)), cos(x*2^(L-1))]."""
+    freq_bands = 2. ** torch.linspace(0., L - 1, steps=L)
+    out = [x]
+    for freq in freq_bands:
+        out.append(torch.sin(x * freq))
+        out.append(torch.cos(x * freq))
+    return torch.cat(out, -1)
+
+
+def prep_view(H, W, K, c2w, poses_ref, N_samples=8, N_point_ray_enc=48, num_neighbor=4,
+              near=0., far=1., or_near=1., or_far=10.):
+    """trt.py:245-302 (render_path body up to the timed loop), minus image replication.
+
+    ``K`` numpy float64 [3,3]; ``c2w`` [3,4]; ``poses_ref`` [n_ref,3,4] (``render_kwargs['poses']``).
+    Returns a dict of float32 tensors; ``project_mat`` is [num_neighbor,3,4] (un-replicated) and
+    ``ro_w`` / ``rd_w`` are the world-space ray origins / directions [N,3] that the reference lifts to
+    homogeneous ``ro1`` / ``rd1``.
+    """
+    c2w = _t(c2w)
+    poses_ref = _t(poses_ref)
+    rays_o, rays_d = get_rays(H, W, K, c2w)
+    viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    or_rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    or_rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    ones = torch.ones_like(or_rays_d[..., :1])
+    or_rays = torch.cat([or_rays_o, or_rays_d, or_near * ones, or_far * ones, viewdirs], -1)
+    sh = rays_d.shape
+    ro, rd = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    ro = torch.reshape(ro, [-1, 3]).float()
+    rd = torch.reshape(rd, [-1, 3]).float()
+    rays = torch.cat([ro, rd, near * ones, far * ones, viewdirs], -1)
+    pts, _ = query_points_linear(ro, rd, 0., 1., N_point_ray_enc)
+    mm_input = pluecker(pts, rd[:, None, :].expand(-1, N_point_ray_enc, -1)).view(-1, N_point_ray_enc * 6)
+    rel = torch.sum((c2w[None, :, 3] - poses_ref[:, :, 3]) ** 2, 1) ** (1 / 2)
+    _, idx = torch.sort(rel, dim=0)
+    ref_nos = idx[:num_neighbor]
+    ref_pose = poses_ref[ref_nos]
+    trans = torch.eye(3)
+    trans[1, 1] = -1
+    trans[2, 2] = -1
+    ref_K = torch.Tensor(np.asarray(K).copy())
+    pm = torch.bmm(trans[None].expand(ref_pose.shape[0], -1, -1), ref_pose)
+    pm = torch.bmm(ref_K[None].expand(ref_pose.shape[0], -1, -1), pm)
+    return dict(rays=rays.contiguous(), or_rays=or_rays.contiguous(), sh=tuple(sh), mm_input=mm_input.contiguous(),
+                ref_nos=ref_nos, project_mat=pm.contiguous(), ro_w=or_rays_o.contiguous(),
+                rd_w=or_rays_d.contiguous(), viewdirs=viewdirs.contiguous())
+
+
+# ----------------------------------------------------------------------------- A.2 / A.6 / A.8 MLPs
+def _lin(sd, name, x):
+    return F.linear(x, _t(sd[name + ".weight"]), _t(sd[name + ".bias"]))
+
+
+def sampler_raw(sd, x, depth=6):
+    """helpers.py:1490-1498: 6x(Linear, ELU) then fc_output -> raw [N, 3S+3]."""
+    h = x
+    for i in range(depth):
+        h = F.elu(_lin(sd, f"fc_backbone.{i}", h))
+    return _lin(sd, "fc_output", h)
+
+
+def sampler_forward(sd, x, S=8):
+    """helpers.py:1490-1507 MinMaxRaySamplerTRT_Net.forward -> (mm_rgb, add, mul, depth)."""
+    out = sampler_raw(sd, x)
+    return torch.sigmoid(out[:, 3 * S:]), out[:, S:2 * S], out[:, 2 * S:3 * S], torch.sigmoid(out[:, :S])
+
+
+def refine_forward(sd, x, S=8):
+    """helpers.py:1526-1540 MinMaxRayEpiSamplerTRT_Net.forward -> (refine_depth, refine_rgb, offsets)."""
+    out = sampler_raw(sd, x)
+    return torch.sigmoid(out[:, :S]), torch.sigmoid(out[:, 4 * S:]), torch.tanh(out[:, S:4 * S])
+
+
+def nerf_forward(sd, e, g, D=8):
+    """helpers.py:1331-1343 DoNeRFTRT.forward with inputLocations {0:(0,63), 7:(63,90)}:
+    ReLU after layers 0..6, the 27-d encoded view direction concatenated before layer 7."""
+    out = e
+    for i in range(D):
+        if i == D - 1:
+            out = torch.cat([out, g], -1)
+        out = _lin(sd, f"layers.{i}", out)
+        if i + 1 < D:
+            out = F.relu(out)
+    return out
+
+
+def run_network(sd, pts, viewdirs):
+    """trt.py:195-208: encode [N,S,3] points (L=10) and per-ray view dirs (L=4), run the NeRF MLP."""
+    flat = pts.reshape(-1, 3)
+    e = embed(flat, 10)
+    dirs = viewdirs[:, None].expand(pts.shape).reshape(-1, 3)
+    g = embed(dirs, 4)
+    return nerf_forward(sd, e, g).reshape(*pts.shape[:-1], 4)
+
+
+# ----------------------------------------------------------------------------- A.3 sort / lift
+def sort_lift(depth_raw, add, mul, near, far):
+    """trt.py:631-637.  near/far are [N,1].  Returns (depth_sorted, add, mul, perm int64, depth3d)."""
+    depth = depth_raw * (far - near) + near
+    depth, perm = torch.sort(depth, dim=-1, stable=True)
+    add = torch.gather(add, 1, perm)
+    mul = torch.gather(mul, 1, perm)
+    depth3d = 1 / (1 - depth - 1e-5)
+    return depth, add, mul, perm, depth3d
+
+
+# ----------------------------------------------------------------------------- A.4 project + gather
+def bmm_k4(M, w):
+    """torch.bmm([B,3,4],[B,4,N]) as MKL executes it: sequential fp32 FMA chain over k (see header).
+
+    The FMA is emulated in float64: the product of two fp32 is exact in fp64, the sum is rounded once
+    to fp64 and once more to fp32 (double rounding differs from a true fma with probability ~2^-29).
+    """
+    acc = M[:, :, 0:1] * w[:, 0:1, :]
+    for k in (1, 2, 3):
+        acc = (M[:, :, k:k + 1].double() * w[:, k:k + 1, :].double() + acc.double()).float()
+    return acc
+
+
+def project(project_mat, ro_w, rd_w, depth3d, Himg, Wimg):
+    """iw.py:597-608.  project_mat [NN,3,4]; ro_w, rd_w [N,3]; depth3d [N,S].
+
+    Batch index b = neighbour*S + sample (trt.py:296-302, 649-650).
+    Returns X_norm, Y_norm [NN*S, N] and the un-divided p2 [NN*S,3,N].
+    """
+    NN = project_mat.shape[0]
+    N, S = depth3d.shape
+    B = NN * S
+    ro1 = torch.cat([ro_w.t(), torch.ones(1, N)], 0)[None].expand(B, -1, -1)          # trt.py:256-262
+    rd1 = torch.cat([rd_w.t(), torch.zeros(1, N)], 0)[None].expand(B, -1, -1)
+    depths = depth3d[None, None].expand(NN, -1, -1, -1).permute(0, 3, 1, 2).reshape(B, 1, N)   # trt.py:649-650
+    w2c = project_mat.unsqueeze(1).expand(-1, S, -1, -1).contiguous().view(B, 3, 4)   # trt.py:300-301
+    w = ro1 + rd1 * depths
+    p2 = bmm_k4(w2c, w)
+    p_raw = p2.clone()
+    p2[:, :2, :] /= p2[:, 2:, :]
+    X = p2[:, 0]
+    Y = p2[:, 1]
+    X_norm = 2 * X / (Wimg - 1) - 1
+    Y_norm = 2 * Y / (Himg - 1) - 1
+    return X_norm, Y_norm, p_raw
+
+
+def grid_sample_bilinear_zeros(img, X_norm, Y_norm):
+    """F.grid_sample(img[B,C,H,W], grid, bilinear, zeros, align_corners=True) restated (iw.py:614).
+
+    img is [B,C,H,W]; X_norm/Y_norm [B,N].  Returns (out [B,C,N], ix, iy, x0 int64, y0 int64).
+    Taps outside the image (or non-finite coordinates) contribute 0 individually.
+    """
+    B, C, H, W = img.shape
+    ix = (X_norm + 1) * ((W - 1) / 2)
+    iy = (Y_norm + 1) * ((H - 1) / 2)
+    x0f = torch.floor(ix)
+    y0f = torch.floor(iy)
+    w = ix - x0f
+    e = 1 - w
+    n = iy - y0f
+    s = 1 - n
+    out = torch.zeros(B, C, ix.shape[1], dtype=img.dtype)
+    flat = img.reshape(B, C, H * W)
+    for dx, dy, wt in ((0, 0, s * e), (1, 0, s * w), (0, 1, n * e), (1, 1, n * w)):
+        xf = x0f + dx
+        yf = y0f + dy
+        ok = (xf >= 0) & (xf <= W - 1) & (yf >= 0) & (yf <= H - 1)
+        xi = torch.where(ok, xf, torch.zeros_like(xf)).long()
+        yi = torch.where(ok, yf, torch.zeros_like(yf)).long()
+        val = torch.gather(flat, 2, (yi * W + xi)[:, None, :].expand(-1, C, -1))
+        out = out + torch.where(ok, wt, torch.zeros_like(wt))[:, None, :] * val
+    big = 2.0 ** 30
+    x0 = torch.where(torch.isfinite(x0f), x0f.clamp(-big, big), torch.full_like(x0f, -big)).long()
+    y0 = torch.where(torch.isfinite(y0f), y0f.clamp(-big, big), torch.full_like(y0f, -big)).long()
+    return out, ix, iy, x0, y0
+
+
+def project_gather(images, project_mat, ro_w, rd_w, depth3d):
+    """A.4 end to end.  images [NN,H,W,3] float32 (``render_kwargs['images'][ref_nos]``).
+
+    Returns dict(epi [N, NN*S*3] with feature index (k*S+s)*3+ch  (trt.py:653-655),
+    warped [NN*S,3,N], ix, iy, x0, y0 [NN*S,N], p_raw).
+    """
+    images = _t(images)
+    NN, H, W, _ = images.shape
+    N, S = depth3d.shape
+    Xn, Yn, p_raw = project(project_mat, ro_w, rd_w, depth3d, H, W)
+    ref_rgb = images.permute(0, 3, 1, 2)
+    ref_rgb = ref_rgb.unsqueeze(1).expand(-1, S, -1, -1, -1).reshape(NN * S, 3, H, W)       # trt.py:296-298
+    warped, ix, iy, x0, y0 = grid_sample_bilinear_zeros(ref_rgb, Xn, Yn)
+    epi = warped.view(NN * S, 3, N).permute(2, 0, 1).reshape(N, 3 * S * NN)
+    return dict(epi=epi.contiguous(), warped=warped, ix=ix, iy=iy, x0=x0, y0=y0, p_raw=p_raw, Xn=Xn, Yn=Yn)
+
+
+# ----------------------------------------------------------------------------- A.5 / A.7
+def refine_input(rays_o, rays_d, depth, epi):
+    """trt.py:656-661: [pluecker(o + d*depth_s, d) for s] (6S) ++ epi (3*NN*S)."""
+    S = depth.shape[1]
+    epi_pts = rays_o[..., None, :] + rays_d[..., None, :] * depth[..., :, None]
+    pl = pluecker(epi_pts, rays_d[:, None, :].repeat(1, S, 1)).view(-1, S, 6).view(rays_o.shape[0], -1)
+    return torch.cat([pl, epi], dim=1)
+
+
+def interval_refine(rays_o, rays_d, depth, near, far, refine_depth, offsets):
+    """trt.py:671-681 -> (epi_z_vals [N,S], query_points [N,S,3])."""
+    N, S = depth.shape
+    offsets = offsets.view(N, S, 3)
+    mids = .5 * (depth[..., 1:] + depth[..., :-1])
+    upper = torch.cat([mids, 0.5 * (far + depth[..., -1:])], -1)
+    lower = torch.cat([0.5 * (near + depth[..., :1]), mids], -1)
+    z = lower + (upper - lower) * refine_depth
+    q = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+    q = q + (1e-2) * offsets
+    return z, q
+
+
+# ----------------------------------------------------------------------------- A.9 compositing
+def raw2outputs(raw, z_vals, rays_d, add, mul):
+    """trt.py:564-597 -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.ones(dists[..., :1].shape) * 1e10], -1)
+    dists = dists * torch.norm(rays_d[..., None, :], dim=-1)
+    rgb = torch.sigmoid(raw[..., :3])
+    alpha = 1. - torch.exp(-F.relu(raw[..., 3] + add) * dists)
+    alpha = alpha * torch.relu(mul)
+    weights = alpha * torch.cumprod(torch.cat([torch.ones((alpha.shape[0], 1)), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    rgb_map = torch.sum(weights[..., None] * rgb, -2)
+    depth_map = torch.sum(weights * z_vals, -1)
+    disp_map = 1. / torch.max(1e-10 * torch.ones_like(depth_map), depth_map / torch.sum(weights, -1))
+    acc_map = torch.sum(weights, -1)
+    return rgb_map, disp_map, acc_map, weights, depth_map
+
+
+# ----------------------------------------------------------------------------- the whole path
+def render_rays(weights, rays, mm_input, images, project_mat, ro_w, rd_w, S=8, keep=True):
+    """trt.py:599-696 with every intermediate exposed.
+
+    ``weights``: dict of the three state_dicts (reference checkpoint key names, trt.py:478-481).
+    ``rays`` [N,11] = (o_ndc, d_ndc, near, far, viewdir).  ``images`` [NN,H,W,3]; ``project_mat`` [NN,3,4].
+    """
+    rays = _t(rays)
+    mm_input, project_mat, ro_w, rd_w = _t(mm_input), _t(project_mat), _t(ro_w), _t(rd_w)
+    o, d = rays[:, 0:3], rays[:, 3:6]
+    viewdirs = rays[:, -3:]
+    bounds = torch.reshape(rays[..., 6:8], [-1, 1, 2])
+    near, far = bounds[..., 0], bounds[..., 1]
+    r = {}
+    _, add0, mul0, depth_raw = sampler_forward(weights["mmr_network_fn_state_dict"], mm_input, S)
+    depth, add, mul, perm, depth3d = sort_lift(depth_raw, add0, mul0, near, far)
+    pg = project_gather(images, project_mat, ro_w, rd_w, depth3d)
+    rin = refine_input(o, d, depth, pg["epi"])
+    refine_depth, _, offsets = refine_forward(weights["refine_net_state_dict"], rin, S)
+    z, q = interval_refine(o, d, depth, near, far, refine_depth, offsets)
+    raw = run_network(weights["network_fine_state_dict"], q, viewdirs)
+    rgb, disp, acc, w, depth_map = raw2outputs(raw, z, d, add, mul)
+    r.update(rgb_map=rgb, depth_map=depth_map)
+    if keep:
+        r.update(depth_raw=depth_raw, add_raw=add0, mul_raw=mul0, depth=depth, add=add, mul=mul, perm=perm,
+                 depth3d=depth3d, epi=pg["epi"], ix=pg["ix"], iy=pg["iy"], x0=pg["x0"], y0=pg["y0"],
+                 refine_input=rin, refine_depth=refine_depth, offsets=offsets, z=z, q=q, raw=raw,
+                 weights=w, acc_map=acc, disp_map=disp)
+    return r
+
+
+def render_view(weights, scene, c2w, S=8, keep=False):
+    """One full view of a ``pronerf_b200.synth.Scene``: prep (trt.py:245-302) + render (trt.py:211-221)."""
+    pv = prep_view(scene.H, scene.W, scene.K, c2w, scene.poses_ref, N_samples=S)
+    images = scene.images_ref[pv["ref_nos"].numpy()]
+    r = render_rays(weights, pv["rays"], pv["mm_input"], images, pv["project_mat"], pv["ro_w"], pv["rd_w"], S, keep)
+    r["rgb_map"] = r["rgb_map"].reshape(scene.H, scene.W, 3)
+    r["depth_map"] = r["depth_map"].reshape(scene.H, scene.W)
+    return r, pv

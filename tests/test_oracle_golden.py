@@ -1,0 +1,125 @@
+"""Pins the CPU oracle (oracle/pronerf_oracle.py) against vectors produced by the reference itself.
+
+The golden files were written by oracle/make_golden.py, which executes the unmodified reference
+functions from /root/reference.  Integer-valued stages (sort permutation, bilinear tap indices --
+checked through exact equality of the gathered colours' tap coordinates) must match exactly;
+floating-point stages to <=1e-6 abs (same torch CPU ops in the same order, so in practice 0).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pronerf_oracle as O
+from pronerf_b200 import synth
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+@pytest.mark.parametrize("which", ["random", "calibrated"])
+def test_stagewise_against_reference(which, golden_small_random, golden_small_calibrated):
+    g = golden_small_random if which == "random" else golden_small_calibrated
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    sd = synth.make_weights(seed=0, calibrated=bool(g["calibrated"]))
+    assert synth.weights_checksum(sd) == float(g["weights_checksum"])
+    assert float(scene.images_ref.astype(np.float64).sum()) == float(g["images_checksum"])
+    np.testing.assert_array_equal(scene.poses_ref, g["poses_ref"])
+
+    # A.1 prep
+    pv = O.prep_view(H, W, scene.K, g["c2w"], scene.poses_ref)
+    np.testing.assert_array_equal(pv["rays"].numpy(), g["rays"])
+    np.testing.assert_array_equal(pv["or_rays"].numpy(), g["or_rays"])
+    np.testing.assert_array_equal(pv["ref_nos"].numpy(), g["ref_nos"])
+    np.testing.assert_array_equal(pv["project_mat"].numpy(), g["project_mat"])
+    np.testing.assert_array_equal(pv["mm_input"].numpy()[::16], g["mm_input_rows16"])
+
+    images = scene.images_ref[g["ref_nos"]]
+    r = O.render_rays(sd, pv["rays"], pv["mm_input"], images, pv["project_mat"], pv["ro_w"], pv["rd_w"])
+
+    # A.2 sampler, A.3 sort (bit-exact permutation)
+    np.testing.assert_allclose(r["depth_raw"].numpy(), g["sampler_depth"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(r["add_raw"].numpy(), g["sampler_add"], atol=1e-6, rtol=0)
+    np.testing.assert_array_equal(r["perm"].numpy(), g["sort_perm"])
+    np.testing.assert_allclose(r["add"].numpy(), g["comp_add"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(r["mul"].numpy(), g["comp_mul"], atol=1e-6, rtol=0)
+    # depth3d as fed to the warp, batch index b = k*S + s
+    np.testing.assert_array_equal(r["depth3d"].t().numpy(), g["warp_depths"][:8, 0, :])
+    # A.4/A.5 gathered colours + Pluecker features
+    np.testing.assert_allclose(r["refine_input"].numpy(), g["refine_input"], atol=1e-6, rtol=0)
+    # A.6 refine net, A.7 interval refinement
+    np.testing.assert_allclose(r["refine_depth"].numpy(), g["refine_depth"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(r["offsets"].numpy(), g["refine_offsets"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(r["z"].numpy(), g["comp_z"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(r["q"].numpy(), g["query_points"], atol=1e-6, rtol=0)
+    # A.8 encode + NeRF MLP
+    np.testing.assert_allclose(r["raw"].numpy(), g["nerf_raw"], atol=2e-4, rtol=1e-4)   # 8 chained GEMMs amplify 1e-7 input noise
+    # A.9 compositing
+    np.testing.assert_allclose(r["weights"].numpy(), g["comp_weights"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(r["rgb_map"].numpy(), g["comp_rgb"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(r["depth_map"].numpy(), g["comp_depth"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(r["rgb_map"].numpy().reshape(H, W, 3), g["rgb"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(r["depth_map"].numpy().reshape(H, W), g["depth"], atol=1e-5, rtol=0)
+    if which == "calibrated":       # the calibrated set must actually exercise the range
+        assert g["rgb"].max() - g["rgb"].min() > 0.5
+        assert g["comp_acc"].max() > 0.9
+
+
+def test_warp_known_answer(golden_kat):
+    """inverse_warp_rod1_rt2_coords_trt on general inputs (per-batch rays, out-of-bounds, z<0)."""
+    g = golden_kat
+    img, depth, ro1, rd1, w2c = (T(g[k]) for k in ("w_img", "w_depth", "w_ro1", "w_rd1", "w_w2c"))
+    B, C, H, W = img.shape
+    w = ro1 + rd1 * depth.view(B, 1, -1)
+    p2 = O.bmm_k4(w2c, w)
+    assert torch.equal(p2, torch.bmm(w2c, w))          # the FMA-chain restatement of MKL's bmm
+    p2[:, :2, :] /= p2[:, 2:, :]
+    Xn = 2 * p2[:, 0] / (W - 1) - 1
+    Yn = 2 * p2[:, 1] / (H - 1) - 1
+    out, ix, iy, x0, y0 = O.grid_sample_bilinear_zeros(img, Xn, Yn)
+    ref = g["w_out"][:, :, 0, :]
+    np.testing.assert_allclose(out.numpy(), ref, atol=2e-6, rtol=0)
+    inb = ((x0 >= 0) & (x0 < W - 1) & (y0 >= 0) & (y0 < H - 1)).float().mean().item()
+    assert 0.05 < inb < 0.95                            # both in- and out-of-bounds taps are covered
+
+
+def test_helpers_known_answer(golden_kat):
+    g = golden_kat
+    x = T(g["embed_x"])
+    np.testing.assert_array_equal(O.embed(x, 10).numpy(), g["embed10"])
+    np.testing.assert_array_equal(O.embed(x, 4).numpy(), g["embed4"])
+    np.testing.assert_array_equal(O.pluecker(T(g["pl_o"]), T(g["pl_d"])).numpy(), g["pl_out"])
+    H, W = [int(v) for v in g["gr_hw"]]
+    ro, rd = O.get_rays(H, W, g["gr_K"], T(g["gr_c2w"]))
+    np.testing.assert_array_equal(ro.numpy(), g["gr_o"])
+    np.testing.assert_array_equal(rd.numpy(), g["gr_d"])
+    no, nd = O.ndc_rays(H, W, g["gr_K"][0][0], 1., ro, rd)
+    np.testing.assert_array_equal(no.numpy(), g["ndc_o"])
+    np.testing.assert_array_equal(nd.numpy(), g["ndc_d"])
+
+
+def test_composite_known_answer(golden_kat):
+    g = golden_kat
+    rgb, disp, acc, w, depth = O.raw2outputs(T(g["c_raw"]), T(g["c_z"]), T(g["c_d"]), T(g["c_add"]), T(g["c_mul"]))
+    np.testing.assert_allclose(rgb.numpy(), g["c_rgb"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(w.numpy(), g["c_w"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(depth.numpy(), g["c_depth"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(acc.numpy(), g["c_acc"], atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(disp.numpy(), g["c_disp"], rtol=1e-5)
+
+
+def test_fern504_subset(golden_fern):
+    """BASELINE-resolution view: oracle on every 97th ray vs the reference's full-frame render."""
+    g = golden_fern
+    scene = synth.make_scene(factor=8)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    assert synth.weights_checksum(sd) == float(g["weights_checksum"])
+    assert float(scene.images_ref.astype(np.float64).sum()) == float(g["images_checksum"])
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    idx = torch.from_numpy(g["idx"])
+    images = scene.images_ref[pv["ref_nos"].numpy()]
+    r = O.render_rays(sd, pv["rays"][idx], pv["mm_input"][idx], images, pv["project_mat"],
+                      pv["ro_w"][idx], pv["rd_w"][idx], keep=False)
+    np.testing.assert_allclose(r["rgb_map"].numpy(), g["rgb_subset"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(r["depth_map"].numpy(), g["depth_subset"], atol=1e-5, rtol=0)
