@@ -1,0 +1,193 @@
+/*
+ * pronerf_b200 -- C ABI of the B200-native (sm_100a) ProNeRF per-ray render hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every pointer named
+ * "device" is a CUDA device pointer (e.g. torch.Tensor.data_ptr()); every launch is asynchronous
+ * on the given stream (pass torch.cuda.current_stream().cuda_stream, or 0 for the legacy stream).
+ * All tensors are dense row-major fp32 unless stated.  Functions return PN_OK (0) or a negative
+ * PN_E* code; pn_last_error() gives the message of the calling thread's last failure.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the upstream
+ * repository KAIST-VICLab/pronerf; "trt.py" = run_S_eS_eN_alter_trt.py, "helpers.py" =
+ * run_nerf_helpers.py, "iw.py" = inverse_warp.py, "engines" = trt_infer_v2.py -- the reference's
+ * own backend plug-in seam, whose MMEngine/RefineEngine/NeRFEngine objects own persistent device
+ * buffers exactly like pn_ctx_t does).
+ */
+#ifndef PRONERF_B200_H
+#define PRONERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_VERSION 100            /* 0.1.0 */
+
+#define PN_OK            0
+#define PN_EINVAL       -1       /* bad argument (shape, null pointer, unsupported size) */
+#define PN_ECUDA        -2       /* a CUDA runtime call or launch failed */
+#define PN_ENODEVICE    -3       /* no sm_100 device */
+#define PN_ESTATE       -4       /* context not ready (weights not loaded, ...) */
+#define PN_ENOMEM       -5
+
+typedef void* pn_stream_t;        /* cudaStream_t */
+typedef struct pn_ctx pn_ctx_t;   /* owns packed weights + scratch, like the reference's engine objects */
+
+/* which network a weight set belongs to */
+#define PN_NET_SAMPLER  0         /* MinMaxRaySamplerTRT_Net     helpers.py:1473-1507 */
+#define PN_NET_REFINE   1         /* MinMaxRayEpiSamplerTRT_Net  helpers.py:1509-1540 */
+#define PN_NET_NERF     2         /* DoNeRFTRT                   helpers.py:1186-1343 */
+
+/* arithmetic tier of the three MLPs */
+#define PN_PREC_FP32    0         /* fp32 SIMT FMA: the <=1e-3 max-abs parity tier            */
+#define PN_PREC_BF16    1         /* bf16 operands, fp32 accumulate in TMEM on tcgen05 tensor cores */
+
+int         pn_version(void);
+const char* pn_last_error(void);
+/* PN_OK iff `device` exists and is compute capability 10.x (the only target; no fallback). */
+int         pn_device_check(int device);
+/* 1 when the PN_PREC_BF16 (tcgen05) tier of the MLPs is compiled into this build, else 0. */
+int         pn_has_bf16_tier(void);
+
+/* ---- context: packed weights + scratch ------------------------------------------------------- */
+int  pn_ctx_create(int device, pn_ctx_t** out);
+void pn_ctx_destroy(pn_ctx_t* ctx);
+
+/* Load one network from nn.Linear-layout device tensors: W[l] is [out_dims[l], in_dims[l]] row-major,
+ * b[l] is [out_dims[l]].  Layer order = fc_backbone.0..5, fc_output (sampler / refine) or
+ * layers.0..7 (DoNeRFTRT); state_dict keys per trt.py:478-481.  Hidden width must be 256.
+ * Packs both the fp32 (k-major) and the bf16 (UMMA canonical, 128B-swizzled) images of the weights. */
+int pn_ctx_load_net(pn_ctx_t* ctx, int net, int n_layers, const int* in_dims, const int* out_dims,
+                    const float* const* W_device, const float* const* b_device, pn_stream_t stream);
+
+/* Stage timing for the roofline report: when enabled, pn_render_rays brackets each of its PN_N_STAGES kernels
+ * with CUDA events on the launch stream (a ring of PN_PROFILE_RING frames; ~1 us per event).
+ * pn_ctx_profile_read synchronises on the last recorded event, writes up to max_frames rows of
+ * PN_N_STAGES per-kernel durations in ms (oldest first), returns the number of rows and clears the ring.
+ * Stage order: sampler MLP, sort+lift, refine-Pluecker, project+gather, refine MLP, interval refine,
+ * encode+NeRF MLP, composite.  (The reference times whole render() calls only, trt.py:327-332.) */
+#define PN_N_STAGES      8
+#define PN_PROFILE_RING  256
+int pn_ctx_profile(pn_ctx_t* ctx, int enable);
+int pn_ctx_profile_read(pn_ctx_t* ctx, float* ms, int max_frames);
+
+/* ---- per-stage entry points (each mirrors one reference call) --------------------------------- */
+
+/* MinMaxRaySamplerTRT_Net.forward (helpers.py:1490-1507) / MMEngine.run (engines:214-229).
+ * x [N, in_dim] -> out [N, 3S+3] with the heads already applied:
+ * [0,S) sigmoid = depth_values, [S,2S) mm_density_add, [2S,3S) mm_density_mul, [3S,3S+3) sigmoid = mm_rgb. */
+int pn_sampler_forward(pn_ctx_t* ctx, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream);
+
+/* MinMaxRayEpiSamplerTRT_Net.forward (helpers.py:1526-1540) / RefineEngine.run (engines:303-311).
+ * x [N, 6S+3*NN*S] -> out [N, 4S+3]: [0,S) sigmoid = refine_depth, [S,4S) tanh = points_offset,
+ * [4S,4S+3) sigmoid = refine_rgb. */
+int pn_refine_forward(pn_ctx_t* ctx, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream);
+
+/* DoNeRFTRT.forward(input_pts [M,63], input_views [M,27]) -> raw [M,4]  (helpers.py:1331-1343) /
+ * NeRFEngine.run (engines:385-394). */
+int pn_nerf_forward(pn_ctx_t* ctx, const float* embedded, const float* embedded_dirs, int64_t M, float* raw,
+                    int precision, pn_stream_t stream);
+
+/* run_network (trt.py:195-208) with both positional encodings fused into the first / last layer:
+ * pts [N,S,3], viewdirs [N,3] (row stride viewdir_stride floats: 3 for a dense tensor, 11 for
+ * ray_batch[:, 8:11]) -> raw [N,S,4].  The encodings never touch HBM. */
+int pn_run_network(pn_ctx_t* ctx, const float* pts, const float* viewdirs, int viewdir_stride, int64_t N, int S,
+                   float* raw, int precision, pn_stream_t stream);
+
+/* Embedder.embed via get_embedder(multires) (helpers.py:654-692): x [M,3] -> [M, 3+6L]. */
+int pn_embed(const float* x, int64_t M, int L, float* out, pn_stream_t stream);
+
+/* Pluecker.forward (helpers.py:629-632): o,d [M,3] -> [M,6] = [normalize(d), o x normalize(d)]. */
+int pn_pluecker(const float* o, const float* d, int64_t M, float* out, pn_stream_t stream);
+
+/* per-view sampler input (trt.py:274-278): rays [N,>=6] (o_ndc, d_ndc, ...) with row stride `ray_stride`
+ * -> mm_input [N, 6P], P points linearly spaced on t in [0,1]. */
+int pn_sampler_input(const float* rays, int ray_stride, int64_t N, int P, float* mm_input, pn_stream_t stream);
+
+/* trt.py:631-637: scale by the per-ray (near, far) at rays[:,6:8], stable ascending sort of the S depths,
+ * gather add/mul with the permutation, lift depth3d = 1/(1 - depth - 1e-5).
+ * heads [N, >=3S] = sampler output (depth at [0,S), add at [S,2S), mul at [2S,3S)), row stride head_stride.
+ * Outputs [N,S] each; perm is int32 (the reference's int64 permutation, narrowed). Any output may be NULL. */
+int pn_sort_lift(const float* heads, int head_stride, const float* rays, int ray_stride, int64_t N, int S,
+                 float* depth, float* add, float* mul, int32_t* perm, float* depth3d, pn_stream_t stream);
+
+/* inverse_warp_rod1_rt2_coords_trt(img, depth, ro1, rd1, w2c, padding_mode='zeros') (iw.py:584-619).
+ * img [B,C,H,W]; depth [B,N]; ro1, rd1 [*,4,N] with batch stride ro_bstride elements (0 for the
+ * reference's expanded views); w2c [B,3,4] -> out [B,C,N].
+ * Optional x0y0 [B,N,2] int32 receives floor(ix), floor(iy) (the integers that must be bit-exact;
+ * clamped to +-2^30, non-finite -> -2^30). */
+int pn_warp(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,
+            int64_t ro_bstride, const float* w2c, int64_t N, float* out, int32_t* x0y0, pn_stream_t stream);
+
+/* Pack NN reference views [NN,H,W,3] (render_kwargs['images'][ref_nos], trt.py:286) into 16-byte RGBA fp32
+ * texels [NN,H,W,4] so that one bilinear tap is one 128-bit load. */
+int pn_pack_images(const float* images_hwc, int NN, int H, int W, float* texels, pn_stream_t stream);
+
+/* trt.py:649-655 fused: lift + project every (neighbour k, sample s) of every ray and gather bilinearly.
+ * texels from pn_pack_images; tex_index_host[k] (HOST ints, NULL = identity) names the texel image neighbour k
+ * reads -- the per-view ref_nos ordering (trt.py:281-286) without moving pixels; project_mat [NN,3,4] (K * diag(1,-1,-1) * pose, trt.py:287-294);
+ * ro_w, rd_w [N,3] world-space ray origin / direction with row stride ray_stride floats (3 for dense
+ * tensors, 11 for or_ray_batch[:, 0:3] / [:, 3:6]); depth3d [N,S].
+ * epi [N, epi_stride] gets feature (k*S+s)*3+ch at column epi_col0 + ... (epi_stride=3*NN*S, epi_col0=0 for
+ * the reference's epi_features; epi_stride=6S+3*NN*S, epi_col0=6S writes straight into refine_input).
+ * Optional x0y0 [NN*S, N, 2] int32 as in pn_warp. */
+int pn_project_gather(const float* texels, const int* tex_index_host, int NN, int H, int W, const float* project_mat,
+                      const float* ro_w, const float* rd_w, int ray_stride, const float* depth3d, int64_t N, int S,
+                      float* epi, int epi_stride, int epi_col0, int32_t* x0y0, pn_stream_t stream);
+
+/* trt.py:656-658: per-sample Pluecker features of (o + d*depth_s, d) into out[:, 0:6S] (row stride out_stride). */
+int pn_refine_pluecker(const float* rays, int ray_stride, const float* depth, int64_t N, int S, float* out,
+                       int out_stride, pn_stream_t stream);
+
+/* trt.py:671-681: interval refinement + 1e-2 * offsets.  refine_out [N, >=4S] (refine_depth at [0,S),
+ * offsets at [S,4S), row stride refine_stride) -> z [N,S], query [N,S,3]. */
+int pn_interval_refine(const float* rays, int ray_stride, const float* depth, const float* refine_out,
+                       int refine_stride, int64_t N, int S, float* z, float* query, pn_stream_t stream);
+
+/* raw2outputs (trt.py:564-597): raw [N,S,4], z [N,S], rays_d = rays[:,3:6] (row stride ray_stride; pass a
+ * [N,3] tensor with ray_d_col=0, ray_stride=3 for the stand-alone function), add/mul [N,S]
+ * -> rgb [N,3], depth [N]; optional disp [N], acc [N], weights [N,S] (NULL to skip). */
+int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col,
+                 const float* add, const float* mul, int64_t N, int S, float* rgb, float* depth, float* disp,
+                 float* acc, float* weights, pn_stream_t stream);
+
+/* ---- per-view prep (trt.py:245-278; helpers.py:2705-2714, 2776-2793) ---------------------------- */
+/* get_rays + viewdir normalise + ndc_rays for one H x W view.  c2w [3,4] row-major HOST floats,
+ * K: fx, fy, cx, cy as doubles.  rays [N,11] = (o_ndc, d_ndc, near, far, viewdir); or_rays [N,11] =
+ * (o_w, d_w, or_near, or_far, viewdir).  row0/nrows select a horizontal band (tile sharding); N = nrows*W. */
+int pn_raygen(int H, int W, double fx, double fy, double cx, double cy, const float* c2w_host, float near_,
+              float far_, float or_near, float or_far, int row0, int nrows, float* rays, float* or_rays,
+              pn_stream_t stream);
+
+/* ---- the whole path --------------------------------------------------------------------------- */
+typedef struct pn_frame {
+  const float* rays;          /* device [N,11]  NDC ray batch (trt.py:269-271)                         */
+  const float* or_rays;       /* device [N,11]  world-space twin (trt.py:250-254); cols 0..5 are used   */
+  const float* mm_input;      /* device [N,6P] or NULL: NULL = generate from rays (same arithmetic)     */
+  const float* texels;        /* device [n_img,H,W,4] from pn_pack_images                               */
+  int tex_index[8];           /* neighbour k reads texel image tex_index[k] (ref_nos order, trt.py:281-286) */
+  const float* project_mat;   /* device [NN,3,4]                                                        */
+  int64_t N;
+  int S, NN, P, H, W;
+  int precision;              /* PN_PREC_*                                                              */
+  float* rgb;                 /* device [N,3]  out                                                      */
+  float* depth;               /* device [N]    out                                                      */
+} pn_frame_t;
+
+/* render_rays (trt.py:599-696): sampler -> sort/lift -> project+gather -> refine -> interval refinement
+ * -> encode + NeRF MLP -> composite, all on `stream`, scratch owned by ctx (grown on demand). */
+int pn_render_rays(pn_ctx_t* ctx, const pn_frame_t* frame, pn_stream_t stream);
+
+/* Same, HOST-buffer flavour (the end-to-end plug-in call): c2w_host [3,4] floats; uploads the pose,
+ * generates rays on the device, renders rows [row0,row0+nrows) and copies rgb [nrows*W,3] / depth [nrows*W]
+ * back into the (ideally pinned) host buffers; synchronises the stream before returning. */
+int pn_render_view_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy,
+                        const float* c2w_host, const float* texels, const int* tex_index_host,
+                        const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
+                        float* rgb_host, float* depth_host, pn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRONERF_B200_H */

@@ -1,0 +1,398 @@
+// C ABI glue: error state, the context (packed weights + scratch), and the composed render path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace pn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return PN_ECUDA;
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+struct pn_ctx {
+  int device = 0;
+  NetF32 f32[3];
+  NetTC tc[3];
+  // scratch for pn_render_rays, grown on demand (never shrunk)
+  float* scratch = nullptr;
+  size_t scratch_floats = 0;
+  // per-view buffers for pn_render_view_host
+  float* view_buf = nullptr;
+  size_t view_floats = 0;
+  float* pm_dev = nullptr;
+  // stage timing ring (pn_ctx_profile)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;      // PN_PROFILE_RING * (PN_N_STAGES + 1), created lazily
+  int prof_head = 0, prof_count = 0;
+};
+
+static int ensure(float** buf, size_t* have, size_t want) {
+  if (*have >= want) return PN_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc((void**)buf, want * sizeof(float));
+  if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(float), cudaGetErrorString(e)); return PN_ENOMEM; }
+  *have = want;
+  return PN_OK;
+}
+
+static void free_net(NetF32& n) {
+  if (n.trunk) cudaFree(n.trunk);
+  if (n.wout) cudaFree(n.wout);
+  if (n.bias) cudaFree(n.bias);
+  n = NetF32();
+}
+
+extern "C" {
+
+int pn_version(void) { return PN_VERSION; }
+const char* pn_last_error(void) { return g_err; }
+int pn_has_bf16_tier(void) { return tc_available() ? 1 : 0; }
+
+int pn_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return PN_ENODEVICE; }
+  if (device < 0 || device >= count) { set_error("device %d out of range (%d present)", device, count); return PN_ENODEVICE; }
+  cudaDeviceProp prop;
+  PN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only and has no fallback", device, prop.major, prop.minor);
+    return PN_ENODEVICE;
+  }
+  return PN_OK;
+}
+
+int pn_ctx_create(int device, pn_ctx_t** out) {
+  PN_REQUIRE(out, "pn_ctx_create: out is NULL");
+  int rc = pn_device_check(device);
+  if (rc != PN_OK) return rc;
+  PN_CUDA_OK(cudaSetDevice(device));
+  pn_ctx* c = new pn_ctx();
+  c->device = device;
+  cudaError_t e = cudaMalloc((void**)&c->pm_dev, 8 * 12 * sizeof(float));
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc(pm_dev)"); }
+  *out = c;
+  return PN_OK;
+}
+
+void pn_ctx_destroy(pn_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 3; ++i) { free_net(c->f32[i]); tc_free_net(c->tc[i]); }
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->view_buf) cudaFree(c->view_buf);
+  if (c->pm_dev) cudaFree(c->pm_dev);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  delete c;
+}
+
+int pn_ctx_profile(pn_ctx_t* c, int enable) {
+  PN_REQUIRE(c, "pn_ctx_profile: ctx is NULL");
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  if (enable && c->ev.empty()) {
+    c->ev.resize((size_t)PN_PROFILE_RING * (PN_N_STAGES + 1));
+    for (auto& e : c->ev) PN_CUDA_OK(cudaEventCreate(&e));
+  }
+  c->profile = enable != 0;
+  c->prof_head = 0;
+  c->prof_count = 0;
+  return PN_OK;
+}
+
+int pn_ctx_profile_read(pn_ctx_t* c, float* ms, int max_frames) {
+  if (!c || !ms) { set_error("pn_ctx_profile_read: null pointer"); return PN_EINVAL; }
+  if (c->prof_count == 0) return 0;
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  int n = c->prof_count < max_frames ? c->prof_count : max_frames;
+  int first = (c->prof_head - c->prof_count + 2 * PN_PROFILE_RING) % PN_PROFILE_RING;
+  int last = (c->prof_head - 1 + PN_PROFILE_RING) % PN_PROFILE_RING;
+  PN_CUDA_OK(cudaEventSynchronize(c->ev[(size_t)last * (PN_N_STAGES + 1) + PN_N_STAGES]));
+  for (int i = 0; i < n; ++i) {
+    int slot = (first + i) % PN_PROFILE_RING;
+    cudaEvent_t* e = &c->ev[(size_t)slot * (PN_N_STAGES + 1)];
+    for (int k = 0; k < PN_N_STAGES; ++k) PN_CUDA_OK(cudaEventElapsedTime(&ms[i * PN_N_STAGES + k], e[k], e[k + 1]));
+  }
+  c->prof_head = 0;
+  c->prof_count = 0;
+  return n;
+}
+
+int pn_ctx_load_net(pn_ctx_t* c, int net, int n_layers, const int* in_dims, const int* out_dims,
+                    const float* const* W, const float* const* b, pn_stream_t stream) {
+  PN_REQUIRE(c && in_dims && out_dims && W && b, "pn_ctx_load_net: null pointer");
+  PN_REQUIRE(net >= 0 && net < 3, "pn_ctx_load_net: unknown net id %d", net);
+  PN_REQUIRE(n_layers >= 2 && n_layers <= kMaxLayers, "pn_ctx_load_net: n_layers=%d unsupported (2..%d)", n_layers, kMaxLayers);
+  for (int l = 0; l < n_layers - 1; ++l) {
+    PN_REQUIRE(out_dims[l] == kHidden, "pn_ctx_load_net: layer %d has width %d; only 256-wide trunks are built", l, out_dims[l]);
+    PN_REQUIRE(l == 0 || in_dims[l] == kHidden, "pn_ctx_load_net: layer %d has %d inputs; skip connections inside the trunk are not built", l, in_dims[l]);
+  }
+  PN_REQUIRE(in_dims[0] >= 1 && in_dims[0] <= 288, "pn_ctx_load_net: first layer has %d inputs (max 288)", in_dims[0]);
+  const int last = n_layers - 1;
+  PN_REQUIRE(out_dims[last] >= 1 && out_dims[last] <= kOutPad, "pn_ctx_load_net: output width %d unsupported (1..%d)", out_dims[last], kOutPad);
+  PN_REQUIRE(in_dims[last] >= kHidden && in_dims[last] <= 288, "pn_ctx_load_net: output layer has %d inputs (256..288)", in_dims[last]);
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = as_stream(stream);
+  NetF32& n = c->f32[net];
+  free_net(n);
+  n.n_layers = n_layers;
+  int rows = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    n.in_dim[l] = in_dims[l];
+    n.out_dim[l] = out_dims[l];
+    if (l < last) {
+      n.k_pad[l] = (in_dims[l] + 15) / 16 * 16;
+      n.k_off[l] = rows;
+      rows += n.k_pad[l];
+    } else {
+      n.k_pad[l] = (in_dims[l] + 3) / 4 * 4;
+    }
+  }
+  n.trunk_rows = rows;
+  PN_CUDA_OK(cudaMalloc((void**)&n.trunk, (size_t)rows * kHidden * sizeof(float)));
+  PN_CUDA_OK(cudaMalloc((void**)&n.wout, (size_t)n.k_pad[last] * kOutPad * sizeof(float)));
+  PN_CUDA_OK(cudaMalloc((void**)&n.bias, (size_t)n_layers * kHidden * sizeof(float)));
+  for (int l = 0; l < n_layers; ++l) {
+    PN_REQUIRE(W[l] && b[l], "pn_ctx_load_net: layer %d weight/bias pointer is NULL", l);
+    int rc;
+    if (l < last)
+      rc = pack_layer_f32(W[l], b[l], out_dims[l], in_dims[l], n.k_pad[l], kHidden, n.trunk + (size_t)n.k_off[l] * kHidden,
+                          n.bias + (size_t)l * kHidden, kHidden, st);
+    else
+      rc = pack_layer_f32(W[l], b[l], out_dims[l], in_dims[l], n.k_pad[l], kOutPad, n.wout, n.bias + (size_t)l * kHidden, kHidden, st);
+    if (rc != PN_OK) return rc;
+  }
+  n.loaded = true;
+  int rc = tc_load_net(c->tc[net], net, n_layers, in_dims, out_dims, W, b, st);
+  if (rc != PN_OK) return rc;
+  return PN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MLP entry points
+static void heads_sampler(MlpLaunch& L, int S) {
+  L.head_lo[0] = 0; L.head_lo[1] = S; L.head_lo[2] = 3 * S; L.head_lo[3] = 3 * S + 3;
+  L.head_act[0] = HEAD_SIGMOID; L.head_act[1] = HEAD_NONE; L.head_act[2] = HEAD_SIGMOID;
+}
+static void heads_refine(MlpLaunch& L, int S) {
+  L.head_lo[0] = 0; L.head_lo[1] = S; L.head_lo[2] = 4 * S; L.head_lo[3] = 4 * S + 3;
+  L.head_act[0] = HEAD_SIGMOID; L.head_act[1] = HEAD_TANH; L.head_act[2] = HEAD_SIGMOID;
+}
+static void heads_none(MlpLaunch& L) {
+  for (int i = 0; i < 4; ++i) L.head_lo[i] = 0;
+  for (int i = 0; i < 3; ++i) L.head_act[i] = HEAD_NONE;
+}
+
+static int run_mlp(pn_ctx_t* c, int net, MlpLaunch& L, int precision, cudaStream_t st) {
+  L.net = &c->f32[net];
+  if (!c->f32[net].loaded) { set_error("network %d not loaded (pn_ctx_load_net)", net); return PN_ESTATE; }
+  if (precision == PN_PREC_FP32) return launch_mlp_f32(L, st);
+  if (precision == PN_PREC_BF16) return tc_launch_mlp(c->tc[net], L, st);
+  set_error("unknown precision %d", precision);
+  return PN_EINVAL;
+}
+
+int pn_sampler_forward(pn_ctx_t* c, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && x && out && N >= 0 && S >= 1, "pn_sampler_forward: bad arguments");
+  const NetF32& n = c->f32[PN_NET_SAMPLER];
+  PN_REQUIRE(!n.loaded || n.out_dim[n.n_layers - 1] == 3 * S + 3, "pn_sampler_forward: net output width %d != 3S+3 (S=%d)",
+             n.out_dim[n.n_layers - 1], S);
+  MlpLaunch L{};
+  L.act = 1; L.input_mode = IN_LOAD; L.in0 = x; L.in1 = nullptr; L.in_stride = n.in_dim[0]; L.S = S; L.P = 0; L.M = N; L.out = out;
+  heads_sampler(L, S);
+  return run_mlp(c, PN_NET_SAMPLER, L, precision, as_stream(stream));
+}
+
+int pn_refine_forward(pn_ctx_t* c, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && x && out && N >= 0 && S >= 1, "pn_refine_forward: bad arguments");
+  const NetF32& n = c->f32[PN_NET_REFINE];
+  PN_REQUIRE(!n.loaded || n.out_dim[n.n_layers - 1] == 4 * S + 3, "pn_refine_forward: net output width %d != 4S+3 (S=%d)",
+             n.out_dim[n.n_layers - 1], S);
+  MlpLaunch L{};
+  L.act = 1; L.input_mode = IN_LOAD; L.in0 = x; L.in1 = nullptr; L.in_stride = n.in_dim[0]; L.S = S; L.P = 0; L.M = N; L.out = out;
+  heads_refine(L, S);
+  return run_mlp(c, PN_NET_REFINE, L, precision, as_stream(stream));
+}
+
+static int check_nerf(const NetF32& n) {
+  if (!n.loaded) return PN_OK;   // run_mlp reports it
+  PN_REQUIRE(n.in_dim[0] == 63 && n.in_dim[n.n_layers - 1] == kHidden + 27 && n.out_dim[n.n_layers - 1] == 4,
+             "NeRF net must be 63 -> 256.. -> (256+27) -> 4 (DoNeRFTRT with multires 10 / 4)");
+  return PN_OK;
+}
+
+int pn_nerf_forward(pn_ctx_t* c, const float* embedded, const float* embedded_dirs, int64_t M, float* raw, int precision,
+                    pn_stream_t stream) {
+  if (M == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && embedded && embedded_dirs && raw && M >= 0, "pn_nerf_forward: bad arguments");
+  int rc = check_nerf(c->f32[PN_NET_NERF]);
+  if (rc != PN_OK) return rc;
+  MlpLaunch L{};
+  L.act = 0; L.input_mode = IN_LOAD2; L.in0 = embedded; L.in1 = embedded_dirs; L.in_stride = 63; L.S = 1; L.P = 0; L.M = M; L.out = raw;
+  heads_none(L);
+  return run_mlp(c, PN_NET_NERF, L, precision, as_stream(stream));
+}
+
+int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int viewdir_stride, int64_t N, int S, float* raw,
+                   int precision, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && pts && viewdirs && raw && N >= 0 && S >= 1 && viewdir_stride >= 3, "pn_run_network: bad arguments");
+  int rc = check_nerf(c->f32[PN_NET_NERF]);
+  if (rc != PN_OK) return rc;
+  MlpLaunch L{};
+  L.act = 0; L.input_mode = IN_ENCODE; L.in0 = pts; L.in1 = viewdirs; L.in_stride = 3; L.in1_stride = viewdir_stride; L.S = S; L.P = 0; L.M = N * S; L.out = raw;
+  heads_none(L);
+  return run_mlp(c, PN_NET_NERF, L, precision, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ the whole path
+// Scratch layout per ray (floats): heads 3S+3 | depth S | add S | mul S | depth3d S | refine_in 6S+3NN*S |
+// refine_out 4S+3 | z S | query 3S | raw 4S
+int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
+  if (f && f->N == 0) return PN_OK;    // empty batch: nothing to validate or launch
+  PN_REQUIRE(c && f, "pn_render_rays: null pointer");
+  PN_REQUIRE(f->rays && f->or_rays && f->texels && f->project_mat && f->rgb && f->depth, "pn_render_rays: frame has a NULL buffer");
+  PN_REQUIRE(f->N >= 0 && f->S >= 1 && f->S <= 64 && f->NN >= 1 && f->NN <= 8 && f->P >= 1 && f->H >= 2 && f->W >= 2,
+             "pn_render_rays: bad frame shape");
+  const int64_t N = f->N;
+  const int S = f->S, NN = f->NN, P = f->P;
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = as_stream(stream);
+  const NetF32& ns = c->f32[PN_NET_SAMPLER];
+  const NetF32& nr = c->f32[PN_NET_REFINE];
+  PN_REQUIRE(ns.loaded && nr.loaded && c->f32[PN_NET_NERF].loaded, "pn_render_rays: load all three networks first");
+  PN_REQUIRE(ns.in_dim[0] == 6 * P && ns.out_dim[ns.n_layers - 1] == 3 * S + 3, "pn_render_rays: sampler net shape does not match P=%d S=%d", P, S);
+  PN_REQUIRE(nr.in_dim[0] == 6 * S + 3 * NN * S && nr.out_dim[nr.n_layers - 1] == 4 * S + 3, "pn_render_rays: refine net shape does not match S=%d NN=%d", S, NN);
+  int rc = check_nerf(c->f32[PN_NET_NERF]);
+  if (rc != PN_OK) return rc;
+
+  const int hs = 3 * S + 3, ri = 6 * S + 3 * NN * S, ro = 4 * S + 3;
+  // carve the arena; every sub-buffer starts on a 256-byte boundary (float4 / bulk accesses need 16)
+  auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
+  const size_t nN = (size_t)N;
+  const size_t total = al(nN * hs) + 4 * al(nN * S) + al(nN * ri) + al(nN * ro) + al(nN * S) + al(nN * 3 * S) + al(nN * 4 * S);
+  rc = ensure(&c->scratch, &c->scratch_floats, total);
+  if (rc != PN_OK) return rc;
+  float* p = c->scratch;
+  float* heads = p;      p += al(nN * hs);
+  float* depth = p;      p += al(nN * S);
+  float* add = p;        p += al(nN * S);
+  float* mul = p;        p += al(nN * S);
+  float* depth3d = p;    p += al(nN * S);
+  float* rin = p;        p += al(nN * ri);
+  float* rout = p;       p += al(nN * ro);
+  float* z = p;          p += al(nN * S);
+  float* query = p;      p += al(nN * 3 * S);
+  float* raw = p;
+
+  cudaEvent_t* pe = nullptr;
+  if (c->profile) {
+    pe = &c->ev[(size_t)c->prof_head * (PN_N_STAGES + 1)];
+    c->prof_head = (c->prof_head + 1) % PN_PROFILE_RING;
+    if (c->prof_count < PN_PROFILE_RING) ++c->prof_count;
+  }
+#define PN_STAGE_MARK(i) do { if (pe) PN_CUDA_OK(cudaEventRecord(pe[i], st)); } while (0)
+  PN_STAGE_MARK(0);
+  // (1) sampler MLP  trt.py:628
+  {
+    MlpLaunch L{};
+    L.act = 1; L.S = S; L.P = P; L.M = N; L.out = heads;
+    if (f->mm_input) { L.input_mode = IN_LOAD; L.in0 = f->mm_input; L.in_stride = 6 * P; }
+    else             { L.input_mode = IN_PLUECKER; L.in0 = f->rays; L.in_stride = 11; }
+    heads_sampler(L, S);
+    rc = run_mlp(c, PN_NET_SAMPLER, L, f->precision, st);
+    if (rc != PN_OK) return rc;
+  }
+  PN_STAGE_MARK(1);
+  // (2) sort + lift  trt.py:631-637
+  rc = pn_sort_lift(heads, hs, f->rays, 11, N, S, depth, add, mul, nullptr, depth3d, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(2);
+  // (3) refine input: Pluecker part + projected colours written in place  trt.py:649-661
+  rc = pn_refine_pluecker(f->rays, 11, depth, N, S, rin, ri, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(3);
+  rc = pn_project_gather(f->texels, f->tex_index, NN, f->H, f->W, f->project_mat, f->or_rays, f->or_rays + 3, 11, depth3d, N, S, rin, ri,
+                         6 * S, nullptr, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(4);
+  // (4) refine MLP  trt.py:668
+  {
+    MlpLaunch L{};
+    L.act = 1; L.input_mode = IN_LOAD; L.in0 = rin; L.in_stride = ri; L.S = S; L.P = 0; L.M = N; L.out = rout;
+    heads_refine(L, S);
+    rc = run_mlp(c, PN_NET_REFINE, L, f->precision, st);
+    if (rc != PN_OK) return rc;
+  }
+  PN_STAGE_MARK(5);
+  // (5) interval refinement + offsets  trt.py:671-681
+  rc = pn_interval_refine(f->rays, 11, depth, rout, ro, N, S, z, query, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(6);
+  // (6) encode + NeRF MLP  trt.py:691 ; viewdirs = rays[:, 8:11]
+  rc = pn_run_network(c, query, f->rays + 8, 11, N, S, raw, f->precision, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(7);
+  // (7) composite  trt.py:694
+  rc = pn_composite(raw, z, f->rays, 11, 3, add, mul, N, S, f->rgb, f->depth, nullptr, nullptr, nullptr, stream);
+  if (rc != PN_OK) return rc;
+  PN_STAGE_MARK(8);
+#undef PN_STAGE_MARK
+  return PN_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ host-buffer flavour
+int pn_render_view_host(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, const float* c2w_host,
+                        const float* texels, const int* tex_index_host, const float* project_mat_host, int NN, int S,
+                        int P, int precision, int row0, int nrows, float* rgb_host, float* depth_host,
+                        pn_stream_t stream) {
+  PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host, "pn_render_view_host: null pointer");
+  PN_REQUIRE(NN >= 1 && NN <= 8 && row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "pn_render_view_host: bad shape");
+  if (nrows == 0) return PN_OK;
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = as_stream(stream);
+  const int64_t n = (int64_t)nrows * W;
+  int rc = ensure(&c->view_buf, &c->view_floats, (size_t)n * (11 + 11 + 3 + 1));
+  if (rc != PN_OK) return rc;
+  float* rays = c->view_buf;
+  float* or_rays = rays + n * 11;
+  float* rgb = or_rays + n * 11;
+  float* depth = rgb + n * 3;
+  PN_CUDA_OK(cudaMemcpyAsync(c->pm_dev, project_mat_host, (size_t)NN * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = pn_raygen(H, W, fx, fy, cx, cy, c2w_host, 0.f, 1.f, 1.f, 10.f, row0, nrows, rays, or_rays, stream);
+  if (rc != PN_OK) return rc;
+  pn_frame_t f;
+  memset(&f, 0, sizeof(f));
+  f.rays = rays; f.or_rays = or_rays; f.mm_input = nullptr; f.texels = texels; f.project_mat = c->pm_dev;
+  for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
+  f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
+  rc = pn_render_rays(c, &f, stream);
+  if (rc != PN_OK) return rc;
+  PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PN_CUDA_OK(cudaMemcpyAsync(depth_host, depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PN_CUDA_OK(cudaStreamSynchronize(st));
+  return PN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Shared declarations for the pronerf_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pronerf_b200.h"
+
+namespace pn {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define PN_CUDA_OK(expr)                                          \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::pn::cuda_fail(_e, #expr);     \
+  } while (0)
+
+#define PN_LAUNCH_OK(what)                                        \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::pn::cuda_fail(_e, what);      \
+  } while (0)
+
+#define PN_REQUIRE(cond, ...)                                     \
+  do {                                                            \
+    if (!(cond)) { ::pn::set_error(__VA_ARGS__); return PN_EINVAL; } \
+  } while (0)
+
+inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kHidden = 256;          // width of every trunk layer (netwidth / mmnetwidth = 256)
+constexpr int kMaxLayers = 8;
+constexpr int kOutPad = 96;           // padded width of an output layer (4S+3 = 67 at S = 16)
+
+// ---------------------------------------------------------------------------------------------
+// One network's packed weights, owned by pn_ctx.
+struct NetF32 {
+  int n_layers = 0;                   // trunk layers + 1 output layer
+  int in_dim[kMaxLayers] = {0};       // as given (nn.Linear in_features)
+  int out_dim[kMaxLayers] = {0};
+  int k_pad[kMaxLayers] = {0};        // in_dim rounded up to a multiple of 16 (trunk) / 4 (output)
+  int k_off[kMaxLayers] = {0};        // first row of a trunk layer inside `trunk`
+  int trunk_rows = 0;                 // sum of k_pad over trunk layers
+  float* trunk = nullptr;             // device, all trunk layers back to back, k-major [trunk_rows][256]
+  float* wout = nullptr;              // device, output layer k-major [k_pad[last]][kOutPad], zero padded
+  float* bias = nullptr;              // device [n_layers][256] (output layer uses the first 64)
+  bool loaded = false;
+};
+
+// How the first-layer operand rows are produced.
+enum InputMode : int {
+  IN_LOAD = 0,        // rows come from a dense [M, K0] tensor
+  IN_LOAD2 = 1,       // DoNeRFTRT.forward: [M,63] embedded + [M,27] embedded_dirs (joins at the last layer)
+  IN_ENCODE = 2,      // run_network: [M,3] points + per-ray [M/S,3] view dirs, encoded in-kernel
+  IN_PLUECKER = 3,    // sampler: rays [N, stride] -> 6P Pluecker features generated in-kernel
+};
+
+// Output-head activations, applied per column range of the last layer.
+enum HeadAct : int { HEAD_NONE = 0, HEAD_SIGMOID = 1, HEAD_TANH = 2 };
+
+struct MlpLaunch {
+  const NetF32* net;
+  int act;                 // 0 = ReLU (NeRF), 1 = ELU (sampler / refine)
+  int input_mode;
+  const float* in0;        // IN_LOAD: x; IN_LOAD2: embedded; IN_ENCODE: pts; IN_PLUECKER: rays
+  const float* in1;        // IN_LOAD2: embedded_dirs; IN_ENCODE: viewdirs
+  int in_stride;           // row stride of in0 in floats
+  int in1_stride;          // row stride of in1 in floats (IN_ENCODE: viewdirs; 3 dense, 11 inside a ray batch)
+  int S;                   // samples per ray (IN_ENCODE: rows per viewdir)
+  int P;                   // IN_PLUECKER: points per ray
+  int64_t M;               // rows
+  float* out;              // [M, out_dim]
+  int head_lo[4];          // column ranges [head_lo[i], head_lo[i+1]) get head_act[i]
+  int head_act[3];
+};
+
+int launch_mlp_f32(const MlpLaunch& L, cudaStream_t stream);
+int pack_layer_f32(const float* W, const float* b, int out_dim, int in_dim, int k_pad, int n_pad, float* wt,
+                   float* bias, int bias_pad, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Accurate fp32 helpers shared by kernels.  Nothing here may be compiled with --use_fast_math.
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float eluf_(float x) { return x > 0.f ? x : (expf(x) - 1.f); }
+
+// [normalize(d), o x normalize(d)]   (F.normalize eps = 1e-12; helpers.py:629-632)
+__device__ __forceinline__ void pluecker6(float ox, float oy, float oz, float dx, float dy, float dz, float* out6) {
+  // torch's vector norm accumulates x*x with an FMA chain (closest match measured on CPU: 99.4% bit-equal)
+  float n = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+  n = fmaxf(n, 1e-12f);
+  float ux = __fdiv_rn(dx, n), uy = __fdiv_rn(dy, n), uz = __fdiv_rn(dz, n);
+  out6[0] = ux; out6[1] = uy; out6[2] = uz;
+  out6[3] = __fsub_rn(__fmul_rn(oy, uz), __fmul_rn(oz, uy));
+  out6[4] = __fsub_rn(__fmul_rn(oz, ux), __fmul_rn(ox, uz));
+  out6[5] = __fsub_rn(__fmul_rn(ox, uy), __fmul_rn(oy, ux));
+}
+
+}  // namespace pn

@@ -1,0 +1,463 @@
+// Per-ray elementwise / scan stages of the ProNeRF render hot path (fp32, HBM-bound).
+//
+//   pn_embed            helpers.py:654-692   frequency positional encoding (stand-alone form)
+//   pn_pluecker         helpers.py:629-632
+//   pn_sampler_input    trt.py:274-278       48-point Pluecker ray encoding
+//   pn_sort_lift        trt.py:631-637       scale, stable 8-sort, gather add/mul, depth lift
+//   pn_refine_pluecker  trt.py:656-658
+//   pn_interval_refine  trt.py:671-681
+//   pn_composite        trt.py:564-597       alpha compositing as a warp-level transmittance scan
+//   pn_raygen           trt.py:245-271; helpers.py:2705-2714, 2776-2793
+//   pn_pack_images      trt.py:286, 296-298  (replaces the x8 replicated planar copy by one RGBA texel array)
+//
+// Arithmetic follows the op order of the reference as executed by PyTorch (see oracle/pronerf_oracle.py);
+// where an integer result depends on it (sort permutation, depth lift feeding the projection) the
+// rounding of every operation is pinned with __f*_rn intrinsics so the compiler cannot contract it.
+#include "common.cuh"
+
+namespace pn {
+
+constexpr int kThreads = 256;
+static inline unsigned blocks_for(int64_t n, int per_block = kThreads) {
+  int64_t b = (n + per_block - 1) / per_block;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+// ------------------------------------------------------------------------------------------------ embed
+// One thread per (row, component); writes x, then sin/cos for L octaves.  Output row is 3+6L floats.
+__global__ void embed_kernel(const float* __restrict__ x, int64_t M, int L, float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * 3) return;
+  int64_t row = t / 3;
+  int c = (int)(t - row * 3);
+  float v = x[t];
+  float* o = out + row * (3 + 6 * L);
+  o[c] = v;
+  float f = 1.f;
+  for (int l = 0; l < L; ++l) {
+    float s, co;
+    sincosf(__fmul_rn(v, f), &s, &co);        // argument = fp32 product x * 2^l (exact), accurate range reduction
+    o[3 + 6 * l + c] = s;
+    o[3 + 6 * l + 3 + c] = co;
+    f *= 2.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pluecker
+__global__ void pluecker_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t M,
+                                float* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float f[6];
+  pluecker6(o[3 * r], o[3 * r + 1], o[3 * r + 2], d[3 * r], d[3 * r + 1], d[3 * r + 2], f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) out[6 * r + i] = f[i];
+}
+
+// torch.linspace(0, 1, P)[i] as the CPU kernel computes it: step = 1/(P-1);
+// first half  fl(step * i), second half fma(-step, P-1-i, 1).
+__device__ __forceinline__ float linspace01(int i, int P) {
+  float step = __fdiv_rn(1.f, (float)(P - 1));
+  return (i < P / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(P - 1 - i), 1.f);
+}
+
+// One thread per (ray, point): 6 outputs.  (All P blocks are equal up to rounding, but the reference feeds
+// the rounded ones to the sampler, so they are reproduced op for op.)
+__global__ void sampler_input_kernel(const float* __restrict__ rays, int ray_stride, int64_t N, int P,
+                                     float* __restrict__ mm) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * P) return;
+  int64_t r = t / P;
+  int p = (int)(t - r * P);
+  const float* ray = rays + r * ray_stride;
+  float tt = (P > 1) ? linspace01(p, P) : 0.f;
+  float ox = __fadd_rn(ray[0], __fmul_rn(ray[3], tt));
+  float oy = __fadd_rn(ray[1], __fmul_rn(ray[4], tt));
+  float oz = __fadd_rn(ray[2], __fmul_rn(ray[5], tt));
+  float f[6];
+  pluecker6(ox, oy, oz, ray[3], ray[4], ray[5], f);
+  float* o = mm + t * 6;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o[i] = f[i];
+}
+
+// ------------------------------------------------------------------------------------------------ sort + lift
+// torch.sort order: ascending, stable, NaN last.
+__device__ __forceinline__ bool sort_gt(float a, float b) { return (a > b) || (isnan(a) && !isnan(b)); }
+
+template <int S>
+__global__ void sort_lift_kernel(const float* __restrict__ heads, int head_stride, const float* __restrict__ rays,
+                                 int ray_stride, int64_t N, float* __restrict__ depth, float* __restrict__ add,
+                                 float* __restrict__ mul, int32_t* __restrict__ perm, float* __restrict__ depth3d) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float* h = heads + r * head_stride;
+  float near_ = rays[r * ray_stride + 6], far_ = rays[r * ray_stride + 7];
+  float span = __fsub_rn(far_, near_);
+  float v[S];
+  int idx[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    v[i] = __fadd_rn(__fmul_rn(h[i], span), near_);     // depth * (far - near) + near   trt.py:631
+    idx[i] = i;
+  }
+  // stable insertion sort, fully unrolled (S is 4/8/16): registers only
+#pragma unroll
+  for (int i = 1; i < S; ++i) {
+#pragma unroll
+    for (int j = i; j > 0; --j) {
+      bool sw = sort_gt(v[j - 1], v[j]);
+      float a = v[j - 1], b = v[j];
+      int ia = idx[j - 1], ib = idx[j];
+      v[j - 1] = sw ? b : a;  v[j] = sw ? a : b;
+      idx[j - 1] = sw ? ib : ia;  idx[j] = sw ? ia : ib;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    if (depth) depth[r * S + i] = v[i];
+    if (perm) perm[r * S + i] = idx[i];
+    if (add) add[r * S + i] = h[S + idx[i]];
+    if (mul) mul[r * S + i] = h[2 * S + idx[i]];
+    // 1/(1 - depth - 1e-5): two subtractions, then a correctly rounded reciprocal   trt.py:637
+    if (depth3d) depth3d[r * S + i] = __fdiv_rn(1.f, __fsub_rn(__fsub_rn(1.f, v[i]), 1e-5f));
+  }
+}
+
+// generic S (<= 64): same algorithm, arrays in local memory
+__global__ void sort_lift_generic_kernel(const float* __restrict__ heads, int head_stride,
+                                         const float* __restrict__ rays, int ray_stride, int64_t N, int S,
+                                         float* __restrict__ depth, float* __restrict__ add, float* __restrict__ mul,
+                                         int32_t* __restrict__ perm, float* __restrict__ depth3d) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float* h = heads + r * head_stride;
+  float near_ = rays[r * ray_stride + 6], far_ = rays[r * ray_stride + 7];
+  float span = __fsub_rn(far_, near_);
+  float v[64];
+  int idx[64];
+  for (int i = 0; i < S; ++i) {
+    float x = __fadd_rn(__fmul_rn(h[i], span), near_);
+    int j = i;
+    while (j > 0 && sort_gt(v[j - 1], x)) { v[j] = v[j - 1]; idx[j] = idx[j - 1]; --j; }
+    v[j] = x; idx[j] = i;
+  }
+  for (int i = 0; i < S; ++i) {
+    if (depth) depth[r * S + i] = v[i];
+    if (perm) perm[r * S + i] = idx[i];
+    if (add) add[r * S + i] = h[S + idx[i]];
+    if (mul) mul[r * S + i] = h[2 * S + idx[i]];
+    if (depth3d) depth3d[r * S + i] = __fdiv_rn(1.f, __fsub_rn(__fsub_rn(1.f, v[i]), 1e-5f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ refine input
+__global__ void refine_pluecker_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth,
+                                       int64_t N, int S, float* __restrict__ out, int out_stride) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * S) return;
+  int64_t r = t / S;
+  int s = (int)(t - r * S);
+  const float* ray = rays + r * ray_stride;
+  float z = depth[t];
+  float ox = __fadd_rn(ray[0], __fmul_rn(ray[3], z));
+  float oy = __fadd_rn(ray[1], __fmul_rn(ray[4], z));
+  float oz = __fadd_rn(ray[2], __fmul_rn(ray[5], z));
+  float f[6];
+  pluecker6(ox, oy, oz, ray[3], ray[4], ray[5], f);
+  float* o = out + r * out_stride + 6 * s;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o[i] = f[i];
+}
+
+// ------------------------------------------------------------------------------------------------ interval refine
+__global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth,
+                                       const float* __restrict__ ro, int ro_stride, int64_t N, int S,
+                                       float* __restrict__ z, float* __restrict__ q) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * S) return;
+  int64_t r = t / S;
+  int s = (int)(t - r * S);
+  const float* ray = rays + r * ray_stride;
+  const float* d = depth + r * S;
+  float near_ = ray[6], far_ = ray[7];
+  float dc = d[s];
+  float upper = (s + 1 < S) ? __fmul_rn(0.5f, __fadd_rn(d[s + 1], dc)) : __fmul_rn(0.5f, __fadd_rn(far_, dc));
+  float lower = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(dc, d[s - 1])) : __fmul_rn(0.5f, __fadd_rn(near_, dc));
+  float frac = ro[r * ro_stride + s];
+  float zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), frac));
+  if (z) z[t] = zz;
+  const float* off = ro + r * ro_stride + S + 3 * s;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    q[t * 3 + c] = __fadd_rn(__fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz)), __fmul_rn(1e-2f, off[c]));
+}
+
+// ------------------------------------------------------------------------------------------------ compositing
+// S lanes per ray (S a power of two <= 32): lane = (ray-in-warp, sample).  Every global access is
+// coalesced (consecutive lanes read consecutive float4 / float); the transmittance T_s = prod_{j<s}(1-a_j+1e-10)
+// is an exclusive product scan over the S-lane segment with __shfl_up_sync, the weighted sums are
+// segment reductions with __shfl_xor_sync.
+// 1 / max(1e-10, depth / acc); torch.max propagates the NaN of 0/0, fmaxf would not.
+__device__ __forceinline__ float disp_of(float wz, float ws) {
+  float q = wz / ws;
+  return 1.f / ((q != q) ? q : fmaxf(1e-10f, q));
+}
+
+template <int S>
+__global__ void composite_scan_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                      const float* __restrict__ rays, int ray_stride, int ray_d_col,
+                                      const float* __restrict__ add, const float* __restrict__ mul, int64_t N,
+                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
+                                      float* __restrict__ acc, float* __restrict__ weights) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one (ray, sample) per thread
+  int64_t r = t / S;
+  int s = (int)(t % S);
+  bool live = r < N;
+  int64_t rr = live ? r : (N - 1);
+  int64_t tt = rr * S + s;
+  float4 rw = reinterpret_cast<const float4*>(raw)[tt];
+  float zc = z[tt];
+  float zn = __shfl_down_sync(0xffffffffu, zc, 1);                  // z_{s+1} (same segment when s < S-1)
+  const float* rd = rays + rr * ray_stride + ray_d_col;
+  float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  float dist = (s == S - 1) ? 1e10f : (zn - zc);
+  dist *= dn;
+  float sig = fmaxf(rw.w + add[tt], 0.f);
+  float alpha = (1.f - expf(-sig * dist)) * fmaxf(mul[tt], 0.f);
+  // exclusive product scan of (1 - alpha + 1e-10) over the segment
+  float f = 1.f - alpha + 1e-10f;
+  float incl = f;
+#pragma unroll
+  for (int o = 1; o < S; o <<= 1) {
+    float up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (s >= o) incl *= up;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (s == 0) T = 1.f;
+  float w = alpha * T;
+  float cr = w * sigmoidf_(rw.x), cg = w * sigmoidf_(rw.y), cb = w * sigmoidf_(rw.z);
+  float wz = w * zc, ws = w;
+#pragma unroll
+  for (int o = S / 2; o > 0; o >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, o);
+    cg += __shfl_xor_sync(0xffffffffu, cg, o);
+    cb += __shfl_xor_sync(0xffffffffu, cb, o);
+    wz += __shfl_xor_sync(0xffffffffu, wz, o);
+    ws += __shfl_xor_sync(0xffffffffu, ws, o);
+  }
+  if (!live) return;
+  if (weights) weights[tt] = w;
+  if (s == 0) {
+    rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+    depth[r] = wz;
+    if (acc) acc[r] = ws;
+    if (disp) disp[r] = disp_of(wz, ws);
+  }
+}
+
+// generic S: one thread per ray, sequential (exactly the reference's cumprod order)
+__global__ void composite_seq_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                     const float* __restrict__ rays, int ray_stride, int ray_d_col,
+                                     const float* __restrict__ add, const float* __restrict__ mul, int64_t N, int S,
+                                     float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
+                                     float* __restrict__ acc, float* __restrict__ weights) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float* rd = rays + r * ray_stride + ray_d_col;
+  float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wz = 0.f, ws = 0.f;
+  for (int s = 0; s < S; ++s) {
+    int64_t tt = r * S + s;
+    float4 rw = reinterpret_cast<const float4*>(raw)[tt];
+    float zc = z[tt];
+    float dist = (s == S - 1) ? 1e10f : (z[tt + 1] - zc);
+    dist *= dn;
+    float alpha = (1.f - expf(-fmaxf(rw.w + add[tt], 0.f) * dist)) * fmaxf(mul[tt], 0.f);
+    float w = alpha * T;
+    T *= (1.f - alpha + 1e-10f);
+    cr += w * sigmoidf_(rw.x); cg += w * sigmoidf_(rw.y); cb += w * sigmoidf_(rw.z);
+    wz += w * zc; ws += w;
+    if (weights) weights[tt] = w;
+  }
+  rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+  depth[r] = wz;
+  if (acc) acc[r] = ws;
+  if (disp) disp[r] = disp_of(wz, ws);
+}
+
+// ------------------------------------------------------------------------------------------------ ray generation
+struct RaygenParams {
+  int H, W, row0, nrows;
+  float fx, fy, cx, cy;          // fp32 images of the float64 intrinsics (torch folds python scalars to fp32)
+  float a, b;                    // -1/(W/(2f)), -1/(H/(2f)) evaluated in double, rounded once
+  float c2w[12];
+  float near_, far_, or_near, or_far;
+};
+
+__global__ void raygen_kernel(RaygenParams p, float* __restrict__ rays, float* __restrict__ or_rays) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)p.nrows * p.W;
+  if (t >= n) return;
+  int j = p.row0 + (int)(t / p.W);
+  int i = (int)(t % p.W);
+  // get_rays  helpers.py:2705-2714
+  float dx = __fdiv_rn(__fsub_rn((float)i, p.cx), p.fx);
+  float dy = __fdiv_rn(-__fsub_rn((float)j, p.cy), p.fy);
+  float dz = -1.f;
+  float d[3], o[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, p.c2w[4 * r]), __fmul_rn(dy, p.c2w[4 * r + 1])), __fmul_rn(dz, p.c2w[4 * r + 2]));
+    o[r] = p.c2w[4 * r + 3];
+  }
+  float nrm = sqrtf(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
+  float v[3] = {__fdiv_rn(d[0], nrm), __fdiv_rn(d[1], nrm), __fdiv_rn(d[2], nrm)};
+  if (or_rays) {
+    float* q = or_rays + t * 11;
+    q[0] = o[0]; q[1] = o[1]; q[2] = o[2]; q[3] = d[0]; q[4] = d[1]; q[5] = d[2];
+    q[6] = p.or_near; q[7] = p.or_far; q[8] = v[0]; q[9] = v[1]; q[10] = v[2];
+  }
+  // ndc_rays with near = 1   helpers.py:2776-2793
+  float tn = __fdiv_rn(-__fadd_rn(1.f, o[2]), d[2]);
+  float ox = __fadd_rn(o[0], __fmul_rn(tn, d[0]));
+  float oy = __fadd_rn(o[1], __fmul_rn(tn, d[1]));
+  float oz = __fadd_rn(o[2], __fmul_rn(tn, d[2]));
+  float rz = __fdiv_rn(1.f, oz);
+  float o0 = __fdiv_rn(__fmul_rn(p.a, ox), oz);
+  float o1 = __fdiv_rn(__fmul_rn(p.b, oy), oz);
+  float o2 = __fadd_rn(1.f, __fmul_rn(rz, 2.f));
+  float d0 = __fmul_rn(p.a, __fsub_rn(__fdiv_rn(d[0], d[2]), __fdiv_rn(ox, oz)));
+  float d1 = __fmul_rn(p.b, __fsub_rn(__fdiv_rn(d[1], d[2]), __fdiv_rn(oy, oz)));
+  float d2 = __fmul_rn(rz, -2.f);
+  float* q = rays + t * 11;
+  q[0] = o0; q[1] = o1; q[2] = o2; q[3] = d0; q[4] = d1; q[5] = d2;
+  q[6] = p.near_; q[7] = p.far_; q[8] = v[0]; q[9] = v[1]; q[10] = v[2];
+}
+
+// ------------------------------------------------------------------------------------------------ image packing
+__global__ void pack_images_kernel(const float* __restrict__ hwc, int64_t npix, float4* __restrict__ texels) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npix) return;
+  texels[t] = make_float4(hwc[3 * t], hwc[3 * t + 1], hwc[3 * t + 2], 0.f);
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" {
+
+int pn_embed(const float* x, int64_t M, int L, float* out, pn_stream_t stream) {
+  if (M == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(x && out && M >= 0 && L >= 0 && L <= 16, "pn_embed: bad arguments (M=%lld L=%d)", (long long)M, L);
+  embed_kernel<<<blocks_for(M * 3), kThreads, 0, as_stream(stream)>>>(x, M, L, out);
+  PN_LAUNCH_OK("pn_embed");
+  return PN_OK;
+}
+
+int pn_pluecker(const float* o, const float* d, int64_t M, float* out, pn_stream_t stream) {
+  if (M == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(o && d && out && M >= 0, "pn_pluecker: bad arguments");
+  pluecker_kernel<<<blocks_for(M), kThreads, 0, as_stream(stream)>>>(o, d, M, out);
+  PN_LAUNCH_OK("pn_pluecker");
+  return PN_OK;
+}
+
+int pn_sampler_input(const float* rays, int ray_stride, int64_t N, int P, float* mm_input, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(rays && mm_input && N >= 0 && P >= 1 && ray_stride >= 6, "pn_sampler_input: bad arguments");
+  sampler_input_kernel<<<blocks_for(N * P), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, N, P, mm_input);
+  PN_LAUNCH_OK("pn_sampler_input");
+  return PN_OK;
+}
+
+int pn_sort_lift(const float* heads, int head_stride, const float* rays, int ray_stride, int64_t N, int S,
+                 float* depth, float* add, float* mul, int32_t* perm, float* depth3d, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(heads && rays && N >= 0 && S >= 1 && S <= 64 && head_stride >= 3 * S && ray_stride >= 8,
+             "pn_sort_lift: bad arguments (S=%d head_stride=%d ray_stride=%d)", S, head_stride, ray_stride);
+  cudaStream_t st = as_stream(stream);
+  unsigned nb = blocks_for(N, 128);
+  switch (S) {
+    case 4:  sort_lift_kernel<4><<<nb, 128, 0, st>>>(heads, head_stride, rays, ray_stride, N, depth, add, mul, perm, depth3d); break;
+    case 8:  sort_lift_kernel<8><<<nb, 128, 0, st>>>(heads, head_stride, rays, ray_stride, N, depth, add, mul, perm, depth3d); break;
+    case 16: sort_lift_kernel<16><<<nb, 128, 0, st>>>(heads, head_stride, rays, ray_stride, N, depth, add, mul, perm, depth3d); break;
+    default: sort_lift_generic_kernel<<<nb, 128, 0, st>>>(heads, head_stride, rays, ray_stride, N, S, depth, add, mul, perm, depth3d);
+  }
+  PN_LAUNCH_OK("pn_sort_lift");
+  return PN_OK;
+}
+
+int pn_refine_pluecker(const float* rays, int ray_stride, const float* depth, int64_t N, int S, float* out,
+                       int out_stride, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(rays && depth && out && N >= 0 && S >= 1 && ray_stride >= 6 && out_stride >= 6 * S,
+             "pn_refine_pluecker: bad arguments");
+  refine_pluecker_kernel<<<blocks_for(N * S), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, N, S, out, out_stride);
+  PN_LAUNCH_OK("pn_refine_pluecker");
+  return PN_OK;
+}
+
+int pn_interval_refine(const float* rays, int ray_stride, const float* depth, const float* refine_out,
+                       int refine_stride, int64_t N, int S, float* z, float* query, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(rays && depth && refine_out && query && N >= 0 && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S,
+             "pn_interval_refine: bad arguments");
+  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, refine_out,
+                                                                               refine_stride, N, S, z, query);
+  PN_LAUNCH_OK("pn_interval_refine");
+  return PN_OK;
+}
+
+int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                 const float* mul, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc, float* weights,
+                 pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(raw && z && rays && add && mul && rgb && depth && N >= 0 && S >= 1 && ray_stride >= ray_d_col + 3,
+             "pn_composite: bad arguments");
+  cudaStream_t st = as_stream(stream);
+#define PN_COMP(SS)                                                                                                  \
+  composite_scan_kernel<SS><<<blocks_for(N * SS), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, \
+                                                                     rgb, depth, disp, acc, weights)
+  switch (S) {
+    case 2: PN_COMP(2); break;
+    case 4: PN_COMP(4); break;
+    case 8: PN_COMP(8); break;
+    case 16: PN_COMP(16); break;
+    case 32: PN_COMP(32); break;
+    default:
+      composite_seq_kernel<<<blocks_for(N), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, S, rgb,
+                                                              depth, disp, acc, weights);
+  }
+#undef PN_COMP
+  PN_LAUNCH_OK("pn_composite");
+  return PN_OK;
+}
+
+int pn_raygen(int H, int W, double fx, double fy, double cx, double cy, const float* c2w_host, float near_, float far_,
+              float or_near, float or_far, int row0, int nrows, float* rays, float* or_rays, pn_stream_t stream) {
+  PN_REQUIRE(H > 0 && W > 0 && c2w_host && rays && row0 >= 0 && nrows >= 0 && row0 + nrows <= H && fx != 0 && fy != 0,
+             "pn_raygen: bad arguments (H=%d W=%d row0=%d nrows=%d)", H, W, row0, nrows);
+  if (nrows == 0) return PN_OK;
+  RaygenParams p;
+  p.H = H; p.W = W; p.row0 = row0; p.nrows = nrows;
+  p.fx = (float)fx; p.fy = (float)fy; p.cx = (float)cx; p.cy = (float)cy;
+  p.a = (float)(-1. / (W / (2. * fx)));
+  p.b = (float)(-1. / (H / (2. * fx)));        // the reference passes K[0][0] as "focal" for both axes (trt.py:265)
+  for (int i = 0; i < 12; ++i) p.c2w[i] = c2w_host[i];
+  p.near_ = near_; p.far_ = far_; p.or_near = or_near; p.or_far = or_far;
+  raygen_kernel<<<blocks_for((int64_t)nrows * W), kThreads, 0, as_stream(stream)>>>(p, rays, or_rays);
+  PN_LAUNCH_OK("pn_raygen");
+  return PN_OK;
+}
+
+int pn_pack_images(const float* images_hwc, int NN, int H, int W, float* texels, pn_stream_t stream) {
+  PN_REQUIRE(images_hwc && texels && NN >= 1 && H >= 1 && W >= 1, "pn_pack_images: bad arguments");
+  int64_t npix = (int64_t)NN * H * W;
+  pack_images_kernel<<<blocks_for(npix), kThreads, 0, as_stream(stream)>>>(images_hwc, npix, reinterpret_cast<float4*>(texels));
+  PN_LAUNCH_OK("pn_pack_images");
+  return PN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// Projection-aware colour gather (inverse_warp.py:584-619 + trt.py:649-655).
+//
+// For every ray, sample s and neighbour view k:  w = ro + rd * depth3d  ->  p = M_k w (3x4)  ->
+// X = p.x/p.z, Y = p.y/p.z  ->  normalise / un-normalise round trip of grid_sample(align_corners=True)
+// ->  bilinear fetch with zero padding.  This is the only data-dependent gather of the path; it is
+// bound by memory (L2/HBM), not arithmetic.
+//
+// Bit-exactness contract: floor(ix), floor(iy) must equal the reference's.  The reference's arithmetic
+// as PyTorch executes it on CPU is restated op for op, every rounding pinned with __f*_rn intrinsics:
+//   w_c   = fl(ro_c + fl(rd_c * depth))                          (separate mul and add, iw.py:600)
+//   p_r   = fma(m_r3, w_3, fma(m_r2, w_2, fma(m_r1, w_1, fl(m_r0 * w_0))))   (MKL sgemm k-loop, iw.py:601)
+//   X     = fl(p_0 / p_2),  Y = fl(p_1 / p_2)                    (iw.py:603)
+//   Xn    = fl(fl(fl(2 X) / (W-1)) - 1)                          (true division, iw.py:607-608)
+//   ix    = fl(fl(Xn + 1) * ((W-1)/2))                           (grid_sample un-normalise)
+//   x0    = floor(ix);  w = ix - x0;  e = 1 - w   (same for y: n, s)
+//   out_c = nw*I[y0][x0] + ne*I[y0][x0+1] + sw*I[y0+1][x0] + se*I[y0+1][x0+1],  taps outside -> 0
+//
+// Data layout: the fast path reads RGBA fp32 texels [NN][H][W] (16 B each, from pn_pack_images), so one
+// tap is one 128-bit read-only load and the two taps of a row are 32 contiguous bytes; the four
+// reference views (12 MB at 504x378) stay L2-resident.  One thread handles one (ray, sample) and loops
+// over the NN views so the ray and depth are loaded once; the 3*NN results of a thread are written
+// straight into the refine network's input row.
+#include "common.cuh"
+
+namespace pn {
+
+struct TexIndex { int v[8]; };
+
+struct Tap {
+  float ix, iy;
+  float x0f, y0f;
+};
+
+__device__ __forceinline__ Tap project_point(const float* __restrict__ M, float w0, float w1, float w2, float w3,
+                                             float wm1, float hm1, float wh, float hh) {
+  float p0 = __fmaf_rn(M[3], w3, __fmaf_rn(M[2], w2, __fmaf_rn(M[1], w1, __fmul_rn(M[0], w0))));
+  float p1 = __fmaf_rn(M[7], w3, __fmaf_rn(M[6], w2, __fmaf_rn(M[5], w1, __fmul_rn(M[4], w0))));
+  float p2 = __fmaf_rn(M[11], w3, __fmaf_rn(M[10], w2, __fmaf_rn(M[9], w1, __fmul_rn(M[8], w0))));
+  float X = __fdiv_rn(p0, p2);
+  float Y = __fdiv_rn(p1, p2);
+  float Xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, X), wm1), 1.f);
+  float Yn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, Y), hm1), 1.f);
+  Tap t;
+  t.ix = __fmul_rn(__fadd_rn(Xn, 1.f), wh);
+  t.iy = __fmul_rn(__fadd_rn(Yn, 1.f), hh);
+  t.x0f = floorf(t.ix);
+  t.y0f = floorf(t.iy);
+  return t;
+}
+
+__device__ __forceinline__ int32_t clamp_index(float f) {
+  const float big = 1073741824.f;   // 2^30
+  if (!(fabsf(f) <= 3.0e38f)) return -1073741824;        // NaN / inf
+  return (int32_t)fminf(fmaxf(f, -big), big);
+}
+
+// Bilinear weights and validity of the four taps (float comparisons: NaN fails them all).
+struct Bilin {
+  float nw, ne, sw, se;
+  bool vx0, vx1, vy0, vy1;
+  int x0, y0;
+};
+
+__device__ __forceinline__ Bilin bilinear_setup(const Tap& t, int W, int H) {
+  Bilin b;
+  float w = __fsub_rn(t.ix, t.x0f), e = __fsub_rn(1.f, w);
+  float n = __fsub_rn(t.iy, t.y0f), s = __fsub_rn(1.f, n);
+  b.nw = __fmul_rn(s, e); b.ne = __fmul_rn(s, w); b.sw = __fmul_rn(n, e); b.se = __fmul_rn(n, w);
+  float x1f = t.x0f + 1.f, y1f = t.y0f + 1.f;
+  b.vx0 = (t.x0f >= 0.f) && (t.x0f <= (float)(W - 1));
+  b.vx1 = (x1f >= 0.f) && (x1f <= (float)(W - 1));
+  b.vy0 = (t.y0f >= 0.f) && (t.y0f <= (float)(H - 1));
+  b.vy1 = (y1f >= 0.f) && (y1f <= (float)(H - 1));
+  // only dereferenced when valid, so the clamp just keeps the conversion defined
+  b.x0 = (int)fminf(fmaxf(t.x0f, -2.f), (float)W);
+  b.y0 = (int)fminf(fmaxf(t.y0f, -2.f), (float)H);
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: RGBA texels, one thread per (ray, sample), loop over neighbours.
+template <int NN_T>
+__global__ void __launch_bounds__(256)
+project_gather_kernel(const float4* __restrict__ texels, TexIndex tex, int NNr, int H, int W, const float* __restrict__ pm,
+                      const float* __restrict__ ro_w, const float* __restrict__ rd_w, int rs, const float* __restrict__ depth3d,
+                      int64_t N, int S, float* __restrict__ epi, int epi_stride, int epi_col0,
+                      int32_t* __restrict__ x0y0) {
+  __shared__ float sM[8 * 12];
+  const int NN = NN_T > 0 ? NN_T : NNr;
+  for (int i = threadIdx.x; i < NN * 12; i += blockDim.x) sM[i] = pm[i];
+  __syncthreads();
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * S) return;
+  int64_t r = t / S;
+  int s = (int)(t - r * S);
+  float d = depth3d[t];
+  float w0 = __fadd_rn(ro_w[rs * r], __fmul_rn(rd_w[rs * r], d));
+  float w1 = __fadd_rn(ro_w[rs * r + 1], __fmul_rn(rd_w[rs * r + 1], d));
+  float w2 = __fadd_rn(ro_w[rs * r + 2], __fmul_rn(rd_w[rs * r + 2], d));
+  float w3 = __fadd_rn(1.f, __fmul_rn(0.f, d));            // ro1[3] = 1, rd1[3] = 0   (trt.py:258-260)
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const float wh = wm1 / 2.f, hh = hm1 / 2.f;
+  float* orow = epi + r * epi_stride + epi_col0;
+#pragma unroll
+  for (int k = 0; k < (NN_T > 0 ? NN_T : 8); ++k) {
+    if (k >= NN) break;
+    Tap tp = project_point(sM + 12 * k, w0, w1, w2, w3, wm1, hm1, wh, hh);
+    Bilin b = bilinear_setup(tp, W, H);
+    const float4* img = texels + (int64_t)tex.v[k] * H * W;
+    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* row0 = img + (int64_t)b.y0 * W + b.x0;
+    const float4* row1 = row0 + W;
+    float4 c00 = (b.vx0 && b.vy0) ? __ldg(row0) : z4;
+    float4 c01 = (b.vx1 && b.vy0) ? __ldg(row0 + 1) : z4;
+    float4 c10 = (b.vx0 && b.vy1) ? __ldg(row1) : z4;
+    float4 c11 = (b.vx1 && b.vy1) ? __ldg(row1 + 1) : z4;
+    float nw = (b.vx0 && b.vy0) ? b.nw : 0.f, ne = (b.vx1 && b.vy0) ? b.ne : 0.f;
+    float sw = (b.vx0 && b.vy1) ? b.sw : 0.f, se = (b.vx1 && b.vy1) ? b.se : 0.f;
+    float* o = orow + (k * S + s) * 3;
+    o[0] = c00.x * nw + c01.x * ne + c10.x * sw + c11.x * se;
+    o[1] = c00.y * nw + c01.y * ne + c10.y * sw + c11.y * se;
+    o[2] = c00.z * nw + c01.z * ne + c10.z * sw + c11.z * se;
+    if (x0y0) {
+      int64_t b_idx = ((int64_t)(k * S + s) * N + r) * 2;
+      x0y0[b_idx] = clamp_index(tp.x0f);
+      x0y0[b_idx + 1] = clamp_index(tp.y0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in form: planar img [B,C,H,W], per-batch depth [B,N], rays [*,4,N] with a batch stride, w2c [B,3,4].
+__global__ void __launch_bounds__(256)
+warp_kernel(const float* __restrict__ img, int B, int C, int H, int W, const float* __restrict__ depth,
+            const float* __restrict__ ro1, const float* __restrict__ rd1, int64_t ro_bstride,
+            const float* __restrict__ w2c, int64_t N, float* __restrict__ out, int32_t* __restrict__ x0y0) {
+  int b = blockIdx.y;
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* ro = ro1 + b * ro_bstride;
+  const float* rd = rd1 + b * ro_bstride;
+  float d = depth[(int64_t)b * N + n];
+  float w0 = __fadd_rn(ro[n], __fmul_rn(rd[n], d));
+  float w1 = __fadd_rn(ro[N + n], __fmul_rn(rd[N + n], d));
+  float w2 = __fadd_rn(ro[2 * N + n], __fmul_rn(rd[2 * N + n], d));
+  float w3 = __fadd_rn(ro[3 * N + n], __fmul_rn(rd[3 * N + n], d));
+  float M[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) M[i] = w2c[b * 12 + i];
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  Tap tp = project_point(M, w0, w1, w2, w3, wm1, hm1, wm1 / 2.f, hm1 / 2.f);
+  Bilin bl = bilinear_setup(tp, W, H);
+  bool v00 = bl.vx0 && bl.vy0, v01 = bl.vx1 && bl.vy0, v10 = bl.vx0 && bl.vy1, v11 = bl.vx1 && bl.vy1;
+  for (int c = 0; c < C; ++c) {
+    const float* pl = img + ((int64_t)b * C + c) * H * W + (int64_t)bl.y0 * W + bl.x0;
+    float a = 0.f;
+    a += v00 ? __ldg(pl) * bl.nw : 0.f;
+    a += v01 ? __ldg(pl + 1) * bl.ne : 0.f;
+    a += v10 ? __ldg(pl + W) * bl.sw : 0.f;
+    a += v11 ? __ldg(pl + W + 1) * bl.se : 0.f;
+    out[((int64_t)b * C + c) * N + n] = a;
+  }
+  if (x0y0) {
+    x0y0[((int64_t)b * N + n) * 2] = clamp_index(tp.x0f);
+    x0y0[((int64_t)b * N + n) * 2 + 1] = clamp_index(tp.y0f);
+  }
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" {
+
+int pn_project_gather(const float* texels, const int* tex_index_host, int NN, int H, int W, const float* project_mat,
+                      const float* ro_w, const float* rd_w, int ray_stride, const float* depth3d, int64_t N, int S,
+                      float* epi, int epi_stride, int epi_col0, int32_t* x0y0, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(texels && project_mat && ro_w && rd_w && depth3d && epi, "pn_project_gather: null pointer");
+  PN_REQUIRE(NN >= 1 && NN <= 8 && H >= 2 && W >= 2 && S >= 1 && N >= 0 && epi_col0 >= 0 && ray_stride >= 3 &&
+                 epi_stride >= epi_col0 + 3 * NN * S,
+             "pn_project_gather: bad shape (NN=%d H=%d W=%d S=%d epi_stride=%d epi_col0=%d)", NN, H, W, S, epi_stride,
+             epi_col0);
+  int64_t total = N * S;
+  unsigned nb = (unsigned)((total + 255) / 256);
+  const float4* tx = reinterpret_cast<const float4*>(texels);
+  TexIndex ti;
+  for (int k = 0; k < 8; ++k) ti.v[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
+  for (int k = 0; k < NN; ++k) PN_REQUIRE(ti.v[k] >= 0, "pn_project_gather: negative texel image index");
+  if (NN == 4)
+    project_gather_kernel<4><<<nb, 256, 0, as_stream(stream)>>>(tx, ti, NN, H, W, project_mat, ro_w, rd_w, ray_stride, depth3d, N, S, epi,
+                                                               epi_stride, epi_col0, x0y0);
+  else
+    project_gather_kernel<0><<<nb, 256, 0, as_stream(stream)>>>(tx, ti, NN, H, W, project_mat, ro_w, rd_w, ray_stride, depth3d, N, S, epi,
+                                                               epi_stride, epi_col0, x0y0);
+  PN_LAUNCH_OK("pn_project_gather");
+  return PN_OK;
+}
+
+int pn_warp(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,
+            int64_t ro_bstride, const float* w2c, int64_t N, float* out, int32_t* x0y0, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
+  PN_REQUIRE(img && depth && ro1 && rd1 && w2c && out, "pn_warp: null pointer");
+  PN_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && H >= 2 && W >= 2 && N >= 0 && ro_bstride >= 0,
+             "pn_warp: bad shape (B=%d C=%d H=%d W=%d)", B, C, H, W);
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
+  warp_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, B, C, H, W, depth, ro1, rd1, ro_bstride, w2c, N, out, x0y0);
+  PN_LAUNCH_OK("pn_warp");
+  return PN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// bf16 tcgen05 tier of the three MLPs (mlp_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pn {
+
+struct NetTC {
+  int n_layers = 0;
+  int in_dim[kMaxLayers] = {0};
+  int out_dim[kMaxLayers] = {0};
+  void* blob = nullptr;          // device: packed bf16 weight images + fp32 biases (layout in mlp_tc.cu)
+  size_t blob_bytes = 0;
+  bool loaded = false;
+};
+
+void tc_free_net(NetTC& n);
+int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const int* out_dims, const float* const* W,
+                const float* const* b, cudaStream_t stream);
+bool tc_available();
+int tc_launch_mlp(const NetTC& n, const MlpLaunch& L, cudaStream_t stream);
+
+}  // namespace pn

@@ -1,0 +1,121 @@
+"""``Renderer``: the resident-state object a serving loop holds (weights packed, reference views resident).
+
+It plays the role of the reference's three TensorRT engine objects plus the per-view state ``render_path``
+rebuilds every frame (trt.py:245-302, trt_infer_v2.py:149-394): one ``pn_ctx_t`` with all three networks, the
+RGBA texels of the ``i_ref`` views, and two entry points per view --
+
+* ``render_view(c2w)``       device-resident: ray generation + ``pn_render_rays``; returns CUDA tensors;
+* ``render_view_host(c2w)``  the end-to-end plug-in call: host pose in, pinned host rgb/depth out.
+
+Rows ``[row0, row0+nrows)`` select a horizontal band of the frame (tile sharding across GPUs).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _abi, ops
+
+
+def neighbour_order(c2w: np.ndarray, poses_ref: np.ndarray, num_neighbor: int) -> np.ndarray:
+    """Nearest reference cameras by translation distance (trt.py:281-284), stable order."""
+    rel = np.sqrt(((c2w[None, :3, 3].astype(np.float32) - poses_ref[:, :3, 3].astype(np.float32)) ** 2).sum(1, dtype=np.float32))
+    return np.argsort(rel, kind="stable")[:num_neighbor]
+
+
+def projection_matrices(K: np.ndarray, poses_ref: np.ndarray, order) -> np.ndarray:
+    """``K * diag(1,-1,-1) * pose`` per neighbour, fp32 (trt.py:287-294; un-inverted c2w, reference quirk Q1)."""
+    Kf = np.asarray(K, dtype=np.float64).astype(np.float32)
+    flip = np.diag([1., -1., -1.]).astype(np.float32)
+    return np.stack([Kf @ (flip @ poses_ref[i, :3, :4].astype(np.float32)) for i in order], 0).astype(np.float32)
+
+
+class Renderer:
+    def __init__(self, weights: dict, images_ref: np.ndarray, poses_ref: np.ndarray, K: np.ndarray, H: int, W: int,
+                 S: int = 8, P: int = 48, num_neighbor: int = 4, precision: str = "fp32", device="cuda:0"):
+        self.device = torch.device(device)
+        _abi.require_device(self.device.index or 0)
+        self.H, self.W, self.K = int(H), int(W), np.asarray(K, dtype=np.float64)
+        self.S, self.P, self.NN, self.precision = S, P, num_neighbor, precision
+        self.poses_ref = np.asarray(poses_ref, dtype=np.float32)
+        self.ctx = ops.Context(self.device)
+        self.load_weights(weights)
+        self.texels = None
+        self._staging = None
+        self.set_images(images_ref)
+
+    # -- state ------------------------------------------------------------------------------------
+    def load_weights(self, weights: dict):
+        """``weights``: the reference checkpoint's three state_dicts (trt.py:478-481), numpy or tensors."""
+        def lin(sd, names):
+            ws, bs = [], []
+            for n in names:
+                w, b = sd[n + ".weight"], sd[n + ".bias"]
+                ws.append(torch.as_tensor(np.asarray(w) if not isinstance(w, torch.Tensor) else w, dtype=torch.float32).to(self.device))
+                bs.append(torch.as_tensor(np.asarray(b) if not isinstance(b, torch.Tensor) else b, dtype=torch.float32).to(self.device))
+            return ws, bs
+        s = weights["mmr_network_fn_state_dict"]
+        nb = sum(1 for k in s if k.startswith("fc_backbone.") and k.endswith(".weight"))
+        names = [f"fc_backbone.{i}" for i in range(nb)] + ["fc_output"]
+        self.ctx.load_net(_abi.PN_NET_SAMPLER, *lin(s, names))
+        self.ctx.load_net(_abi.PN_NET_REFINE, *lin(weights["refine_net_state_dict"], names))
+        n = weights["network_fine_state_dict"]
+        nl = sum(1 for k in n if k.startswith("layers.") and k.endswith(".weight"))
+        self.ctx.load_net(_abi.PN_NET_NERF, *lin(n, [f"layers.{i}" for i in range(nl)]))
+        torch.cuda.synchronize(self.device)
+
+    def set_images(self, images_ref, non_blocking: bool = False):
+        """Upload + pack the reference views [n_ref,H,W,3] (numpy, or a pinned CPU tensor for the async path)."""
+        t = images_ref if isinstance(images_ref, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images_ref, dtype=np.float32))
+        if tuple(t.shape[1:]) != (self.H, self.W, 3):
+            raise ValueError(f"images must be [n,{self.H},{self.W},3], got {tuple(t.shape)}")
+        if self._staging is None or self._staging.shape != t.shape:
+            self._staging = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._staging.copy_(t, non_blocking=non_blocking)
+            self.texels = ops.pack_images(self._staging)
+        self.image_bytes = t.numel() * 4
+
+    # -- per view ---------------------------------------------------------------------------------
+    def view_params(self, c2w):
+        c2w = np.asarray(c2w, dtype=np.float32)
+        order = neighbour_order(c2w, self.poses_ref, self.NN)
+        return c2w, [int(i) for i in order], projection_matrices(self.K, self.poses_ref, order)
+
+    def prepare_view(self, c2w, row0: int = 0, nrows=None):
+        """Device-resident inputs of one view (outside the timed region of the kernel-only metric)."""
+        c2w, order, pm = self.view_params(c2w)
+        rays, or_rays = ops.raygen(self.H, self.W, self.K, c2w, self.device, row0=row0, nrows=nrows)
+        return dict(rays=rays, or_rays=or_rays, project_mat=torch.from_numpy(pm).to(self.device), tex_index=order,
+                    rgb=torch.empty((rays.shape[0], 3), device=self.device), depth=torch.empty((rays.shape[0],), device=self.device))
+
+    def render_prepared(self, prep):
+        """One pass of the hot path (8 kernels) over a prepared view; returns (rgb [n,3], depth [n]) CUDA tensors."""
+        return self.ctx.render_rays(prep["rays"], prep["or_rays"], self.texels, prep["project_mat"], self.S, self.P,
+                                    self.H, self.W, tex_index=prep["tex_index"], precision=self.precision,
+                                    out_rgb=prep["rgb"], out_depth=prep["depth"])
+
+    def render_view(self, c2w, row0: int = 0, nrows=None):
+        return self.render_prepared(self.prepare_view(c2w, row0, nrows))
+
+    def render_view_host(self, c2w, rgb_host=None, depth_host=None, row0: int = 0, nrows=None):
+        """End to end with HOST buffers: uploads the pose + matrices, renders, downloads rgb/depth (synchronous)."""
+        c2w, order, pm = self.view_params(c2w)
+        return self.ctx.render_view_host(self.H, self.W, self.K, c2w, self.texels, pm, self.S, self.P, tex_index=order,
+                                         precision=self.precision, row0=row0, nrows=nrows, rgb_host=rgb_host,
+                                         depth_host=depth_host)
+
+
+# FLOP / byte accounting used by bench.py and DESIGN.md
+def flops_per_ray(S: int = 8, P: int = 48, NN: int = 4, W: int = 256) -> dict:
+    """ALGORITHMIC flops per ray (2 x MAC of the reference's nn.Linear shapes)."""
+    sampler = 2 * (6 * P * W + 5 * W * W + W * (3 * S + 3))
+    refine = 2 * ((6 * S + 3 * NN * S) * W + 5 * W * W + W * (4 * S + 3))
+    nerf = S * 2 * (63 * W + 6 * W * W + (W + 27) * 4)
+    return dict(sampler=sampler, refine=refine, nerf=nerf, total=sampler + refine + nerf)
+
+
+def gather_bytes_per_ray(S: int = 8, NN: int = 4, H: int = 378, W: int = 504, n_rays=None) -> float:
+    """Compulsory bytes of the gather kernel: depth3d + world ray + written features + the texel set once."""
+    n_rays = H * W if n_rays is None else n_rays
+    return 4.0 * S + 24.0 + 4.0 * 3 * NN * S + NN * H * W * 16.0 / n_rays

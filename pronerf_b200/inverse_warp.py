@@ -1,0 +1,18 @@
+"""Mirror of the one ``inverse_warp.py`` entry the infer path calls (inverse_warp.py:584-619)."""
+from __future__ import annotations
+
+from . import ops
+
+
+def inverse_warp_rod1_rt2_coords_trt(img, depth, ro1, rd1, w2c, scale=1., padding_mode='zeros'):
+    """Project ``ro1 + rd1*depth`` with the 3x4 matrices ``w2c`` and bilinearly fetch ``img``.
+
+    img [B,3,H,W]; depth [B,H',W']; ro1/rd1 [B,4,H'*W'] (homogeneous world rays; the reference passes stride-0
+    expanded views); w2c [B,3,4].  Returns ``(projected_img [B,3,H',W'], None)`` like the reference.
+    Only ``padding_mode='zeros'`` (what the infer path uses, trt.py:652) is built.
+    """
+    if padding_mode != 'zeros':
+        raise NotImplementedError("pronerf_b200 builds padding_mode='zeros' only (the infer path's mode)")
+    B, H, W = depth.shape
+    out = ops.warp(img, depth.reshape(B, -1), ro1, rd1, w2c)
+    return out.view(B, img.shape[1], H, W), None

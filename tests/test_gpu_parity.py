@@ -1,0 +1,313 @@
+"""GPU parity: every CUDA stage (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (stated per test):
+* integer-valued results -- sort permutation, sorted depths, lifted depth3d, floor(ix)/floor(iy) of the
+  projected coordinates -- must be BIT-EXACT;
+* fp32 elementwise stages: <= 2e-6 abs;   * fp32 MLP outputs: <= 2e-4 abs + 1e-4 rel (7-8 chained GEMMs);
+* end to end rgb / depth: <= 1e-3 max-abs (the north-star bound for the fp32 tier).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pronerf_oracle as O
+from pronerf_b200 import synth
+from tests.util import T, call_kwargs, make_kwargs, make_modules
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pronerf_b200 import _abi, ops as _ops
+    _abi.require_device(0)
+    return _ops
+
+
+def test_embed(ops, golden_kat):
+    x = T(golden_kat["embed_x"], DEV)
+    for L, key in ((10, "embed10"), (4, "embed4")):
+        got = ops.embed(x, L).cpu().numpy()
+        np.testing.assert_allclose(got, golden_kat[key], atol=1e-6, rtol=0)          # reference's own vectors
+    big = (torch.rand(4099, 3) * 2 - 1) * 1.3
+    np.testing.assert_allclose(ops.embed(big.to(DEV), 10).cpu().numpy(), O.embed(big, 10).numpy(), atol=1e-6, rtol=0)
+
+
+def test_pluecker(ops, golden_kat):
+    got = ops.pluecker(T(golden_kat["pl_o"], DEV), T(golden_kat["pl_d"], DEV)).cpu().numpy()
+    np.testing.assert_allclose(got, golden_kat["pl_out"], atol=1e-6, rtol=1e-6)
+
+
+def test_raygen_and_sampler_input(ops):
+    scene = synth.make_small_scene(H=30, W=44)
+    c2w = scene.poses[3]
+    pv = O.prep_view(scene.H, scene.W, scene.K, c2w, scene.poses_ref)
+    rays, or_rays = ops.raygen(scene.H, scene.W, scene.K, c2w, DEV)
+    np.testing.assert_allclose(or_rays.cpu().numpy(), pv["or_rays"].numpy(), atol=1e-6, rtol=1e-6)
+    np.testing.assert_allclose(rays.cpu().numpy(), pv["rays"].numpy(), atol=2e-6, rtol=1e-6)
+    # the integer-critical inputs of the projection (world origin / direction) must be bit-exact
+    assert torch.equal(or_rays[:, :6].cpu(), pv["or_rays"][:, :6])
+    mm = ops.sampler_input(pv["rays"].to(DEV), 48).cpu().numpy()
+    np.testing.assert_allclose(mm, pv["mm_input"].numpy(), atol=1e-6, rtol=0)
+    # band of rows == the same rows of the full frame (tile sharding)
+    r2, o2 = ops.raygen(scene.H, scene.W, scene.K, c2w, DEV, row0=7, nrows=11)
+    assert torch.equal(r2, rays[7 * scene.W:18 * scene.W]) and torch.equal(o2, or_rays[7 * scene.W:18 * scene.W])
+
+
+@pytest.mark.parametrize("S", [4, 8, 16, 5])
+def test_sort_lift_bit_exact(ops, S):
+    g = torch.Generator().manual_seed(S)
+    N = 5000
+    heads = torch.rand(N, 3 * S + 3, generator=g)
+    heads[:64, 1] = heads[:64, 0]                       # exact ties: stability matters
+    heads[64:96, :S] = 0.25
+    rays = torch.zeros(N, 11)
+    rays[:, 6] = torch.rand(N, generator=g) * 0.1
+    rays[:, 7] = 1.0 - torch.rand(N, generator=g) * 0.1
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    d_ref, a_ref, m_ref, p_ref, d3_ref = O.sort_lift(heads[:, :S], heads[:, S:2 * S], heads[:, 2 * S:3 * S], near, far)
+    d, a, m, p, d3 = ops.sort_lift(heads.to(DEV), rays.to(DEV), S)
+    assert torch.equal(p.cpu().long(), p_ref)
+    assert torch.equal(d.cpu(), d_ref) and torch.equal(a.cpu(), a_ref) and torch.equal(m.cpu(), m_ref)
+    assert torch.equal(d3.cpu(), d3_ref)
+
+
+def test_warp_known_answer(ops, golden_kat):
+    g = golden_kat
+    img, depth, ro1, rd1, w2c = (T(g[k], DEV) for k in ("w_img", "w_depth", "w_ro1", "w_rd1", "w_w2c"))
+    from pronerf_b200.inverse_warp import inverse_warp_rod1_rt2_coords_trt
+    out, none = inverse_warp_rod1_rt2_coords_trt(img, depth, ro1, rd1, w2c, padding_mode='zeros')
+    assert none is None and out.shape == g["w_out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["w_out"], atol=2e-6, rtol=0)           # reference's own output
+    # floor indices vs the oracle: bit-exact
+    B, C, H, W = img.shape
+    w = T(g["w_ro1"]) + T(g["w_rd1"]) * T(g["w_depth"]).view(B, 1, -1)
+    p2 = O.bmm_k4(T(g["w_w2c"]), w)
+    p2[:, :2, :] /= p2[:, 2:, :]
+    _, _, _, x0, y0 = O.grid_sample_bilinear_zeros(T(g["w_img"]), 2 * p2[:, 0] / (W - 1) - 1, 2 * p2[:, 1] / (H - 1) - 1)
+    _, idx = ops.warp(img, depth.reshape(B, -1), ro1, rd1, w2c, want_index=True)
+    idx = idx.cpu().long()
+    big = 2 ** 30
+    assert torch.equal(idx[..., 0], x0.clamp(-big, big)) and torch.equal(idx[..., 1], y0.clamp(-big, big))
+    # stride-0 expanded rays (what the reference passes, trt.py:262)
+    ro_e, rd_e = ro1[:1].expand(B, -1, -1), rd1[:1].expand(B, -1, -1)
+    out_e = ops.warp(img, depth.reshape(B, -1), ro_e, rd_e, w2c)
+    out_c = ops.warp(img, depth.reshape(B, -1), ro_e.contiguous(), rd_e.contiguous(), w2c)
+    assert torch.equal(out_e, out_c)
+
+
+@pytest.mark.parametrize("which", ["random", "calibrated"])
+def test_project_gather_bit_exact_indices(ops, which, golden_small_random, golden_small_calibrated):
+    g = golden_small_random if which == "random" else golden_small_calibrated
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    images = scene.images_ref[g["ref_nos"]]
+    depth3d = T(g["warp_depths"][:8, 0, :].T.copy())
+    if which == "calibrated":                     # widen: far / behind / non-finite depths
+        depth3d = depth3d.clone()
+        depth3d[::7, 3] *= 40.0
+        depth3d[5::11, 1] = float("inf")
+        depth3d[3::13, 6] = -2.0
+    ro, rd = T(g["or_rays"][:, 0:3].copy()), T(g["or_rays"][:, 3:6].copy())
+    pm = T(g["project_mat"])
+    ref = O.project_gather(images, pm, ro, rd, depth3d)
+    tex = ops.pack_images(T(images, DEV))
+    epi, idx = ops.project_gather(tex, pm.to(DEV), ro.to(DEV), rd.to(DEV), depth3d.to(DEV), want_index=True)
+    idx = idx.cpu().long()
+    big = 2 ** 30
+    assert torch.equal(idx[..., 0], ref["x0"].clamp(-big, big)), "floor(ix) must be bit-exact"
+    assert torch.equal(idx[..., 1], ref["y0"].clamp(-big, big)), "floor(iy) must be bit-exact"
+    np.testing.assert_allclose(epi.cpu().numpy(), ref["epi"].numpy(), atol=2e-6, rtol=0)
+    if which == "random":
+        np.testing.assert_allclose(epi.cpu().numpy(), g["refine_input"][:, 48:], atol=2e-6, rtol=0)   # the reference's own
+    # texel index table == physically reordered images (per-view ref_nos ordering without moving pixels)
+    order = [2, 0, 3, 1]
+    tex2 = ops.pack_images(T(images[order], DEV))             # slot j holds original image order[j]
+    inv = [int(v) for v in np.argsort(order)]                 # neighbour k must read slot inv[k]
+    epi2 = ops.project_gather(tex2, pm.to(DEV), ro.to(DEV), rd.to(DEV), depth3d.to(DEV), tex_index=inv)
+    assert torch.equal(epi2, epi)
+
+
+@pytest.mark.parametrize("which", ["random", "calibrated"])
+def test_mlps_fp32(ops, which, golden_small_random, golden_small_calibrated):
+    g = golden_small_random if which == "random" else golden_small_calibrated
+    sd = synth.make_weights(seed=0, calibrated=(which == "calibrated"))
+    nerf, samp, refn = make_modules(sd, DEV)
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    pv = O.prep_view(H, W, scene.K, g["c2w"], scene.poses_ref)
+    with torch.no_grad():
+        mm_rgb, add, mul, depth = samp(pv["mm_input"].to(DEV))
+        tol = dict(atol=2e-4, rtol=1e-4)
+        np.testing.assert_allclose(depth.cpu().numpy(), g["sampler_depth"], **tol)
+        np.testing.assert_allclose(add.cpu().numpy(), g["sampler_add"], **tol)
+        np.testing.assert_allclose(mul.cpu().numpy(), g["sampler_mul"], **tol)
+        np.testing.assert_allclose(mm_rgb.cpu().numpy(), g["sampler_mm_rgb"], **tol)
+        # sampler input generated inside the kernel == loaded input
+        ctx = samp._ctx()
+        rd_, rgb_, off_ = refn(T(g["refine_input"], DEV))
+        np.testing.assert_allclose(rd_.cpu().numpy(), g["refine_depth"], **tol)
+        np.testing.assert_allclose(off_.cpu().numpy(), g["refine_offsets"], **tol)
+        np.testing.assert_allclose(rgb_.cpu().numpy(), g["refine_rgb"], **tol)
+        # NeRF: explicit-encoding module forward and the fused run_network
+        q = T(g["query_points"], DEV)
+        v = T(g["query_viewdirs"], DEV)
+        e = ops.embed(q.reshape(-1, 3), 10)
+        gd = ops.embed(v[:, None].expand(q.shape).reshape(-1, 3), 4)
+        raw_a = nerf(e, gd).reshape(q.shape[0], q.shape[1], 4)
+        raw_b = nerf._ctx().run_network(q, v)
+        tol = dict(atol=5e-4, rtol=2e-4) if which == "random" else dict(atol=5e-3, rtol=5e-4)   # calibrated sigma row x60
+        np.testing.assert_allclose(raw_a.cpu().numpy(), g["nerf_raw"], **tol)
+        np.testing.assert_allclose(raw_b.cpu().numpy(), g["nerf_raw"], **tol)
+        np.testing.assert_allclose(raw_a.cpu().numpy(), raw_b.cpu().numpy(), atol=1e-4, rtol=1e-4)
+
+
+def test_interval_refine_and_composite(ops, golden_small_calibrated, golden_kat):
+    g = golden_small_calibrated
+    rays = T(g["rays"])
+    depth, add, mul, perm, d3 = O.sort_lift(T(g["sampler_depth"]), T(g["sampler_add"]), T(g["sampler_mul"]), rays[:, 6:7], rays[:, 7:8])
+    rout = torch.cat([T(g["refine_depth"]), T(g["refine_offsets"])], -1)
+    z, q = ops.interval_refine(rays.to(DEV), depth.to(DEV), rout.to(DEV), 8)
+    np.testing.assert_allclose(z.cpu().numpy(), g["comp_z"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(q.cpu().numpy(), g["query_points"], atol=1e-6, rtol=0)
+    pl = ops.refine_pluecker(rays.to(DEV), depth.to(DEV))
+    np.testing.assert_allclose(pl.cpu().numpy(), g["refine_input"][:, :48], atol=1e-6, rtol=1e-6)
+    from pronerf_b200.render import raw2outputs
+    k = golden_kat
+    for raw, zz, d, a, m, want in (
+            (k["c_raw"], k["c_z"], k["c_d"], k["c_add"], k["c_mul"], (k["c_rgb"], k["c_disp"], k["c_acc"], k["c_w"], k["c_depth"])),
+            (g["nerf_raw"], g["comp_z"], g["rays"][:, 3:6].copy(), g["comp_add"], g["comp_mul"],
+             (g["comp_rgb"], g["comp_disp"], g["comp_acc"], g["comp_weights"], g["comp_depth"]))):
+        rgb, disp, acc, w, dep = raw2outputs(T(raw, DEV), T(zz, DEV), T(d, DEV), 0., False, pytest=False,
+                                             mm_density_add=T(a, DEV), mm_density_mul=T(m, DEV), iter=1e6)
+        np.testing.assert_allclose(rgb.cpu().numpy(), want[0], atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(w.cpu().numpy(), want[3], atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(dep.cpu().numpy(), want[4], atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(acc.cpu().numpy(), want[2], atol=2e-6, rtol=1e-5)
+        ok = np.isfinite(want[1])
+        np.testing.assert_allclose(disp.cpu().numpy()[ok], want[1][ok], rtol=2e-4)
+    # generic sample counts (sequential kernel) vs the oracle
+    gen = torch.Generator().manual_seed(5)
+    for S in (3, 6, 16, 32):
+        N = 777
+        raw = torch.randn(N, S, 4, generator=gen) * 2
+        zz = torch.sort(torch.rand(N, S, generator=gen), -1)[0]
+        d = torch.randn(N, 3, generator=gen)
+        a, m = torch.randn(N, S, generator=gen), torch.rand(N, S, generator=gen)
+        want = O.raw2outputs(raw, zz, d, a, m)
+        got = ops.composite(raw.to(DEV), zz.to(DEV), d.to(DEV), a.to(DEV), m.to(DEV))
+        np.testing.assert_allclose(got[0].cpu().numpy(), want[0].numpy(), atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(got[4].cpu().numpy(), want[4].numpy(), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("which", ["random", "calibrated"])
+@pytest.mark.parametrize("route", ["fused", "staged", "reference_kwargs"])
+def test_render_end_to_end_small(ops, which, route, golden_small_random, golden_small_calibrated):
+    """render() through the reference call surface vs the reference's own rgb/depth (fp32 tier, 1e-3)."""
+    from pronerf_b200.render import prepare_view, render
+    g = golden_small_random if which == "random" else golden_small_calibrated
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    sd = synth.make_weights(seed=0, calibrated=(which == "calibrated"))
+    nets = make_modules(sd, DEV)
+    kw = make_kwargs(nets, scene, DEV)
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(g["c2w"], [H, W, scene.focal], scene.K, kw)
+        assert list(kw["ref_nos"]) == list(g["ref_nos"])
+        np.testing.assert_allclose(kw["project_mat_host"], g["project_mat"], atol=1e-4, rtol=1e-6)
+        ck = call_kwargs(kw)
+        if route == "staged":
+            ck["fused"] = False
+        if route == "reference_kwargs":          # exactly the tensors the reference's render_path builds
+            S = 8
+            imgs = T(scene.images_ref[g["ref_nos"]], DEV).permute(0, 3, 1, 2)
+            ck["ref_rgb"] = imgs.unsqueeze(1).expand(-1, S, -1, -1, -1).contiguous().view(4 * S, 3, H, W)
+            ck["ref_pose"] = T(g["project_mat"], DEV).unsqueeze(1).expand(-1, S, -1, -1).contiguous().view(4 * S, 3, 4)
+            ck["mm_input"] = ops.sampler_input(rays, 48)
+            for k in ("texels", "project_mat", "tex_index"):
+                ck.pop(k)
+            rays, or_rays = T(g["rays"], DEV), T(g["or_rays"], DEV)
+        rgb0, rgb1, depth, extras = render(rays, or_rays, sh, **ck)
+    assert extras == {} and rgb0.shape == (H, W, 3) and depth.shape == (H, W)
+    assert rgb0.data_ptr() == rgb1.data_ptr()                                   # reference quirk Q5: same tensor
+    np.testing.assert_allclose(rgb1.cpu().numpy(), g["rgb"], atol=1e-3, rtol=0)
+    np.testing.assert_allclose(depth.cpu().numpy(), g["depth"], atol=1e-3, rtol=0)
+
+
+def test_full_frame_504x378(ops, golden_fern):
+    """BASELINE resolution, full frame: subset vs the reference's render, plus size-independent properties."""
+    from pronerf_b200.render import prepare_view, render
+    g = golden_fern
+    scene = synth.make_scene(factor=8)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    nets = make_modules(sd, DEV)
+    kw = make_kwargs(nets, scene, DEV)
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(g["c2w"], scene.hwf, scene.K, kw)
+        ck = call_kwargs(kw)
+        rgb, _, depth, _ = render(rays, or_rays, sh, **ck)
+        rgbf, depthf = rgb.reshape(-1, 3), depth.reshape(-1)
+        idx = torch.from_numpy(g["idx"]).to(DEV)
+        np.testing.assert_allclose(rgbf[idx].cpu().numpy(), g["rgb_subset"], atol=1e-3, rtol=0)
+        np.testing.assert_allclose(depthf[idx].cpu().numpy(), g["depth_subset"], atol=1e-3, rtol=0)
+        # checksum of the whole frame vs the reference's (mean error well inside the tolerance)
+        n = rgbf.shape[0]
+        assert abs(float(rgbf.double().sum()) - float(g["rgb_sum"].sum())) / (3 * n) < 1e-4
+        assert abs(float(depthf.double().sum()) - float(g["depth_sum"])) / n < 1e-4
+        # rays are independent: rendering two halves / a permuted batch gives bit-identical pixels
+        half = n // 2 + 13
+        ra, _, da, _ = render(rays[:half], or_rays[:half], (half, 3), **ck)
+        rb, _, db, _ = render(rays[half:], or_rays[half:], (n - half, 3), **ck)
+        assert torch.equal(torch.cat([ra, rb]), rgbf) and torch.equal(torch.cat([da, db]), depthf)
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(DEV)
+        rp, _, dp, _ = render(rays[perm].contiguous(), or_rays[perm].contiguous(), (n, 3), **ck)
+        assert torch.equal(rp, rgbf[perm]) and torch.equal(dp, depthf[perm])
+        # staged route == fused route, bit for bit (same kernels, different plumbing)
+        ck2 = dict(ck, fused=False)
+        rs, _, ds, _ = render(rays, or_rays, sh, **ck2)
+        assert torch.equal(rs, rgb) and torch.equal(ds, depth)
+
+
+def test_edge_cases(ops):
+    scene = synth.make_small_scene(H=16, W=20)
+    sd = synth.make_weights(seed=1, calibrated=True)
+    nets = make_modules(sd, DEV)
+    kw = make_kwargs(nets, scene, DEV)
+    from pronerf_b200.render import prepare_view, render
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(scene.poses[0], scene.hwf, scene.K, kw)
+        ck = call_kwargs(kw)
+        full, _, dfull, _ = render(rays, or_rays, sh, **ck)
+        for n in (0, 1, 63, 64, 65, 127):                                        # empty, single, ragged tiles
+            r, _, d, _ = render(rays[:n], or_rays[:n], (n, 3), **ck)
+            assert r.shape == (n, 3) and d.shape == (n,)
+            assert torch.equal(r, full.reshape(-1, 3)[:n]) and torch.equal(d, dfull.reshape(-1)[:n])
+    # loud failures, no fallback
+    with pytest.raises(RuntimeError):
+        ops.embed(torch.zeros(4, 3), 10)                                         # CPU tensor
+    with pytest.raises(RuntimeError):
+        nets[0].cpu()(torch.zeros(4, 63), torch.zeros(4, 27))
+    ctx = ops.Context(DEV)
+    with pytest.raises(RuntimeError, match="not loaded"):
+        ctx.sampler_forward(torch.zeros(4, 288, device=DEV), 8)
+    with pytest.raises(NotImplementedError):
+        render(rays, or_rays, sh, **dict(ck, use_trt=True))
+
+
+def test_other_sample_counts(ops):
+    """S = 4 and S = 16 (BASELINE config 5) against the oracle, fp32 tier."""
+    for S in (4, 16):
+        scene = synth.make_small_scene(H=12, W=16)
+        sd = synth.make_weights(seed=2, N_samples=S, calibrated=True)
+        nets = make_modules(sd, DEV, S=S)
+        kw = make_kwargs(nets, scene, DEV, S=S)
+        from pronerf_b200.render import prepare_view, render
+        with torch.no_grad():
+            rays, or_rays, sh = prepare_view(scene.poses[8], scene.hwf, scene.K, kw)
+            rgb, _, depth, _ = render(rays, or_rays, sh, **call_kwargs(kw))
+        pv = O.prep_view(scene.H, scene.W, scene.K, scene.poses[8], scene.poses_ref, N_samples=S)
+        images = scene.images_ref[pv["ref_nos"].numpy()]
+        ref = O.render_rays(sd, pv["rays"], pv["mm_input"], images, pv["project_mat"], pv["ro_w"], pv["rd_w"], S=S, keep=False)
+        np.testing.assert_allclose(rgb.reshape(-1, 3).cpu().numpy(), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
+        np.testing.assert_allclose(depth.reshape(-1).cpu().numpy(), ref["depth_map"].numpy(), atol=1e-3, rtol=0)

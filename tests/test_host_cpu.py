@@ -1,0 +1,179 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic (CLI, config parsing,
+synthetic scene, tile sharding incl. a world_size-2 gloo gather), and loud failure without a GPU."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from pronerf_b200 import _abi
+    from pronerf_b200.build import build
+    build()
+    lib = _abi.lib()
+    header = open(os.path.join(ROOT, "include", "pronerf_b200.h")).read()
+    declared = set(re.findall(r"\b(pn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pn_ctx"}                       # struct tag
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pronerf_b200.h but not exported"
+        assert name in _abi.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_abi.SIGNATURES) <= declared
+    assert lib.pn_version() == 100
+    assert lib.pn_has_bf16_tier() in (0, 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    from pronerf_b200 import _abi, ops
+    assert _abi.lib().pn_device_check(0) != 0
+    assert "CUDA" in _abi.last_error() or "device" in _abi.last_error()
+    with pytest.raises(RuntimeError):
+        ops.embed(torch.zeros(4, 3), 10)
+    with pytest.raises(RuntimeError):
+        ops.Context("cuda:0")
+    from pronerf_b200.models import DoNeRFTRT
+    with pytest.raises(RuntimeError, match="no CPU"):
+        DoNeRFTRT(D=8, W=256, n_in=90, n_out=4, skip='auto')(torch.zeros(2, 63), torch.zeros(2, 27))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pronerf_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+    for f in ("pronerf/cli.py",):
+        assert "oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_state_dict_keys_match_reference_checkpoint_layout():
+    from pronerf_b200 import synth
+    from pronerf_b200.models import DoNeRFTRT, MinMaxRayEpiSamplerTRT_Net, MinMaxRaySamplerTRT_Net, load_state_dicts
+    nerf = DoNeRFTRT(D=8, W=256, n_in=90, n_out=4, skip='auto')
+    samp = MinMaxRaySamplerTRT_Net(D=6, W=256, input_ch=288, output_ch=27, skips=[10000], N_samples=8)
+    refn = MinMaxRayEpiSamplerTRT_Net(D=6, W=256, input_ch=144, output_ch=35, skips=[10000], N_samples=8)
+    assert sorted(nerf.state_dict()) == sorted([f"layers.{i}.{p}" for i in range(8) for p in ("weight", "bias")])
+    want = sorted([f"fc_backbone.{i}.{p}" for i in range(6) for p in ("weight", "bias")] + ["fc_output.weight", "fc_output.bias"])
+    assert sorted(samp.state_dict()) == want and sorted(refn.state_dict()) == want
+    assert [tuple(l.weight.shape) for l in nerf.layers] == [(256, 63)] + [(256, 256)] * 6 + [(4, 283)]
+    assert nerf.name == "relu1(256x80..63-7.63.)" and nerf.inputLocations == {0: (0, 63), 7: (63, 90)}
+    assert sum(p.numel() for p in nerf.parameters()) == 412272
+    assert sum(p.numel() for p in samp.parameters()) == 409883
+    assert sum(p.numel() for p in refn.parameters()) == 375075
+    load_state_dicts(nerf, samp, refn, synth.make_weights(seed=3))          # strict load of the checkpoint key set
+    with pytest.raises(NotImplementedError):
+        MinMaxRaySamplerTRT_Net(D=6, W=256, input_ch=288, output_ch=27, skips=[4], N_samples=8)
+
+
+def test_cli_and_config_parser():
+    import pronerf.cli as cli
+    from pronerf_b200.render import config_parser
+    p = cli.build_parser()
+    a = p.parse_args(["infer", "--render-test", "--max-images", "1", "--checkpoint", "x.tar", "--", "--no_reload", "--precision", "fp32"])
+    argv = cli.build_argv(a)
+    assert argv[:2] == ["--config", str(cli.DEFAULT_TRT_CONFIG)]
+    assert argv[2:] == ["--ft_path", "x.tar", "--render_test", "--max_images", "1", "--no_reload", "--precision", "fp32"]
+    args = config_parser().parse_args(argv)
+    assert (args.N_samples, args.N_point_ray_enc, args.num_neighbor, args.factor, args.llffhold) == (8, 48, 4, 8, 8)
+    assert args.use_viewdirs and not args.use_trt and args.no_reload and args.max_images == 1 and args.precision == "fp32"
+    assert args.mmnetdepth == 6 and args.mmnetwidth == 256 and args.mmnetskips == "[10000]"
+    e = p.parse_args(["eval"])
+    assert e.render_test is True
+    with pytest.raises(SystemExit):
+        cli.main(["train-stage1"])
+    out = subprocess.run([sys.executable, "-m", "pronerf.cli", "--help"], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0 and "infer" in out.stdout
+
+
+def test_synthetic_scene_is_deterministic_and_fern_shaped():
+    from pronerf_b200 import synth
+    a, b = synth.make_scene(factor=8), synth.make_scene(factor=8)
+    assert (a.H, a.W) == (378, 504) and abs(a.focal - 407.5625) < 1e-6
+    assert list(a.i_test) == [0, 8, 16] and len(a.i_ref) == 4 and not set(a.i_ref) & set(a.i_test)
+    np.testing.assert_array_equal(a.poses, b.poses)
+    np.testing.assert_array_equal(a.images_ref, b.images_ref)
+    assert a.images_ref.dtype == np.float32 and 0.0 <= a.images_ref.min() and a.images_ref.max() <= 1.0
+    assert np.allclose(a.images_ref * 255, np.round(a.images_ref * 255), atol=1e-4)      # 8-bit content
+    pb = synth.make_poses_bounds()
+    assert pb.shape == (20, 17) and pb.dtype == np.float64
+    assert abs(a.bds.min() - 1.0 / 0.75) < 1e-5
+    w1, w2 = synth.make_weights(seed=0), synth.make_weights(seed=0)
+    assert synth.weights_checksum(w1) == synth.weights_checksum(w2)
+    assert synth.weights_checksum(w1) != synth.weights_checksum(synth.make_weights(seed=1))
+
+
+def test_png_writer(tmp_path):
+    import zlib
+    from pronerf_b200.pngio import write_png
+    img = (np.arange(6 * 5 * 3) % 256).astype(np.uint8).reshape(6, 5, 3)
+    path = tmp_path / "a.png"
+    write_png(str(path), img)
+    data = path.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    i = data.index(b"IDAT")
+    n = int.from_bytes(data[i - 4:i], "big")
+    raw = zlib.decompress(data[i + 4:i + 4 + n])
+    rows = [raw[r * (1 + 15) + 1:(r + 1) * (1 + 15)] for r in range(6)]
+    assert b"".join(rows) == img.tobytes()
+    try:
+        import cv2
+        back = cv2.imread(str(path), cv2.IMREAD_COLOR)[..., ::-1]
+        np.testing.assert_array_equal(back, img)
+    except ImportError:
+        pass
+
+
+def test_shard_rows_partition():
+    from pronerf_b200.multigpu import all_shards, shard_rows
+    for H in (378, 3024, 7, 8):
+        for world in (1, 2, 4, 8):
+            sh = all_shards(H, world)
+            assert sh[0][0] == 0 and sum(n for _, n in sh) == H
+            for (a, n), (b, _) in zip(sh, sh[1:]):
+                assert a + n == b
+            assert max(n for _, n in sh) - min(n for _, n in sh) <= 1
+    with pytest.raises(ValueError):
+        shard_rows(10, 2, 2)
+
+
+def _gloo_worker(rank, world, port, H, W, q):
+    import torch.distributed as dist
+    from pronerf_b200.multigpu import gather_frame, shard_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(H * W * 4, dtype=torch.float32).reshape(H * W, 4)
+        row0, nrows = shard_rows(H, world, rank)
+        band = full[row0 * W:(row0 + nrows) * W]
+        rgb, depth = gather_frame(band[:, :3].contiguous(), band[:, 3].contiguous(), H, W, dst=0)
+        if rank == 0:
+            ok = torch.equal(rgb.reshape(-1, 3), full[:, :3]) and torch.equal(depth.reshape(-1), full[:, 3])
+            q.put(bool(ok))
+        else:
+            assert rgb is None and depth is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_gather_gloo(world):
+    """N>1 host path on CPU: band partition + ragged gather to rank 0 over gloo reassembles the frame exactly."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, 11, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
