@@ -8,8 +8,11 @@ struct NetTC {
   int n_layers = 0;
   int in_dim[kMaxLayers] = {0};
   int out_dim[kMaxLayers] = {0};
+  int net_id = -1;
   void* blob = nullptr;          // device: packed bf16 weight images + fp32 biases (layout in mlp_tc.cu)
   size_t blob_bytes = 0;
+  int* error_flag = nullptr;     // device: set by the kernel's barrier watchdog before it traps
+  bool supported = false;        // shape within the tensor-core kernel's limits
   bool loaded = false;
 };
 
