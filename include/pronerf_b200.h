@@ -49,6 +49,9 @@ const char* pn_last_error(void);
 int         pn_device_check(int device);
 /* 1 when the PN_PREC_BF16 (tcgen05) tier of the MLPs is compiled into this build, else 0. */
 int         pn_has_bf16_tier(void);
+/* Debug aid (not part of the render path): when set to a device buffer of 208 int64, CTA 0 of every subsequent
+ * bf16 MLP launch records clock64() stamps of its second tile's pipeline events; NULL switches it off. */
+int         pn_debug_tc_timeline(void* dev_buf_208_i64);
 
 /* ---- context: packed weights + scratch ------------------------------------------------------- */
 int  pn_ctx_create(int device, pn_ctx_t** out);

@@ -44,12 +44,12 @@ constexpr int OFF_RING = OFF_A + A_BYTES;
 constexpr int OFF_BIAS = OFF_RING + N_SLOTS * SLOT_BYTES;
 constexpr int OFF_WDIR = OFF_BIAS + BIAS_FLOATS * 4;
 constexpr int OFF_BAR = OFF_WDIR + WDIR_FLOATS * 4;
-// barriers: full[4], empty[4], a_ready[5], acc_full[2]  (8 bytes each) + tmem pointer
-constexpr int N_BARS = N_SLOTS * 2 + MAX_KB + 2;
+// barriers: full[4], empty[4], a_ready[8] (32-column halves), in_ready, acc_full[2]  (8 bytes each) + tmem pointer
+constexpr int N_BARS = N_SLOTS * 2 + 8 + 1 + 2;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;                           // producer, MMA issuer, 2 x 4 epilogue warps
 constexpr int TMEM_COLS = 512;
 
 struct Params {
@@ -74,6 +74,7 @@ struct Params {
   int head_lo[4];
   int head_act[3];
   int* error_flag;
+  long long* timeline;          // debug: CTA 0 writes clock64() stamps (see TL_* below), nullptr in production
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -215,6 +216,66 @@ __device__ __forceinline__ float head_apply_fast(float v, int kind) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// packed fp32x2 add (Blackwell FADD2): {o0,o1} = {x0,x1} + {b0,b1}
+__device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, float& o0, float& o1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 c, a, b;\n\t"
+      "mov.b64 {%0, %1}, c;\n\t}"
+      : "=f"(o0), "=f"(o1)
+      : "f"(x0), "f"(x1), "f"(b0), "f"(b1));
+}
+// two floats -> packed bf16x2 with ReLU folded into the conversion (lo in the low half)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float elu_fast(float v) {
+  // max(v,0) + (exp(min(v,0)) - 1): branch-free, one MUFU.EX2
+  float n = fminf(v, 0.f);
+  return fmaxf(v, 0.f) + (exp2f(n * 1.4426950408889634f) - 1.f);
+}
+
+// One 32-column half of a K block: accumulator columns -> bias + activation -> bf16 -> A operand (4 x 16 B per row).
+template <int ACT>
+__device__ __forceinline__ void epilogue_half(const float* v, const float4* bias4, uint32_t dst_block, int r, int c0) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 ba = bias4[2 * c], bb = bias4[2 * c + 1];
+    const float* x = v + 8 * c;
+    float y[8];
+    add2(x[0], x[1], ba.x, ba.y, y[0], y[1]);
+    add2(x[2], x[3], ba.z, ba.w, y[2], y[3]);
+    add2(x[4], x[5], bb.x, bb.y, y[4], y[5]);
+    add2(x[6], x[7], bb.z, bb.w, y[6], y[7]);
+    uint32_t w[4];
+    if (ACT == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = pack_bf16_relu(y[2 * u], y[2 * u + 1]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = pack_bf16(elu_fast(y[2 * u]), elu_fast(y[2 * u + 1]));
+    }
+    st_shared_v4(dst_block + a_chunk_off(r, c0 + c), w[0], w[1], w[2], w[3]);
+  }
+}
+
+// debug timeline slots (second tile of CTA 0): [0..7]*8 layers MMA half issue, epilogue events
+constexpr int TL_MMA = 0;        // + l*8 + kb*2 + half          (64)
+constexpr int TL_ACC = 64;       // + grp*8 + l                  (16)
+constexpr int TL_ARR = 80;       // + grp*64 + l*8 + kb*2 + half (128)
+constexpr int TL_N = 208;
+__device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
+  if (tl && on) tl[slot] = clock64();
+}
+
+constexpr int STAGE_BLOCK = 4;          // A block used as the layer-0 operand of 1-block first layers (NeRF), and as
+                                        // the fifth K block of the 288-wide sampler input
+
+// ACT: 0 ReLU / 1 ELU.  MODE: InputMode.
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -225,17 +286,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
   const uint32_t bar0 = base + OFF_BAR;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (N_SLOTS + s); };
-  auto bar_aready = [&](int kb) { return bar0 + 8u * (2 * N_SLOTS + kb); };
-  auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * N_SLOTS + MAX_KB + b); };
+  auto bar_aready = [&](int h) { return bar0 + 8u * (2 * N_SLOTS + h); };            // h = 32-column half block, 0..7
+  auto bar_inready = [&]() { return bar0 + 8u * (2 * N_SLOTS + 8); };                // staging block (STAGE_BLOCK)
+  auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * N_SLOTS + 9 + b); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (p.M + TILE_M - 1) / TILE_M;
+  constexpr bool kStaged = (MODE == IN_ENCODE || MODE == IN_LOAD2);   // 1-block first layer living in STAGE_BLOCK
+  const int kb0 = p.kblocks[0];
 
   // ---- one-time setup ----
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int kb = 0; kb < MAX_KB; ++kb) mbar_init(bar_aready(kb), 128);
+    for (int h = 0; h < 8; ++h) mbar_init(bar_aready(h), 4);
+    mbar_init(bar_inready(), 4);
     mbar_init(bar_accfull(0), 1);
     mbar_init(bar_accfull(1), 1);
     fence_barrier_init();
@@ -243,8 +308,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
   if (warp >= 2) {
     const int t = threadIdx.x - 64;
-    for (int i = t; i < p.n_layers * kHidden; i += 128) s_bias[i] = p.bias[i];
-    if (p.wdir) for (int i = t; i < 4 * 27; i += 128) s_wdir[i] = p.wdir[i];
+    for (int i = t; i < p.n_layers * kHidden; i += NTHREADS - 64) s_bias[i] = p.bias[i];
+    if (p.wdir) for (int i = t; i < 4 * 27; i += NTHREADS - 64) s_wdir[i] = p.wdir[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -273,41 +338,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     uint32_t g = 0, layer_ctr = 0;
-    uint32_t a_phase = 0;                                  // bit kb = parity to wait for on a_ready[kb]
+    uint32_t a_phase = 0;                                  // bit h = parity to wait for on a_ready[h]; bit 8 = in_ready
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int l = 0; l < p.n_layers; ++l, ++layer_ctr) {
         const uint32_t d_tmem = tmem_base + (layer_ctr & 1u) * kHidden;
         const uint32_t idesc = umma_idesc(p.n_pad[l]);
-        for (int kb = 0; kb < p.kblocks[l]; ++kb, ++g) {
+        const int nkb = p.kblocks[l];
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int slot = g % N_SLOTS;
-          mbar_wait(bar_aready(kb), (a_phase >> kb) & 1u, p.error_flag, 2);
-          a_phase ^= 1u << kb;
+          // which A block holds this K block, and which barriers publish it
+          const bool staged = (l == 0) && (kStaged || kb == STAGE_BLOCK);
+          const int blk = staged ? STAGE_BLOCK : kb;
           mbar_wait(bar_full(slot), (g / N_SLOTS) & 1, p.error_flag, 3);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint64_t a_desc = umma_desc(base + OFF_A + kb * A_BLOCK_BYTES);
-            const uint64_t b_desc = umma_desc(base + OFF_RING + slot * SLOT_BYTES);
+          const uint64_t a_desc = umma_desc(base + OFF_A + blk * A_BLOCK_BYTES);
+          const uint64_t b_desc = umma_desc(base + OFF_RING + slot * SLOT_BYTES);
 #pragma unroll
-            for (int s = 0; s < KBLK / 16; ++s)            // K = 16 per instruction: +32 bytes = +2 in desc units
-              umma_bf16(d_tmem, a_desc + 2u * s, b_desc + 2u * s, idesc, (kb | s) != 0 ? 1u : 0u);
+          for (int half = 0; half < 2; ++half) {
+            if (staged) {
+              if (half == 0) { mbar_wait(bar_inready(), (a_phase >> 8) & 1u, p.error_flag, 2); a_phase ^= 1u << 8; }
+            } else {
+              const int h = 2 * kb + half;
+              mbar_wait(bar_aready(h), (a_phase >> h) & 1u, p.error_flag, 2);
+              a_phase ^= 1u << h;
+            }
+            tc_fence_after();
+            if (lane == 0) {
+              tl_mark(p.timeline, blockIdx.x == 0 && tile == (long long)gridDim.x, TL_MMA + l * 8 + kb * 2 + half);
+#pragma unroll
+              for (int s = 2 * half; s < 2 * half + 2; ++s)   // K = 16 per instruction: +32 bytes = +2 in desc units
+                umma_bf16(d_tmem, a_desc + 2u * s, b_desc + 2u * s, idesc, (kb | s) != 0 ? 1u : 0u);
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
             umma_commit(bar_empty(slot));                  // slot is free once these MMAs have read it
-            if (kb == p.kblocks[l] - 1) umma_commit(bar_accfull(layer_ctr & 1u));
+            if (kb == nkb - 1) umma_commit(bar_accfull(layer_ctr & 1u));
           }
           __syncwarp();
         }
       }
     }
   } else {
-    // =============================== epilogue / operand producers (thread = row) ===============================
+    // =============================== epilogue / operand producers ===============================
+    // Two groups of 4 warps; group g drains K blocks kb % 2 == g of every trunk layer.  thread = row within a group.
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                           // row of the tile owned by this thread
     uint32_t acc_par = 0, layer_ctr = 0;
     const uint32_t a_base = base + OFF_A;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long row = tile * TILE_M + r;
+
+    // layer-0 operand of tile `t` (see MODE); `which` selects the K blocks this group fills
+    auto produce_input = [&](long long t) {
+      const long long row = t * TILE_M + r;
       const bool live = row < p.M;
-      // ---------- first-layer operand ----------
-      if (p.input_mode == IN_ENCODE) {
+      if (MODE == IN_ENCODE) {
+        // group 1 only: gamma_10(point) -> STAGE_BLOCK
         float x[3] = {0.f, 0.f, 0.f};
         if (live) { x[0] = p.in0[row * 3]; x[1] = p.in0[row * 3 + 1]; x[2] = p.in0[row * 3 + 2]; }
         float e[64];
@@ -318,11 +403,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
           for (int c = 0; c < 3; ++c) sincos_octaves(x[c], l, &e[3 + 6 * l + c], &e[6 + 6 * l + c]);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          st_shared_v4(a_base + a_chunk_off(r, c), pack_bf16(e[8 * c], e[8 * c + 1]), pack_bf16(e[8 * c + 2], e[8 * c + 3]),
-                       pack_bf16(e[8 * c + 4], e[8 * c + 5]), pack_bf16(e[8 * c + 6], e[8 * c + 7]));
+          st_shared_v4(a_base + STAGE_BLOCK * A_BLOCK_BYTES + a_chunk_off(r, c), pack_bf16(e[8 * c], e[8 * c + 1]),
+                       pack_bf16(e[8 * c + 2], e[8 * c + 3]), pack_bf16(e[8 * c + 4], e[8 * c + 5]),
+                       pack_bf16(e[8 * c + 6], e[8 * c + 7]));
         fence_proxy_async();
-        mbar_arrive(bar_aready(0));
-      } else if (p.input_mode == IN_PLUECKER) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_inready());
+      } else if (MODE == IN_PLUECKER) {
         // 6 Pluecker features of the ray, replicated P times (the P copies agree to 2.4e-7, far below bf16 resolution)
         float f6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (live) {
@@ -330,8 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
           pluecker6(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], f6);
         }
         uint32_t pk[3] = {pack_bf16(f6[0], f6[1]), pack_bf16(f6[2], f6[3]), pack_bf16(f6[4], f6[5])};
-        const int kmax = 6 * p.P;                          // 288
-        for (int kb = 0; kb < p.kblocks[0]; ++kb) {
+        const int kmax = 6 * p.P;
+        for (int kb = grp; kb < kb0; kb += 2) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t w[4];
@@ -343,15 +430,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
             st_shared_v4(a_base + kb * A_BLOCK_BYTES + a_chunk_off(r, c), w[0], w[1], w[2], w[3]);
           }
           fence_proxy_async();
-          mbar_arrive(bar_aready(kb));
+          __syncwarp();
+          if (lane == 0) {
+            if (kb == STAGE_BLOCK) mbar_arrive(bar_inready());
+            else { mbar_arrive(bar_aready(2 * kb)); mbar_arrive(bar_aready(2 * kb + 1)); }
+          }
         }
       } else {
         // IN_LOAD / IN_LOAD2: warp-cooperative coalesced row loads; lane owns elements (2*lane, 2*lane+1) of a K block
         const int k0 = p.k0;
-        for (int kb = 0; kb < p.kblocks[0]; ++kb) {
+        for (int kb = (kStaged ? 0 : grp); kb < kb0; kb += 2) {
+          const int blk = kStaged ? STAGE_BLOCK : kb;
           for (int rr = 0; rr < 32; ++rr) {
             const int trow = q * 32 + rr;
-            const long long grow = tile * TILE_M + trow;
+            const long long grow = t * TILE_M + trow;
             const int k = kb * 64 + 2 * lane;
             float v0 = 0.f, v1 = 0.f;
             if (grow < p.M) {
@@ -359,46 +451,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
               if (k < k0) v0 = __ldg(src + k);
               if (k + 1 < k0) v1 = __ldg(src + k + 1);
             }
-            st_shared_b32(a_base + kb * A_BLOCK_BYTES + a_chunk_off(trow, lane >> 2) + (lane & 3) * 4, pack_bf16(v0, v1));
+            st_shared_b32(a_base + blk * A_BLOCK_BYTES + a_chunk_off(trow, lane >> 2) + (lane & 3) * 4, pack_bf16(v0, v1));
           }
-          __syncwarp();
           fence_proxy_async();
-          mbar_arrive(bar_aready(kb));
+          __syncwarp();
+          if (lane == 0) {
+            if (blk == STAGE_BLOCK) mbar_arrive(bar_inready());
+            else { mbar_arrive(bar_aready(2 * kb)); mbar_arrive(bar_aready(2 * kb + 1)); }
+          }
         }
       }
+    };
 
-      // ---------- layers ----------
+    // prologue: first tile's operand (staged modes: group 1 owns the staging block)
+    if (!kStaged || grp == 1) produce_input(blockIdx.x);
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row = tile * TILE_M + r;
+      const bool live = row < p.M;
       for (int l = 0; l < p.n_layers; ++l, ++layer_ctr) {
         const uint32_t b = layer_ctr & 1u;
         mbar_wait(bar_accfull(b), (acc_par >> b) & 1u, p.error_flag, 4);
         acc_par ^= 1u << b;
         tc_fence_after();
+        const bool tl_on = blockIdx.x == 0 && tile == (long long)gridDim.x && q == 0 && lane == 0;
+        tl_mark(p.timeline, tl_on, TL_ACC + grp * 8 + l);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kHidden;
         if (l < last) {
-          const float* bl = s_bias + l * kHidden;
+          const float4* bl4 = reinterpret_cast<const float4*>(s_bias + l * kHidden);
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {                    // 64 output columns = K block j of the next layer
+          for (int kb = grp; kb < 4; kb += 2) {            // this group's K blocks of the next layer's operand
             float v[64];
-            tmem_ld32(taddr + j * 64, v);
-            tmem_ld32(taddr + j * 64 + 32, v + 32);
+            tmem_ld32(taddr + kb * 64, v);
+            tmem_ld32(taddr + kb * 64 + 32, v + 32);
+            float4 bias4[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bias4[i] = bl4[kb * 16 + i];       // overlaps the TMEM load latency
             tmem_wait_ld();
+            const uint32_t dst = a_base + kb * A_BLOCK_BYTES;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              uint32_t w[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int col = c * 8 + 2 * u;
-                float a0 = act_apply(v[col] + bl[j * 64 + col], p.act);
-                float a1 = act_apply(v[col + 1] + bl[j * 64 + col + 1], p.act);
-                w[u] = pack_bf16(a0, a1);
-              }
-              st_shared_v4(a_base + j * A_BLOCK_BYTES + a_chunk_off(r, c), w[0], w[1], w[2], w[3]);
+            for (int half = 0; half < 2; ++half) {
+              epilogue_half<ACT>(v + 32 * half, bias4 + 8 * half, dst, r, 4 * half);
+              fence_proxy_async();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_aready(2 * kb + half));
+              tl_mark(p.timeline, tl_on, TL_ARR + grp * 64 + l * 8 + kb * 2 + half);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar_aready(j));
           }
-        } else {
+          // staged first layers: group 1 builds the NEXT tile's layer-0 operand while the MMAs of this tile run
+          // (the staging block is free once layer 0's accumulator has been observed complete)
+          if (kStaged && grp == 1 && l == 1 && tile + gridDim.x < n_tiles) produce_input(tile + gridDim.x);
+        } else if (grp == 0) {
           // output layer: n_out <= 48 columns of the accumulator
           float v[48];
           const int npad = p.n_pad[last];
@@ -408,10 +512,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
           tmem_wait_ld();
           tc_fence_before();
           const float* bo = s_bias + last * kHidden;
-          if (p.wdir) {
+          if (kStaged) {
             // view-direction term of DoNeRFTRT's last layer: W7[:, 256:283] . gamma_4(viewdir)
             float g[27];
-            if (p.input_mode == IN_LOAD2) {
+            if (MODE == IN_LOAD2) {
 #pragma unroll
               for (int i = 0; i < 27; ++i) g[i] = live ? p.in1[row * 27 + i] : 0.f;
             } else {
@@ -449,6 +553,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
           }
         }
       }
+      // non-staged modes: next tile's operand goes into blocks the output layer has just finished reading
+      if (!kStaged && tile + gridDim.x < n_tiles) produce_input(tile + gridDim.x);
     }
   }
 
@@ -487,6 +593,9 @@ __global__ void pack_tc_wdir_kernel(const float* __restrict__ W, int in_dim, flo
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ host side
+static long long* g_tc_timeline = nullptr;
+void tc_set_timeline(long long* dev_buf) { g_tc_timeline = dev_buf; }
+
 struct TcLayout {
   int kblocks[kMaxLayers];
   int n_pad[kMaxLayers];
@@ -577,14 +686,24 @@ int tc_launch_mlp(const NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   for (int i = 0; i < 4; ++i) p.head_lo[i] = Lc.head_lo[i];
   for (int i = 0; i < 3; ++i) p.head_act[i] = Lc.head_act[i];
   p.error_flag = n.error_flag;
+  p.timeline = g_tc_timeline;
   if (Lc.input_mode == IN_PLUECKER && 6 * Lc.P != n.in_dim[0]) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
   int dev = 0, sms = 0;
   PN_CUDA_OK(cudaGetDevice(&dev));
   PN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  PN_CUDA_OK(cudaFuncSetAttribute(tc::mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
   long long tiles = (Lc.M + tc::TILE_M - 1) / tc::TILE_M;
   unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  tc::mlp_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);
+#define PN_TC_LAUNCH(ACT, MODE)                                                                                            \
+  do {                                                                                                                     \
+    PN_CUDA_OK(cudaFuncSetAttribute(tc::mlp_tc_kernel<ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC)); \
+    tc::mlp_tc_kernel<ACT, MODE><<<grid, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);                                      \
+  } while (0)
+  if (Lc.act == 0 && Lc.input_mode == IN_ENCODE) PN_TC_LAUNCH(0, IN_ENCODE);
+  else if (Lc.act == 0 && Lc.input_mode == IN_LOAD2) PN_TC_LAUNCH(0, IN_LOAD2);
+  else if (Lc.act == 1 && Lc.input_mode == IN_PLUECKER) PN_TC_LAUNCH(1, IN_PLUECKER);
+  else if (Lc.act == 1 && Lc.input_mode == IN_LOAD) PN_TC_LAUNCH(1, IN_LOAD);
+  else { set_error("tc: unsupported (activation, input mode) = (%d, %d)", Lc.act, Lc.input_mode); return PN_EINVAL; }
+#undef PN_TC_LAUNCH
   PN_LAUNCH_OK("mlp_tc_kernel");
   return PN_OK;
 }

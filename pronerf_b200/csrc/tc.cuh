@@ -20,6 +20,7 @@ void tc_free_net(NetTC& n);
 int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const int* out_dims, const float* const* W,
                 const float* const* b, cudaStream_t stream);
 bool tc_available();
+void tc_set_timeline(long long* dev_buf);   // debug: clock64 stamps of CTA 0's second tile (208 slots)
 int tc_launch_mlp(const NetTC& n, const MlpLaunch& L, cudaStream_t stream);
 
 }  // namespace pn
