@@ -1,93 +1,127 @@
-// bf16 tensor-core tier of the three MLPs: a persistent, warp-specialised, fully fused kernel on
-// tcgen05.mma with fp32 accumulators in TMEM and bulk-async (TMA engine) weight streaming.
+// Tensor-core tier of the three MLPs: a persistent, warp-specialised, fully fused kernel on tcgen05.mma
+// (fp16 operands, fp32 accumulators in TMEM) running on CTA PAIRS (cta_group::2) with two row tiles in flight.
 //
 //   sampler  MinMaxRaySamplerTRT_Net     helpers.py:1473-1507   288 -> 256 x6 (ELU) -> 27
 //   refine   MinMaxRayEpiSamplerTRT_Net  helpers.py:1509-1540   144 -> 256 x6 (ELU) -> 35
 //   NeRF     DoNeRFTRT                   helpers.py:1186-1343   63 -> 256 x7 (ReLU) -> [256 ++ 27] -> 4
 //
-// One CTA per SM (persistent over 128-row tiles).  Per tile and layer the GEMM is
-//   D[128 x N] (fp32, TMEM) = A[128 x K] (bf16, smem, K-major, 128B swizzle) * W^T (bf16, smem, K-major)
-// issued as M128 x N256 x K16 tcgen05.mma instructions by one thread.  Roles:
+// A cluster of two CTAs (one per SM of a TPC) walks 512-row units.  Each CTA owns two 128-row tiles ("slots" X and
+// Y); one tcgen05.mma.cta_group::2 instruction multiplies the 256 rows of a slot pair (128 from each CTA) by a
+// [256 x 16] weight step whose rows are split between the two CTAs' shared memories, so every SM reads half of the
+// weights and the instruction stream is issued once per pair (by the leader CTA's MMA thread).
 //
-//   warp 0      weight producer: streams every layer's weights, in consumption order, through a 4-slot ring
-//               (32 KB = one 64-wide K block of a 256-row layer) with cp.async.bulk + mbarrier complete_tx;
-//               the global image is pre-swizzled into the UMMA canonical layout so a linear copy lands it.
-//   warp 1      MMA issuer: waits for (activation K-block ready, weight slot full), issues 4 MMAs per K block,
-//               tcgen05.commit frees the slot; after a layer's last block commits "accumulator full".
-//   warps 2-5   epilogue / operand producers (thread = row): tcgen05.ld the accumulator 64 columns at a time,
-//               bias + ReLU/ELU, convert to bf16 and store straight into the next layer's A operand (the
-//               swizzle makes the row-per-thread 16-byte stores bank-conflict free), fence.proxy.async, and
-//               signal that K block -- so layer l+1 starts while layer l's epilogue is still draining.
-//               Two 256-column accumulators ping-pong in TMEM (512 columns) to make that overlap legal.
+//   D_slot[256 x N] (fp32, TMEM, 128 lanes per CTA) = A_slot[256 x K] (fp16, smem, K-major, 128B swizzle) * W^T
 //
-// The first-layer operand is generated in the kernel (frequency encoding, Pluecker features) or loaded;
-// the NeRF view-direction term (27 inputs of the last layer, identical for a ray's samples) is added on the
-// CUDA cores in the output epilogue, so the tensor-core part of the last layer is a clean K = 256, N = 16 GEMM.
-#include <cuda_bf16.h>
+// Pipeline (per slot the layers are strictly sequential; the two slots are half a period apart, so the tensor pipe
+// runs slot Y's layer while the CUDA cores drain slot X's accumulator):
+//
+//   warp 16     weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
+//               consumption order, through a 5-slot ring with cp.async.bulk + mbarrier complete_tx; the global image
+//               is pre-swizzled into the UMMA canonical layout so a linear copy lands a ready B operand.
+//   warp 17     leader: MMA issuer -- per (layer, slot): wait "operand ready", then per K block wait "weights
+//               landed in both CTAs", issue 4 MMAs (M256 N256 K16), tcgen05.commit frees the ring slot in both CTAs;
+//               after the last block commit "accumulator full" to both CTAs.
+//               follower: relay -- forwards "my half of the weights landed" to the leader's full barrier.
+//   warps 0-15  epilogue / operand producers (16 warps; warp = TMEM lane quadrant x 64-column group; thread = row):
+//               tcgen05.ld the accumulator, bias + ReLU/ELU, convert to fp16 and store straight into the slot's
+//               A operand for the next layer (the swizzle makes row-per-thread 16-byte stores conflict free), then
+//               fence.proxy.async and arrive on the leader's "operand ready" barrier (remote arrive from the follower).
+//
+// The first-layer operand is generated in the kernel (frequency encoding, Pluecker features) or loaded; the NeRF
+// view-direction term (27 inputs of the last layer, identical for a ray's samples) is a per-ray fp32 pre-pass added in
+// the output epilogue, so the tensor-core part of the last layer is a clean K = 256, N = 16 GEMM.
+#include <cuda_fp16.h>
 
 #include "tc.cuh"
 
 namespace pn {
 namespace tc {
 
-constexpr int TILE_M = 128;
-constexpr int KBLK = 64;                                // bf16 elements per 128-byte swizzle row
-constexpr int A_BLOCK_BYTES = TILE_M * 128;             // one K block of the activation tile: 16 KB
-constexpr int MAX_KB = 5;                               // first layer up to 320 inputs
-constexpr int A_BYTES = MAX_KB * A_BLOCK_BYTES;         // 80 KB
-constexpr int SLOT_BYTES = kHidden * 128;               // 32 KB
-constexpr int N_SLOTS = 4;
+constexpr int TILE_M = 128;                             // rows per CTA per slot
+constexpr int PAIR_M = 2 * TILE_M;                      // rows per MMA (cta_group::2)
+constexpr int UNIT_M = 2 * PAIR_M;                      // rows per cluster iteration (two slots)
+constexpr int A_BLOCK_BYTES = TILE_M * 128;             // one 64-wide K block of a slot's operand: 16 KB
+constexpr int A_SLOT_BYTES = 4 * A_BLOCK_BYTES;         // 64 KB
+constexpr int RING_SLOT_BYTES = (kHidden / 2) * 128;    // this CTA's half of a 256-row weight K block: 16 KB
+constexpr int N_RING = 5;
 constexpr int BIAS_FLOATS = kMaxLayers * kHidden;       // 8 KB
-constexpr int WDIR_FLOATS = 4 * 28;
 constexpr int OFF_A = 0;
-constexpr int OFF_RING = OFF_A + A_BYTES;
-constexpr int OFF_BIAS = OFF_RING + N_SLOTS * SLOT_BYTES;
-constexpr int OFF_WDIR = OFF_BIAS + BIAS_FLOATS * 4;
-constexpr int OFF_BAR = OFF_WDIR + WDIR_FLOATS * 4;
-// barriers: full[4], empty[4], a_ready[8] (32-column halves), in_ready, acc_full[2]  (8 bytes each) + tmem pointer
-constexpr int N_BARS = N_SLOTS * 2 + 8 + 1 + 2;
+constexpr int OFF_RING = OFF_A + 2 * A_SLOT_BYTES;
+constexpr int OFF_BIAS = OFF_RING + N_RING * RING_SLOT_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;
+// barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2], acc_full[2]
+constexpr int N_BARS = 2 * N_RING + 4;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
-constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B
-constexpr int NTHREADS = 320;                           // producer, MMA issuer, 2 x 4 epilogue warps
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B (swizzle atom)
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 576
+// The two single-thread roles get the HIGHEST warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
+// issuer (or weight producer) stalls the whole pair (measured: 2x slower issue as warp 1 behind four epilogue warps).
+constexpr int W_PRODUCER = N_EPI_WARPS;                 // warp 16 (scheduler 0)
+constexpr int W_MMA = N_EPI_WARPS + 1;                  // warp 17 (scheduler 1)
 constexpr int TMEM_COLS = 512;
+constexpr int MAX_PHASES = 10;
+
+enum EpiKind : int { EPI_HIDDEN = 0, EPI_MORE = 1, EPI_OUT = 2 };
+
+// One (layer, K range) step of a slot: MMAs over nkb K blocks, then an epilogue.
+struct Phase {
+  int layer;        // bias row / weight layer
+  int nkb;          // K blocks consumed
+  int k16_last;     // K=16 steps in the last block (1..4)
+  int n_pad;        // MMA N (multiple of 16)
+  int acc;          // 1: accumulate onto what the previous phase left in TMEM
+  int epi;          // EpiKind
+  uint32_t w_off;   // byte offset of the first chunk in the weight image
+};
 
 struct Params {
-  // network
-  int n_layers;
-  int kblocks[kMaxLayers];
-  int n_pad[kMaxLayers];
-  const uint8_t* wimg;          // chunk stream
+  int n_phases;
+  Phase ph[MAX_PHASES];
+  const uint8_t* wimg;
   const float* bias;            // [n_layers][256]
-  const float* wdir;            // [4][27] or nullptr
-  int k0;                       // true width of the first layer
+  int n_layers;
   int n_out;
-  int act;                      // 0 ReLU, 1 ELU
-  // io
-  int input_mode;
+  int k0;                       // width of the loaded first-layer operand (IN_LOAD / IN_LOAD2)
   const float* in0;
-  const float* in1;
-  int in_stride, in1_stride;
-  int S, P;
+  int in_stride;
+  const float* dirterm;         // NeRF: [M / dir_div][4] fp32 view-direction term of the last layer (no bias)
+  int dir_div;
   long long M;
   float* out;
   int head_lo[4];
   int head_act[3];
   int* error_flag;
-  long long* timeline;          // debug: CTA 0 writes clock64() stamps (see TL_* below), nullptr in production
+  long long* timeline;          // debug: leader CTA of cluster 0 stamps clock64() of its second iteration
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics (release at
+// CTA scope), as CUTLASS's ClusterBarrier does: a cluster-scope release would cost a MEMBAR.GPU per arrive, and
+// everything published through these barriers lives in the arriving CTA's own shared memory (performed locally,
+// made visible to the tensor-core proxy by fence.proxy.async beforehand).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
+      : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -122,20 +156,23 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrive (count 1) on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -163,6 +200,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (dense tile).
@@ -175,16 +217,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = n.
+// Instruction descriptor, kind::f16: D = f32 (bit 4), A = B = f16 (format 0), both K-major, M = 256 (pair), N = n.
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// byte offset of 16-byte chunk c (8 bf16) of row r inside one K block (swizzle: chunk ^= row % 8)
+// byte offset of 16-byte chunk c (8 halves) of row r inside one K block (swizzle: chunk ^= row % 8)
 __device__ __forceinline__ uint32_t a_chunk_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
@@ -195,27 +233,29 @@ __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 
-// sin / cos of x * 2^l for l = 0..L-1 with one range reduction: t = x / 2pi in turns, scaled exactly by powers
-// of two; the fractional turn goes to the SFU.  (bf16 tier: the operand is rounded to 8 bits anyway.)
-__device__ __forceinline__ void sincos_octaves(float x, int l, float* s, float* c) {
-  float t = x * 0.15915494309189535f * (float)(1 << l);
-  float f = t - rintf(t);
-  float a = f * 6.283185307179586f;
-  *s = __sinf(a);
-  *c = __cosf(a);
+// two floats -> packed f16x2 (lo in the low half), saturating to the largest finite half
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
-
-__device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == 0) return fmaxf(v, 0.f);
-  return v > 0.f ? v : (__expf(v) - 1.f);
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
-__device__ __forceinline__ float head_apply_fast(float v, int kind) {
-  if (kind == HEAD_SIGMOID) return 1.f / (1.f + __expf(-v));
-  if (kind == HEAD_TANH) return tanhf(v);
-  return v;
+// ELU on a packed pair, in half precision: max(h, 2^(min(h,0) * log2 e) - 1)   (for h > 0 the right side is 0 < h;
+// for h <= 0, e^h - 1 >= h).  One MUFU.EX2 per element; everything else is packed half2 arithmetic.
+__device__ __forceinline__ uint32_t pack_h2_elu(float lo, float hi) {
+  const uint32_t h = pack_h2(lo, hi);
+  uint32_t m, t, e, n, r;
+  asm("min.f16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(t) : "r"(m), "r"(0x3DC53DC5u));      // log2(e) = 1.4427 -> 0x3DC5
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(t));
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(n) : "r"(e), "r"(0xBC00BC00u));       // - 1.0
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h), "r"(n));
+  return r;
 }
-
-// ------------------------------------------------------------------------------------------------ the kernel
 // packed fp32x2 add (Blackwell FADD2): {o0,o1} = {x0,x1} + {b0,b1}
 __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, float& o0, float& o1) {
   asm("{\n\t.reg .b64 a, b, c;\n\t"
@@ -226,24 +266,57 @@ __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, flo
       : "=f"(o0), "=f"(o1)
       : "f"(x0), "f"(x1), "f"(b0), "f"(b1));
 }
-// two floats -> packed bf16x2 with ReLU folded into the conversion (lo in the low half)
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ float elu_fast(float v) {
-  // max(v,0) + (exp(min(v,0)) - 1): branch-free, one MUFU.EX2
-  float n = fminf(v, 0.f);
-  return fmaxf(v, 0.f) + (exp2f(n * 1.4426950408889634f) - 1.f);
+
+__device__ __forceinline__ float head_apply_fast(float v, int kind) {
+  if (kind == HEAD_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (kind == HEAD_TANH) return tanhf(v);
+  return v;
 }
 
-// One 32-column half of a K block: accumulator columns -> bias + activation -> bf16 -> A operand (4 x 16 B per row).
+// Element k (0..63) of the padded frequency encoding gamma_10(x) = [x, sin(2^l x), cos(2^l x)]_{l<10}, 0
+// (helpers.py:666-671).  One exact range reduction in turns (x * 2^l / 2pi, power-of-two scaling is exact), then the SFU.
+template <int K>
+__device__ __forceinline__ float encode_elem(const float* x) {
+  if (K < 3) return x[K];
+  if (K >= 63) return 0.f;
+  constexpr int j = (K >= 3 ? K - 3 : 0);
+  constexpr int l = j / 6, rem = j % 6, c = rem % 3;
+  constexpr bool is_cos = rem >= 3;
+  float t = x[c] * 0.15915494309189535f * (float)(1 << l);
+  t -= rintf(t);
+  if (is_cos) { t += 0.25f; }                            // cos(a) = sin(a + pi/2); |t| <= 0.75, still SFU-accurate
+  return __sinf(t * 6.283185307179586f);
+}
+// 16 consecutive elements [16*CG, 16*CG+16) as 8 packed half pairs
+template <int CG>
+__device__ __forceinline__ void encode16(const float* x, uint32_t* w) {
+#define PN_E(i) encode_elem<16 * CG + (i)>(x)
+  w[0] = pack_h2(PN_E(0), PN_E(1));   w[1] = pack_h2(PN_E(2), PN_E(3));
+  w[2] = pack_h2(PN_E(4), PN_E(5));   w[3] = pack_h2(PN_E(6), PN_E(7));
+  w[4] = pack_h2(PN_E(8), PN_E(9));   w[5] = pack_h2(PN_E(10), PN_E(11));
+  w[6] = pack_h2(PN_E(12), PN_E(13)); w[7] = pack_h2(PN_E(14), PN_E(15));
+#undef PN_E
+}
+
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// 32 accumulator columns -> bias + activation -> fp16 -> 4 x 16 B of this thread's row in the next layer's operand.
+// The TMEM load and the 8 bias loads are issued together (volatile asm keeps them ahead of the wait), so one latency is
+// exposed per call and the other epilogue warps of the scheduler fill it.  row_base = block + row offset, xr = (r & 7) << 4.
 template <int ACT>
-__device__ __forceinline__ void epilogue_half(const float* v, const float4* bias4, uint32_t dst_block, int r, int c0) {
+__device__ __forceinline__ void epilogue_half(uint32_t taddr, uint32_t bias_addr, uint32_t row_base, uint32_t xr, int c0) {
+  float v[32];
+  float4 b[8];
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = ld_shared_v4f(bias_addr + 16u * i);
+  tmem_wait_ld();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float4 ba = bias4[2 * c], bb = bias4[2 * c + 1];
+    const float4 ba = b[2 * c], bb = b[2 * c + 1];
     const float* x = v + 8 * c;
     float y[8];
     add2(x[0], x[1], ba.x, ba.y, y[0], y[1]);
@@ -251,332 +324,343 @@ __device__ __forceinline__ void epilogue_half(const float* v, const float4* bias
     add2(x[4], x[5], bb.x, bb.y, y[4], y[5]);
     add2(x[6], x[7], bb.z, bb.w, y[6], y[7]);
     uint32_t w[4];
-    if (ACT == 0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = pack_bf16_relu(y[2 * u], y[2 * u + 1]);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = pack_bf16(elu_fast(y[2 * u]), elu_fast(y[2 * u + 1]));
-    }
-    st_shared_v4(dst_block + a_chunk_off(r, c0 + c), w[0], w[1], w[2], w[3]);
+    for (int u = 0; u < 4; ++u) w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : pack_h2_elu(y[2 * u], y[2 * u + 1]);
+    st_shared_v4(row_base + ((uint32_t)((c0 + c) << 4) ^ xr), w[0], w[1], w[2], w[3]);
   }
 }
 
-// debug timeline slots (second tile of CTA 0): [0..7]*8 layers MMA half issue, epilogue events
-constexpr int TL_MMA = 0;        // + l*8 + kb*2 + half          (64)
-constexpr int TL_ACC = 64;       // + grp*8 + l                  (16)
-constexpr int TL_ARR = 80;       // + grp*64 + l*8 + kb*2 + half (128)
+// debug timeline slots (leader CTA of cluster 0, its second iteration): index = base + phase * 2 + slot
+constexpr int TL_MMA0 = 0;       // MMA thread: operand-ready wait satisfied
+constexpr int TL_MMA1 = 20;      // MMA thread: last MMA of the phase issued
+constexpr int TL_ACC = 40;       // epilogue warp 0: accumulator-full observed
+constexpr int TL_ARR = 60;       // epilogue warp 0: arrived on operand-ready
+constexpr int TL_ARRL = 80;      // epilogue warp 15: arrived on operand-ready
+constexpr int TL_EPI = 100;     // epilogue warp 0, phase 2 slot 0: [0] first half stored, [1] second half stored, [2] proxy fence done
+constexpr int TL_SYNC = 140;    // clock64() right after the setup cluster barrier: [0] leader, [1] follower (per-SM clock offset)
 constexpr int TL_N = 208;
 __device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
   if (tl && on) tl[slot] = clock64();
 }
 
-constexpr int STAGE_BLOCK = 4;          // A block used as the layer-0 operand of 1-block first layers (NeRF), and as
-                                        // the fifth K block of the 288-wide sampler input
-
 // ACT: 0 ReLU / 1 ELU.  MODE: InputMode.
 template <int ACT, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;              // 1024-byte aligned (swizzle atom)
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;              // identical in both CTAs of the pair
   uint8_t* sm = smem_raw + (base - raw_addr);
   float* s_bias = reinterpret_cast<float*>(sm + OFF_BIAS);
-  float* s_wdir = reinterpret_cast<float*>(sm + OFF_WDIR);
   const uint32_t bar0 = base + OFF_BAR;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (N_SLOTS + s); };
-  auto bar_aready = [&](int h) { return bar0 + 8u * (2 * N_SLOTS + h); };            // h = 32-column half block, 0..7
-  auto bar_inready = [&]() { return bar0 + 8u * (2 * N_SLOTS + 8); };                // staging block (STAGE_BLOCK)
-  auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * N_SLOTS + 9 + b); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (N_RING + s); };
+  auto bar_aready = [&](int t) { return bar0 + 8u * (2 * N_RING + t); };
+  auto bar_accfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 2 + t); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long n_tiles = (p.M + TILE_M - 1) / TILE_M;
-  constexpr bool kStaged = (MODE == IN_ENCODE || MODE == IN_LOAD2);   // 1-block first layer living in STAGE_BLOCK
-  const int kb0 = p.kblocks[0];
+  const uint32_t rank = cluster_ctarank();
+  const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const long long n_pairs = (p.M + PAIR_M - 1) / PAIR_M;          // 256-row MMA tiles
+  // iteration `it` of this cluster covers pair tiles T0 = (it * n_clusters + cluster_id) * 2 (slot 0) and T0 + 1 (slot 1)
+  auto pair0 = [&](long long it) { return (it * n_clusters + cluster_id) * 2; };
 
   // ---- one-time setup ----
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int h = 0; h < 8; ++h) mbar_init(bar_aready(h), 4);
-    mbar_init(bar_inready(), 4);
-    mbar_init(bar_accfull(0), 1);
-    mbar_init(bar_accfull(1), 1);
+  if (warp == W_MMA && lane == 0) {
+    for (int s = 0; s < N_RING; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_aready(t), 2 * N_EPI_WARPS); mbar_init(bar_accfull(t), 1); }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < p.n_layers * kHidden; i += NTHREADS - 64) s_bias[i] = p.bias[i];
-    if (p.wdir) for (int i = t; i < 4 * 27; i += NTHREADS - 64) s_wdir[i] = p.wdir[i];
+  if (warp == W_PRODUCER) tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
+  if (warp < N_EPI_WARPS) {
+    for (int i = threadIdx.x; i < p.n_layers * kHidden; i += N_EPI_WARPS * 32) s_bias[i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int last = p.n_layers - 1;
+  if (p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
 
-  if (warp == 0) {
-    // =============================== weight producer ===============================
+  if (warp == W_PRODUCER) {
+    // =============================== weight producer (both CTAs) ===============================
     if (lane == 0) {
-      uint32_t g = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint8_t* src = p.wimg;
-        for (int l = 0; l < p.n_layers; ++l) {
-          const uint32_t bytes = (uint32_t)p.n_pad[l] * 128u;
-          for (int kb = 0; kb < p.kblocks[l]; ++kb, ++g) {
-            const int slot = g % N_SLOTS;
-            mbar_wait(bar_empty(slot), ((g / N_SLOTS) & 1) ^ 1, p.error_flag, 1);
-            mbar_arrive_expect_tx(bar_full(slot), bytes);
-            bulk_copy_g2s(base + OFF_RING + slot * SLOT_BYTES, src, bytes, bar_full(slot));
-            src += bytes;
+      uint32_t slot = 0, ring_par = 1;                       // empty barriers: the first pass over the ring is free
+      for (long long it = 0; pair0(it) < n_pairs; ++it) {
+        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
+        for (int ph = 0; ph < p.n_phases; ++ph) {
+          const int nkb = p.ph[ph].nkb;
+          const uint32_t half_bytes = (uint32_t)p.ph[ph].n_pad * 64u;
+          const uint8_t* src0 = p.wimg + p.ph[ph].w_off + rank * half_bytes;
+          for (int t = 0; t < nv; ++t) {
+            const uint8_t* src = src0;
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(bar_empty(slot), ring_par, p.error_flag, 1);
+              mbar_arrive_expect_tx(bar_full(slot), half_bytes);
+              bulk_copy_g2s(base + OFF_RING + slot * RING_SLOT_BYTES, src, half_bytes, bar_full(slot));
+              src += 2 * half_bytes;
+              if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
+            }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    uint32_t g = 0, layer_ctr = 0;
-    uint32_t a_phase = 0;                                  // bit h = parity to wait for on a_ready[h]; bit 8 = in_ready
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int l = 0; l < p.n_layers; ++l, ++layer_ctr) {
-        const uint32_t d_tmem = tmem_base + (layer_ctr & 1u) * kHidden;
-        const uint32_t idesc = umma_idesc(p.n_pad[l]);
-        const int nkb = p.kblocks[l];
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int slot = g % N_SLOTS;
-          // which A block holds this K block, and which barriers publish it
-          const bool staged = (l == 0) && (kStaged || kb == STAGE_BLOCK);
-          const int blk = staged ? STAGE_BLOCK : kb;
-          mbar_wait(bar_full(slot), (g / N_SLOTS) & 1, p.error_flag, 3);
-          const uint64_t a_desc = umma_desc(base + OFF_A + blk * A_BLOCK_BYTES);
-          const uint64_t b_desc = umma_desc(base + OFF_RING + slot * SLOT_BYTES);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (staged) {
-              if (half == 0) { mbar_wait(bar_inready(), (a_phase >> 8) & 1u, p.error_flag, 2); a_phase ^= 1u << 8; }
-            } else {
-              const int h = 2 * kb + half;
-              mbar_wait(bar_aready(h), (a_phase >> h) & 1u, p.error_flag, 2);
-              a_phase ^= 1u << h;
-            }
+  } else if (warp == W_MMA) {
+    if (lane == 0 && rank != 0) {
+      // =============================== follower: weights-landed relay ===============================
+      uint32_t slot = 0, ring_par = 0;
+      for (long long it = 0; pair0(it) < n_pairs; ++it) {
+        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
+        for (int ph = 0; ph < p.n_phases; ++ph) {
+          const int n = nv * p.ph[ph].nkb;
+          for (int i = 0; i < n; ++i) {
+            mbar_wait(bar_full(slot), ring_par, p.error_flag, 5);
+            mbar_arrive_cluster(bar_full(slot), 0);
+            if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
+          }
+        }
+      }
+    } else if (rank == 0) {
+      // =============================== leader: MMA issuer ===============================
+      // The whole warp walks the loop convergently (waits included) and one elected lane issues: with warp-uniform
+      // control flow every tcgen05 operand lives in uniform registers.  A single thread retires one dependent
+      // instruction every ~5 cycles, so this loop is kept to a few dozen instructions per K block (4 MMAs = 512 cycles).
+      uint32_t slot = 0, ring_par = 0;
+      uint32_t ar_par = 0;                                   // bit t = parity to wait for on a_ready[t]
+      constexpr uint32_t kDescHi = 0x40004040u;              // SBO 1024 B | descriptor version 1 | SWIZZLE_128B
+      const uint32_t a_lo0 = (((base + OFF_A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo0 = (((base + OFF_RING) >> 4) & 0x3FFFu) | (1u << 16);
+      for (long long it = 0; pair0(it) < n_pairs; ++it) {
+        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
+        const bool tl_on = blockIdx.x == 0 && it == 1 && lane == 0;
+        for (int ph = 0; ph < p.n_phases; ++ph) {
+          const int nkb = p.ph[ph].nkb, k16_last = p.ph[ph].k16_last;
+          const uint32_t acc0 = (uint32_t)p.ph[ph].acc;
+          const uint32_t idesc = umma_idesc(p.ph[ph].n_pad);
+          for (int t = 0; t < nv; ++t) {
+            mbar_wait(bar_aready(t), (ar_par >> t) & 1u, p.error_flag, 2);
+            ar_par ^= 1u << t;
             tc_fence_after();
-            if (lane == 0) {
-              tl_mark(p.timeline, blockIdx.x == 0 && tile == (long long)gridDim.x, TL_MMA + l * 8 + kb * 2 + half);
-#pragma unroll
-              for (int s = 2 * half; s < 2 * half + 2; ++s)   // K = 16 per instruction: +32 bytes = +2 in desc units
-                umma_bf16(d_tmem, a_desc + 2u * s, b_desc + 2u * s, idesc, (kb | s) != 0 ? 1u : 0u);
+            tl_mark(p.timeline, tl_on, TL_MMA0 + ph * 2 + t);
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * kHidden;
+            uint32_t a_lo = a_lo0 + (uint32_t)t * (A_SLOT_BYTES >> 4);
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+              tc_fence_after();
+              const uint64_t a_desc = ((uint64_t)kDescHi << 32) | a_lo;
+              const uint64_t b_desc = ((uint64_t)kDescHi << 32) | (b_lo0 + slot * (RING_SLOT_BYTES >> 4));
+              if (elect_one()) {
+                if (kb + 1 < nkb || k16_last == 4) {         // K = 16 per instruction: +32 bytes = +2 in descriptor units
+                  umma_f16_pair(d_tmem, a_desc, b_desc, idesc, acc0 | (uint32_t)kb);
+                  umma_f16_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                  umma_f16_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                  umma_f16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                } else {
+                  for (int s2 = 0; s2 < k16_last; ++s2) umma_f16_pair(d_tmem, a_desc + 2u * s2, b_desc + 2u * s2, idesc, acc0 | (uint32_t)(kb | s2));
+                }
+                umma_commit_pair(bar_empty(slot));           // ring slot is free (in both CTAs) once these MMAs have read it
+              }
+              __syncwarp();
+              a_lo += A_BLOCK_BYTES >> 4;
+              if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
             }
+            if (elect_one()) umma_commit_pair(bar_accfull(t));
             __syncwarp();
+            tl_mark(p.timeline, tl_on, TL_MMA1 + ph * 2 + t);
           }
-          if (lane == 0) {
-            umma_commit(bar_empty(slot));                  // slot is free once these MMAs have read it
-            if (kb == nkb - 1) umma_commit(bar_accfull(layer_ctr & 1u));
-          }
-          __syncwarp();
         }
       }
     }
   } else {
-    // =============================== epilogue / operand producers ===============================
-    // Two groups of 4 warps; group g drains K blocks kb % 2 == g of every trunk layer.  thread = row within a group.
-    const int grp = (warp - 2) >> 2;
+    // =============================== epilogue / operand producers (both CTAs) ===============================
+    const int ew = warp;
+    const int cg = ew >> 2;                                // 64-column group = K block of the next layer's operand
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                           // row of the tile owned by this thread
-    uint32_t acc_par = 0, layer_ctr = 0;
     const uint32_t a_base = base + OFF_A;
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), xr = (uint32_t)(r & 7) << 4;
+    uint32_t acc_par = 0;
 
-    // layer-0 operand of tile `t` (see MODE); `which` selects the K blocks this group fills
-    auto produce_input = [&](long long t) {
-      const long long row = t * TILE_M + r;
-      const bool live = row < p.M;
+    // global row of this thread in slot t of iteration it
+    auto row_of = [&](long long it, int t) { return (pair0(it) + t) * PAIR_M + (long long)rank * TILE_M + r; };
+
+    // --- first-layer operand, "compute" modes: 16 elements per thread, computed ahead of time into `pre` ---
+    auto precompute_input = [&](long long row, uint32_t* pre) {
       if (MODE == IN_ENCODE) {
-        // group 1 only: gamma_10(point) -> STAGE_BLOCK
         float x[3] = {0.f, 0.f, 0.f};
-        if (live) { x[0] = p.in0[row * 3]; x[1] = p.in0[row * 3 + 1]; x[2] = p.in0[row * 3 + 2]; }
-        float e[64];
-        e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; e[63] = 0.f;
-#pragma unroll
-        for (int l = 0; l < 10; ++l)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) sincos_octaves(x[c], l, &e[3 + 6 * l + c], &e[6 + 6 * l + c]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(a_base + STAGE_BLOCK * A_BLOCK_BYTES + a_chunk_off(r, c), pack_bf16(e[8 * c], e[8 * c + 1]),
-                       pack_bf16(e[8 * c + 2], e[8 * c + 3]), pack_bf16(e[8 * c + 4], e[8 * c + 5]),
-                       pack_bf16(e[8 * c + 6], e[8 * c + 7]));
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_inready());
+        if (row < p.M) { x[0] = __ldg(p.in0 + row * 3); x[1] = __ldg(p.in0 + row * 3 + 1); x[2] = __ldg(p.in0 + row * 3 + 2); }
+        switch (cg) {
+          case 0: encode16<0>(x, pre); break;
+          case 1: encode16<1>(x, pre); break;
+          case 2: encode16<2>(x, pre); break;
+          default: encode16<3>(x, pre); break;
+        }
       } else if (MODE == IN_PLUECKER) {
-        // 6 Pluecker features of the ray, replicated P times (the P copies agree to 2.4e-7, far below bf16 resolution)
-        float f6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
+        // the 6 Pluecker features of the ray; the sampler's P replicated copies are folded into the weights
+        // (W_eff = sum over copies, tc_load_net), so the operand is 6 wide
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre[i] = 0u;
+        if (cg == 0 && row < p.M) {
           const float* ray = p.in0 + row * p.in_stride;
-          pluecker6(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], f6);
-        }
-        uint32_t pk[3] = {pack_bf16(f6[0], f6[1]), pack_bf16(f6[2], f6[3]), pack_bf16(f6[4], f6[5])};
-        const int kmax = 6 * p.P;
-        for (int kb = grp; kb < kb0; kb += 2) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              int k = kb * 64 + c * 8 + 2 * j;             // even element index; pairs never straddle a feature pair
-              w[j] = (k < kmax) ? pk[(k % 6) >> 1] : 0u;
-            }
-            st_shared_v4(a_base + kb * A_BLOCK_BYTES + a_chunk_off(r, c), w[0], w[1], w[2], w[3]);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (kb == STAGE_BLOCK) mbar_arrive(bar_inready());
-            else { mbar_arrive(bar_aready(2 * kb)); mbar_arrive(bar_aready(2 * kb + 1)); }
-          }
-        }
-      } else {
-        // IN_LOAD / IN_LOAD2: warp-cooperative coalesced row loads; lane owns elements (2*lane, 2*lane+1) of a K block
-        const int k0 = p.k0;
-        for (int kb = (kStaged ? 0 : grp); kb < kb0; kb += 2) {
-          const int blk = kStaged ? STAGE_BLOCK : kb;
-          for (int rr = 0; rr < 32; ++rr) {
-            const int trow = q * 32 + rr;
-            const long long grow = t * TILE_M + trow;
-            const int k = kb * 64 + 2 * lane;
-            float v0 = 0.f, v1 = 0.f;
-            if (grow < p.M) {
-              const float* src = p.in0 + grow * p.in_stride;
-              if (k < k0) v0 = __ldg(src + k);
-              if (k + 1 < k0) v1 = __ldg(src + k + 1);
-            }
-            st_shared_b32(a_base + blk * A_BLOCK_BYTES + a_chunk_off(trow, lane >> 2) + (lane & 3) * 4, pack_bf16(v0, v1));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (blk == STAGE_BLOCK) mbar_arrive(bar_inready());
-            else { mbar_arrive(bar_aready(2 * kb)); mbar_arrive(bar_aready(2 * kb + 1)); }
-          }
+          float f6[6];
+          pluecker6(__ldg(ray), __ldg(ray + 1), __ldg(ray + 2), __ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5), f6);
+          pre[0] = pack_h2(f6[0], f6[1]); pre[1] = pack_h2(f6[2], f6[3]); pre[2] = pack_h2(f6[4], f6[5]);
         }
       }
     };
-
-    // prologue: first tile's operand (staged modes: group 1 owns the staging block)
-    if (!kStaged || grp == 1) produce_input(blockIdx.x);
-
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long row = tile * TILE_M + r;
-      const bool live = row < p.M;
-      for (int l = 0; l < p.n_layers; ++l, ++layer_ctr) {
-        const uint32_t b = layer_ctr & 1u;
-        mbar_wait(bar_accfull(b), (acc_par >> b) & 1u, p.error_flag, 4);
-        acc_par ^= 1u << b;
-        tc_fence_after();
-        const bool tl_on = blockIdx.x == 0 && tile == (long long)gridDim.x && q == 0 && lane == 0;
-        tl_mark(p.timeline, tl_on, TL_ACC + grp * 8 + l);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kHidden;
-        if (l < last) {
-          const float4* bl4 = reinterpret_cast<const float4*>(s_bias + l * kHidden);
-#pragma unroll 1
-          for (int kb = grp; kb < 4; kb += 2) {            // this group's K blocks of the next layer's operand
-            float v[64];
-            tmem_ld32(taddr + kb * 64, v);
-            tmem_ld32(taddr + kb * 64 + 32, v + 32);
-            float4 bias4[16];
+    auto store_pre = [&](int t, const uint32_t* pre) {
+      const uint32_t dst = a_base + t * A_SLOT_BYTES;      // block 0
+      st_shared_v4(dst + a_chunk_off(r, 2 * cg), pre[0], pre[1], pre[2], pre[3]);
+      st_shared_v4(dst + a_chunk_off(r, 2 * cg + 1), pre[4], pre[5], pre[6], pre[7]);
+    };
+    // --- first-layer operand, "load" modes: warp (q, cg) loads rows q*32 + cg*8 .. +7 of K blocks [kb_lo, kb_lo+nblk) ---
+    auto load_input = [&](long long it, int t, int kb_lo, int nblk) {
+      const long long row_base = (pair0(it) + t) * PAIR_M + (long long)rank * TILE_M;
+      const int k0 = p.k0;
+      for (int kb = 0; kb < nblk; ++kb) {
+        const uint32_t dst = a_base + t * A_SLOT_BYTES + kb * A_BLOCK_BYTES;
+        const int k = (kb_lo + kb) * 64 + 2 * lane;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) bias4[i] = bl4[kb * 16 + i];       // overlaps the TMEM load latency
-            tmem_wait_ld();
-            const uint32_t dst = a_base + kb * A_BLOCK_BYTES;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              epilogue_half<ACT>(v + 32 * half, bias4 + 8 * half, dst, r, 4 * half);
-              fence_proxy_async();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_aready(2 * kb + half));
-              tl_mark(p.timeline, tl_on, TL_ARR + grp * 64 + l * 8 + kb * 2 + half);
-            }
+        for (int i = 0; i < 8; ++i) {
+          const int trow = q * 32 + cg * 8 + i;
+          const long long grow = row_base + trow;
+          float v0 = 0.f, v1 = 0.f;
+          if (grow < p.M) {
+            const float* src = p.in0 + grow * p.in_stride;
+            if (k < k0) v0 = __ldg(src + k);
+            if (k + 1 < k0) v1 = __ldg(src + k + 1);
           }
-          // staged first layers: group 1 builds the NEXT tile's layer-0 operand while the MMAs of this tile run
-          // (the staging block is free once layer 0's accumulator has been observed complete)
-          if (kStaged && grp == 1 && l == 1 && tile + gridDim.x < n_tiles) produce_input(tile + gridDim.x);
-        } else if (grp == 0) {
-          // output layer: n_out <= 48 columns of the accumulator
-          float v[48];
-          const int npad = p.n_pad[last];
-          tmem_ld16(taddr, v);
-          if (npad > 16) tmem_ld16(taddr + 16, v + 16);
-          if (npad > 32) tmem_ld16(taddr + 32, v + 32);
-          tmem_wait_ld();
-          tc_fence_before();
-          const float* bo = s_bias + last * kHidden;
-          if (kStaged) {
-            // view-direction term of DoNeRFTRT's last layer: W7[:, 256:283] . gamma_4(viewdir)
-            float g[27];
-            if (MODE == IN_LOAD2) {
-#pragma unroll
-              for (int i = 0; i < 27; ++i) g[i] = live ? p.in1[row * 27 + i] : 0.f;
-            } else {
-              float d[3] = {0.f, 0.f, 0.f};
-              if (live) {
-                const float* vd = p.in1 + (row / p.S) * p.in1_stride;
-                d[0] = vd[0]; d[1] = vd[1]; d[2] = vd[2];
-              }
-              g[0] = d[0]; g[1] = d[1]; g[2] = d[2];
-#pragma unroll
-              for (int lv = 0; lv < 4; ++lv)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) sincos_octaves(d[c], lv, &g[3 + 6 * lv + c], &g[6 + 6 * lv + c]);
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              float a = v[o] + bo[o];
-#pragma unroll
-              for (int i = 0; i < 27; ++i) a = fmaf(s_wdir[o * 27 + i], g[i], a);
-              v[o] = a;
-            }
-            if (live) *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
-          } else if (live) {
-            float* orow = p.out + row * p.n_out;
-#pragma unroll
-            for (int o = 0; o < 48; ++o) {
-              if (o < p.n_out) {
-                int kind = HEAD_NONE;
-#pragma unroll
-                for (int gq = 0; gq < 3; ++gq)
-                  if (o >= p.head_lo[gq] && o < p.head_lo[gq + 1]) kind = p.head_act[gq];
-                orow[o] = head_apply_fast(v[o] + bo[o], kind);
-              }
-            }
-          }
+          st_shared_b32(dst + a_chunk_off(trow, lane >> 2) + (lane & 3) * 4, pack_h2(v0, v1));
         }
       }
-      // non-staged modes: next tile's operand goes into blocks the output layer has just finished reading
-      if (!kStaged && tile + gridDim.x < n_tiles) produce_input(tile + gridDim.x);
+    };
+    constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER);
+    const int kb_first = p.ph[0].nkb;                      // K blocks of the first phase (<= 4)
+    auto publish = [&](int t, long long* tl = nullptr) {   // operand of slot t is complete (from this warp's side)
+      fence_proxy_async();
+      if (tl) *tl = clock64();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_aready(t), 0);
+    };
+
+    // prologue: first unit's operands
+    if (pair0(0) < n_pairs) {
+      const int nv = (pair0(0) + 1 < n_pairs) ? 2 : 1;
+      for (int t = 0; t < nv; ++t) {
+        if (kCompute) {
+          uint32_t pre[8];
+          precompute_input(row_of(0, t), pre);
+          store_pre(t, pre);
+        } else {
+          load_input(0, t, 0, kb_first);
+        }
+        publish(t);
+      }
+    }
+
+    for (long long it = 0; pair0(it) < n_pairs; ++it) {
+      const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
+      const bool tl_on = blockIdx.x == 0 && it == 1 && lane == 0;
+      for (int ph = 0; ph < p.n_phases; ++ph) {
+        const Phase& P = p.ph[ph];
+        for (int t = 0; t < nv; ++t) {
+          // does slot t have a tile in the next iteration?
+          const bool has_next = (P.epi == EPI_OUT) && (pair0(it + 1) + t < n_pairs);
+          uint32_t pre[8];
+          if (kCompute && has_next) precompute_input(row_of(it + 1, t), pre);   // overlaps the wait below
+          float4 dterm = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((MODE == IN_ENCODE || MODE == IN_LOAD2) && P.epi == EPI_OUT && cg == 0) {
+            const long long row = row_of(it, t);
+            if (row < p.M) dterm = __ldg(reinterpret_cast<const float4*>(p.dirterm) + row / p.dir_div);
+          }
+          mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+          acc_par ^= 1u << t;
+          tc_fence_after();
+          tl_mark(p.timeline, tl_on && ew == 0, TL_ACC + ph * 2 + t);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * kHidden;
+          if (P.epi == EPI_HIDDEN) {
+            long long* tl = (p.timeline && tl_on && ew == 0 && ph == 2 && t == 0) ? p.timeline + TL_EPI : nullptr;
+            const uint32_t bias_addr = base + OFF_BIAS + (uint32_t)(P.layer * kHidden + cg * 64) * 4u;
+            const uint32_t row_base = a_base + t * A_SLOT_BYTES + cg * A_BLOCK_BYTES + row_off;
+            epilogue_half<ACT>(taddr + cg * 64, bias_addr, row_base, xr, 0);
+            if (tl) tl[0] = clock64();
+            epilogue_half<ACT>(taddr + cg * 64 + 32, bias_addr + 128u, row_base, xr, 4);
+            if (tl) tl[1] = clock64();
+          } else if (P.epi == EPI_MORE) {
+            // first layer wider than 256: the remaining K blocks replace the ones just consumed
+            load_input(it, t, kb_first, p.ph[ph + 1].nkb);
+          } else {
+            if (cg == 0) {
+              // output layer: n_out <= 48 columns of the accumulator
+              const long long row = row_of(it, t);
+              const bool live = row < p.M;
+              float v[48];
+              tmem_ld16(taddr, v);
+              if (P.n_pad > 16) tmem_ld16(taddr + 16, v + 16);
+              if (P.n_pad > 32) tmem_ld16(taddr + 32, v + 32);
+              tmem_wait_ld();
+              const float* bo = s_bias + P.layer * kHidden;
+              if (MODE == IN_ENCODE || MODE == IN_LOAD2) {
+                // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
+                if (live)
+                  *reinterpret_cast<float4*>(p.out + row * 4) =
+                      make_float4(v[0] + bo[0] + dterm.x, v[1] + bo[1] + dterm.y, v[2] + bo[2] + dterm.z, v[3] + bo[3] + dterm.w);
+              } else if (live) {
+                float* orow = p.out + row * p.n_out;
+#pragma unroll
+                for (int o = 0; o < 48; ++o) {
+                  if (o < p.n_out) {
+                    int kind = HEAD_NONE;
+#pragma unroll
+                    for (int gq = 0; gq < 3; ++gq)
+                      if (o >= p.head_lo[gq] && o < p.head_lo[gq + 1]) kind = p.head_act[gq];
+                    orow[o] = head_apply_fast(v[o] + bo[o], kind);
+                  }
+                }
+              }
+            }
+            // the slot's operand buffer is free (all MMAs of this tile are complete): next tile's first-layer operand
+            if (has_next) {
+              if (kCompute) store_pre(t, pre);
+              else load_input(it + 1, t, 0, kb_first);
+            }
+          }
+          publish(t, (p.timeline && tl_on && ew == 0 && ph == 2 && t == 0) ? p.timeline + TL_EPI + 2 : nullptr);
+          tl_mark(p.timeline, tl_on && ew == 0, TL_ARR + ph * 2 + t);
+          tl_mark(p.timeline, tl_on && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+        }
+      }
     }
   }
 
-  // ---- teardown ----
+  // ---- teardown: nobody may leave while the peer can still touch this CTA's shared memory or barriers ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();
+  if (warp == W_PRODUCER) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// W [out][in] fp32 -> stream of K-block chunks, each [n_pad rows][64 k] bf16 in the UMMA K-major 128B-swizzle layout
-__global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int n_pad, int kblocks,
-                               uint8_t* __restrict__ dst) {
+// W [out][in] fp32 -> stream of K-block chunks.  A chunk holds n_pad rows x 64 k fp16 as [CTA-0 half][CTA-1 half],
+// each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout.  fold > 1: input column k stands for the sum of
+// columns k, k + fold_stride, ... (the sampler's P replicated Pluecker blocks).
+__global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int fold, int fold_stride, int n_pad,
+                               int kblocks, uint8_t* __restrict__ dst) {
   const int total = kblocks * n_pad * 64;
+  const int half_rows = n_pad / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int kb = idx / (n_pad * 64);
     const int rem = idx - kb * n_pad * 64;
     const int n = rem >> 6, k = rem & 63;
     const int ks = kb * 64 + k;
-    const float v = (n < out_dim && ks < k_used) ? W[(size_t)n * in_dim + ks] : 0.f;
-    const size_t off = (size_t)kb * n_pad * 128 + (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+    float v = 0.f;
+    if (n < out_dim && ks < k_used)
+      for (int f = 0; f < fold; ++f) v += W[(size_t)n * in_dim + ks + f * fold_stride];
+    const int h = n / half_rows, rr = n - h * half_rows;
+    const size_t off = (size_t)kb * n_pad * 128 + (size_t)h * half_rows * 128 + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 +
+                       (((k >> 3) ^ (rr & 7)) << 4) + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
   }
 }
 
@@ -590,6 +674,44 @@ __global__ void pack_tc_wdir_kernel(const float* __restrict__ W, int in_dim, flo
   if (i < 4 * 27) dst[i] = W[(size_t)(i / 27) * in_dim + kHidden + (i % 27)];
 }
 
+// View-direction term of DoNeRFTRT's last layer, fp32: out[i][o] = sum_j W7[o][256 + j] * g[j].
+// mode 0: g = gamma_4(viewdir i) (helpers.py:666-671; one per ray);  mode 1: g = row i of embedded_dirs [n, 27].
+__global__ void dirterm_kernel(const float* __restrict__ in, int stride, int mode, const float* __restrict__ wdir, long long n,
+                               float* __restrict__ out) {
+  __shared__ float s_w[4 * 27];
+  if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g[27];
+    if (mode == 0) {
+      const float* v = in + i * stride;
+      const float d[3] = {v[0], v[1], v[2]};
+      g[0] = d[0]; g[1] = d[1]; g[2] = d[2];
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float s, co;
+          sincosf(d[c] * (float)(1 << l), &s, &co);
+          g[3 + 6 * l + c] = s;
+          g[6 + 6 * l + c] = co;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 27; ++j) g[j] = in[i * stride + j];
+    }
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 27; ++j) a = fmaf(s_w[k * 27 + j], g[j], a);
+      o[k] = a;
+    }
+    *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -599,7 +721,10 @@ void tc_set_timeline(long long* dev_buf) { g_tc_timeline = dev_buf; }
 struct TcLayout {
   int kblocks[kMaxLayers];
   int n_pad[kMaxLayers];
+  int k_used[kMaxLayers];
   size_t chunk_off[kMaxLayers];
+  bool has_fold;                 // sampler: a second, folded image of layer 0 (6 inputs) for the in-kernel Pluecker operand
+  size_t fold_off;
   size_t img_bytes, bias_off, wdir_off, total;
 };
 
@@ -609,12 +734,16 @@ static TcLayout tc_layout(int net_id, int n_layers, const int* in_dims, const in
   for (int l = 0; l < n_layers; ++l) {
     const bool last = l == n_layers - 1;
     int k_used = in_dims[l];
-    if (last && net_id == PN_NET_NERF) k_used = kHidden;    // the 27 view-direction inputs go through wdir
+    if (last && net_id == PN_NET_NERF) k_used = kHidden;    // the 27 view-direction inputs go through the dirterm pre-pass
+    L.k_used[l] = k_used;
     L.kblocks[l] = (k_used + 63) / 64;
     L.n_pad[l] = last ? (out_dims[l] + 15) / 16 * 16 : kHidden;
     L.chunk_off[l] = off;
     off += (size_t)L.kblocks[l] * L.n_pad[l] * 128;
   }
+  L.has_fold = net_id == PN_NET_SAMPLER && in_dims[0] % 6 == 0;
+  L.fold_off = off;
+  if (L.has_fold) off += (size_t)kHidden * 128;
   L.img_bytes = off;
   L.bias_off = (off + 255) & ~(size_t)255;
   L.wdir_off = L.bias_off + (size_t)n_layers * kHidden * 4;
@@ -625,6 +754,7 @@ static TcLayout tc_layout(int net_id, int n_layers, const int* in_dims, const in
 void tc_free_net(NetTC& n) {
   if (n.blob) cudaFree(n.blob);
   if (n.error_flag) cudaFree(n.error_flag);
+  if (n.dirterm) cudaFree(n.dirterm);
   n = NetTC();
 }
 
@@ -636,8 +766,8 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   n.net_id = net_id;
   n.n_layers = n_layers;
   for (int l = 0; l < n_layers; ++l) { n.in_dim[l] = in_dims[l]; n.out_dim[l] = out_dims[l]; }
-  n.supported = in_dims[0] <= tc::MAX_KB * 64 && out_dims[n_layers - 1] <= 48;
-  if (!n.supported) return PN_OK;                           // fp32 tier still works; bf16 launch reports it
+  n.supported = in_dims[0] <= 8 * 64 && out_dims[n_layers - 1] <= 48;
+  if (!n.supported) return PN_OK;                           // fp32 tier still works; the fp16 launch reports it
   TcLayout L = tc_layout(net_id, n_layers, in_dims, out_dims);
   PN_CUDA_OK(cudaMalloc(&n.blob, L.total));
   PN_CUDA_OK(cudaMalloc((void**)&n.error_flag, sizeof(int)));
@@ -645,14 +775,17 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   n.blob_bytes = L.total;
   uint8_t* blob = reinterpret_cast<uint8_t*>(n.blob);
   for (int l = 0; l < n_layers; ++l) {
-    const bool last = l == n_layers - 1;
-    int k_used = (last && net_id == PN_NET_NERF) ? kHidden : in_dims[l];
     int total = L.kblocks[l] * L.n_pad[l] * 64;
-    tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[l], out_dims[l], in_dims[l], k_used, L.n_pad[l], L.kblocks[l],
+    tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[l], out_dims[l], in_dims[l], L.k_used[l], 1, 0, L.n_pad[l], L.kblocks[l],
                                                                  blob + L.chunk_off[l]);
     PN_LAUNCH_OK("pack_tc_kernel");
     tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden);
     PN_LAUNCH_OK("pack_tc_bias_kernel");
+  }
+  if (L.has_fold) {
+    tc::pack_tc_kernel<<<(kHidden * 64 + 255) / 256, 256, 0, stream>>>(W[0], out_dims[0], in_dims[0], 6, in_dims[0] / 6, 6, kHidden, 1,
+                                                                        blob + L.fold_off);
+    PN_LAUNCH_OK("pack_tc_kernel(fold)");
   }
   if (net_id == PN_NET_NERF) {
     tc::pack_tc_wdir_kernel<<<1, 128, 0, stream>>>(W[n_layers - 1], in_dims[n_layers - 1], reinterpret_cast<float*>(blob + L.wdir_off));
@@ -662,41 +795,99 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   return PN_OK;
 }
 
-int tc_launch_mlp(const NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
+static int tc_max_clusters(const void* func, int* out) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 148);
+  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.dynamicSmemBytes = tc::SMEM_ALLOC;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  PN_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, func, &cfg));
+  *out = n;
+  return PN_OK;
+}
+
+int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   if (!n.loaded) {
-    set_error(n.supported ? "PN_PREC_BF16: network weights not loaded" : "PN_PREC_BF16: this network shape is outside the tensor-core "
-              "kernel's limits (first layer <= 320 inputs, output <= 48); use PN_PREC_FP32");
+    set_error(n.supported ? "PN_PREC_FP16: network weights not loaded" : "PN_PREC_FP16: this network shape is outside the tensor-core "
+              "kernel's limits (first layer <= 512 inputs, output <= 48); use PN_PREC_FP32");
     return PN_ESTATE;
   }
   if (Lc.M == 0) return PN_OK;
   TcLayout L = tc_layout(n.net_id, n.n_layers, n.in_dim, n.out_dim);
   tc::Params p{};
-  p.n_layers = n.n_layers;
-  for (int l = 0; l < n.n_layers; ++l) { p.kblocks[l] = L.kblocks[l]; p.n_pad[l] = L.n_pad[l]; }
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(n.blob);
   p.wimg = blob;
   p.bias = reinterpret_cast<const float*>(blob + L.bias_off);
-  p.wdir = n.net_id == PN_NET_NERF ? reinterpret_cast<const float*>(blob + L.wdir_off) : nullptr;
-  p.k0 = n.in_dim[0];
+  p.n_layers = n.n_layers;
   p.n_out = n.out_dim[n.n_layers - 1];
-  p.act = Lc.act;
-  p.input_mode = Lc.input_mode;
-  p.in0 = Lc.in0; p.in1 = Lc.in1; p.in_stride = Lc.in_stride; p.in1_stride = Lc.in1_stride;
-  p.S = Lc.S > 0 ? Lc.S : 1; p.P = Lc.P; p.M = Lc.M; p.out = Lc.out;
+  p.k0 = n.in_dim[0];
+  p.in0 = Lc.in0; p.in_stride = Lc.in_stride;
+  p.M = Lc.M; p.out = Lc.out;
   for (int i = 0; i < 4; ++i) p.head_lo[i] = Lc.head_lo[i];
   for (int i = 0; i < 3; ++i) p.head_act[i] = Lc.head_act[i];
   p.error_flag = n.error_flag;
   p.timeline = g_tc_timeline;
-  if (Lc.input_mode == IN_PLUECKER && 6 * Lc.P != n.in_dim[0]) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
-  int dev = 0, sms = 0;
-  PN_CUDA_OK(cudaGetDevice(&dev));
-  PN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long tiles = (Lc.M + tc::TILE_M - 1) / tc::TILE_M;
-  unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (Lc.input_mode == IN_PLUECKER) {
+    if (6 * Lc.P != n.in_dim[0] || !L.has_fold) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
+  }
+  // phase table: layer 0 (possibly split when wider than 256 inputs, or folded), hidden layers, output layer
+  int np = 0;
+  auto add_phase = [&](int layer, int nkb, int k16_last, int n_pad, int acc, int epi, size_t w_off) {
+    tc::Phase& P = p.ph[np++];
+    P.layer = layer; P.nkb = nkb; P.k16_last = k16_last; P.n_pad = n_pad; P.acc = acc; P.epi = epi; P.w_off = (uint32_t)w_off;
+  };
+  const int last = n.n_layers - 1;
+  if (Lc.input_mode == IN_PLUECKER) {
+    add_phase(0, 1, 1, kHidden, 0, tc::EPI_HIDDEN, L.fold_off);                 // 6 inputs: one K = 16 step
+  } else {
+    const int kb0 = L.kblocks[0];
+    auto k16 = [&](int kb_count, int k_used) { int rem = k_used - (kb_count - 1) * 64; return (rem + 15) / 16; };
+    if (kb0 <= 4) {
+      add_phase(0, kb0, k16(kb0, L.k_used[0]), kHidden, 0, tc::EPI_HIDDEN, L.chunk_off[0]);
+    } else {
+      add_phase(0, 4, 4, kHidden, 0, tc::EPI_MORE, L.chunk_off[0]);
+      add_phase(0, kb0 - 4, k16(kb0 - 4, L.k_used[0] - 256), kHidden, 1, tc::EPI_HIDDEN, L.chunk_off[0] + (size_t)4 * kHidden * 128);
+    }
+  }
+  for (int l = 1; l < last; ++l) add_phase(l, 4, 4, kHidden, 0, tc::EPI_HIDDEN, L.chunk_off[l]);
+  add_phase(last, 4, 4, L.n_pad[last], 0, tc::EPI_OUT, L.chunk_off[last]);
+  p.n_phases = np;
+
+  // NeRF: view-direction term of the last layer, fp32, one row per ray (run_network) or per sample (forward)
+  if (n.net_id == PN_NET_NERF) {
+    const long long rows = Lc.input_mode == IN_ENCODE ? Lc.M / (Lc.S > 0 ? Lc.S : 1) : Lc.M;
+    if ((size_t)rows > n.dirterm_rows) {
+      if (n.dirterm) cudaFree(n.dirterm);
+      n.dirterm = nullptr; n.dirterm_rows = 0;
+      PN_CUDA_OK(cudaMalloc((void**)&n.dirterm, (size_t)rows * 4 * sizeof(float)));
+      n.dirterm_rows = (size_t)rows;
+    }
+    const float* wdir = reinterpret_cast<const float*>(blob + L.wdir_off);
+    const unsigned blocks = (unsigned)((rows + 255) / 256 < 148 * 8 ? (rows + 255) / 256 : 148 * 8);
+    if (Lc.input_mode == IN_ENCODE) tc::dirterm_kernel<<<blocks, 256, 0, stream>>>(Lc.in1, Lc.in1_stride, 0, wdir, rows, n.dirterm);
+    else tc::dirterm_kernel<<<blocks, 256, 0, stream>>>(Lc.in1, 27, 1, wdir, rows, n.dirterm);
+    PN_LAUNCH_OK("dirterm_kernel");
+    p.dirterm = n.dirterm;
+    p.dir_div = Lc.input_mode == IN_ENCODE ? (Lc.S > 0 ? Lc.S : 1) : 1;
+  }
+
+  const long long units = (Lc.M + tc::UNIT_M - 1) / tc::UNIT_M;
 #define PN_TC_LAUNCH(ACT, MODE)                                                                                            \
   do {                                                                                                                     \
-    PN_CUDA_OK(cudaFuncSetAttribute(tc::mlp_tc_kernel<ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC)); \
-    tc::mlp_tc_kernel<ACT, MODE><<<grid, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);                                      \
+    auto kern = tc::mlp_tc_kernel<ACT, MODE>;                                                                              \
+    static int max_clusters = 0;                                                                                           \
+    if (max_clusters == 0) {                                                                                               \
+      PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));                 \
+      int rc = tc_max_clusters((const void*)kern, &max_clusters);                                                          \
+      if (rc != PN_OK) return rc;                                                                                          \
+      if (max_clusters <= 0) { set_error("tc: no co-resident CTA pair fits on this device"); return PN_ECUDA; }            \
+    }                                                                                                                      \
+    const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);                                     \
+    kern<<<2 * clusters, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);                                                       \
   } while (0)
   if (Lc.act == 0 && Lc.input_mode == IN_ENCODE) PN_TC_LAUNCH(0, IN_ENCODE);
   else if (Lc.act == 0 && Lc.input_mode == IN_LOAD2) PN_TC_LAUNCH(0, IN_LOAD2);

@@ -1,4 +1,4 @@
-// bf16 tcgen05 tier of the three MLPs (mlp_tc.cu).
+// fp16 tcgen05 tier of the three MLPs (mlp_tc.cu).
 #pragma once
 #include "common.cuh"
 
@@ -9,9 +9,11 @@ struct NetTC {
   int in_dim[kMaxLayers] = {0};
   int out_dim[kMaxLayers] = {0};
   int net_id = -1;
-  void* blob = nullptr;          // device: packed bf16 weight images + fp32 biases (layout in mlp_tc.cu)
+  void* blob = nullptr;          // device: packed fp16 weight images + fp32 biases (layout in mlp_tc.cu)
   size_t blob_bytes = 0;
   int* error_flag = nullptr;     // device: set by the kernel's barrier watchdog before it traps
+  float* dirterm = nullptr;      // device scratch (NeRF): per-ray view-direction term of the last layer, grown on demand
+  size_t dirterm_rows = 0;
   bool supported = false;        // shape within the tensor-core kernel's limits
   bool loaded = false;
 };
@@ -21,6 +23,6 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
                 const float* const* b, cudaStream_t stream);
 bool tc_available();
 void tc_set_timeline(long long* dev_buf);   // debug: clock64 stamps of CTA 0's second tile (208 slots)
-int tc_launch_mlp(const NetTC& n, const MlpLaunch& L, cudaStream_t stream);
+int tc_launch_mlp(NetTC& n, const MlpLaunch& L, cudaStream_t stream);
 
 }  // namespace pn

@@ -1,4 +1,4 @@
-"""Dump the pipeline timeline of CTA 0's second tile of the NeRF tcgen05 kernel (debug aid)."""
+"""Dump the pipeline timeline of cluster 0's second iteration of the NeRF tcgen05 kernel (debug aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,19 +8,27 @@ dev = "cuda:0"
 sd = synth.make_weights(seed=0)
 nerf, samp, refn = make_modules(sd, dev)
 M = 190512
-pts = (torch.rand(M, 8, 3, device=dev) * 2 - 1); vd = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
-ctx = nerf._ctx()
+which = sys.argv[1] if len(sys.argv) > 1 else "nerf"
 buf = torch.zeros(208, dtype=torch.int64, device=dev)
-ctx.run_network(pts, vd, "bf16"); torch.cuda.synchronize()
+if which == "nerf":
+    pts = (torch.rand(M, 8, 3, device=dev) * 2 - 1); vd = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
+    ctx = nerf._ctx(); run = lambda: ctx.run_network(pts, vd, "bf16"); nph = 8
+elif which == "refine":
+    x = torch.randn(M, 144, device=dev) * 0.5
+    ctx = refn._ctx(); run = lambda: ctx.refine_forward(x, 8, "bf16"); nph = 7
+else:
+    x = torch.randn(M, 288, device=dev) * 0.5
+    ctx = samp._ctx(); run = lambda: ctx.sampler_forward(x, 8, "bf16"); nph = 8
+run(); torch.cuda.synchronize()
 _abi.lib().pn_debug_tc_timeline(buf.data_ptr())
-ctx.run_network(pts, vd, "bf16"); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 _abi.lib().pn_debug_tc_timeline(None)
 t = buf.cpu().tolist()
 t0 = min(x for x in t if x > 0)
-print("layer: MMA issue times (kb0h0 kb0h1 kb1h0 ... kb3h1) relative cycles")
-for l in range(8):
-    print(l, [t[l*8+i]-t0 if t[l*8+i] else None for i in range(8)])
-for g in range(2):
-    print("group", g, "acc_full seen:", [t[64+g*8+l]-t0 if t[64+g*8+l] else None for l in range(8)])
-    for l in range(7):
-        print("  arrive l", l, [t[80+g*64+l*8+i]-t0 if t[80+g*64+l*8+i] else None for i in range(8)])
+rel = lambda i: (t[i] - t0) if t[i] else None
+print(f"[{which}] phase slot: mma_start mma_issued | acc_seen(w2) arrive(w2) arrive(w17)   (cycles, relative)")
+for ph in range(nph):
+    for s in range(2):
+        i = ph * 2 + s
+        print(f"  ph {ph} slot {s}: {rel(i)} {rel(20 + i)} | {rel(40 + i)} {rel(60 + i)} {rel(80 + i)}")
+print("epilogue warp 0, phase 2 slot 0: acc seen", rel(40 + 4), " ld done", rel(100), " stores done", rel(101), " fence done", rel(102), " arrived", rel(60 + 4))
