@@ -12,7 +12,7 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpronerf_b200.so")
+LIB_PATH = os.environ.get("PN_B200_LIB") or os.path.join(HERE, "libpronerf_b200.so")   # env override: A/B builds while tuning
 
 PN_NET_SAMPLER, PN_NET_REFINE, PN_NET_NERF = 0, 1, 2
 PN_PREC_FP32, PN_PREC_BF16 = 0, 1

@@ -37,6 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    if os.environ.get("PN_TC_TIMELINE") == "1":        # debug build: pipeline clock stamps in the tensor-core MLP kernel
+        cmd.insert(1, "-DPN_TC_TIMELINE=1")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

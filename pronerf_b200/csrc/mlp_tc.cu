@@ -15,14 +15,14 @@
 // Pipeline (per slot the layers are strictly sequential; the two slots are half a period apart, so the tensor pipe
 // runs slot Y's layer while the CUDA cores drain slot X's accumulator):
 //
-//   warp 16     weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
+//   warp 8      weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
 //               consumption order, through a 5-slot ring with cp.async.bulk + mbarrier complete_tx; the global image
 //               is pre-swizzled into the UMMA canonical layout so a linear copy lands a ready B operand.
-//   warp 17     leader: MMA issuer -- per (layer, slot): wait "operand ready", then per K block wait "weights
+//   warp 9      leader: MMA issuer -- per (layer, slot): wait "operand ready", then per K block wait "weights
 //               landed in both CTAs", issue 4 MMAs (M256 N256 K16), tcgen05.commit frees the ring slot in both CTAs;
 //               after the last block commit "accumulator full" to both CTAs.
 //               follower: relay -- forwards "my half of the weights landed" to the leader's full barrier.
-//   warps 0-15  epilogue / operand producers (16 warps; warp = TMEM lane quadrant x 64-column group; thread = row):
+//   warps 0-7   epilogue / operand producers (8 warps; warp = TMEM lane quadrant x 128-column half; thread = row):
 //               tcgen05.ld the accumulator, bias + ReLU/ELU, convert to fp16 and store straight into the slot's
 //               A operand for the next layer (the swizzle makes row-per-thread 16-byte stores conflict free), then
 //               fence.proxy.async and arrive on the leader's "operand ready" barrier (remote arrive from the follower).
@@ -31,6 +31,9 @@
 // view-direction term (27 inputs of the last layer, identical for a ray's samples) is a per-ray fp32 pre-pass added in
 // the output epilogue, so the tensor-core part of the last layer is a clean K = 256, N = 16 GEMM.
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <type_traits>
 
 #include "tc.cuh"
 
@@ -49,17 +52,17 @@ constexpr int OFF_A = 0;
 constexpr int OFF_RING = OFF_A + 2 * A_SLOT_BYTES;
 constexpr int OFF_BIAS = OFF_RING + N_RING * RING_SLOT_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;
-// barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2], acc_full[2]
-constexpr int N_BARS = 2 * N_RING + 4;
+// barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2 slots][2 halves], acc_full[2]
+constexpr int N_BARS = 2 * N_RING + 6;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B (swizzle atom)
-constexpr int N_EPI_WARPS = 16;
-constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 576
+constexpr int N_EPI_WARPS = 8;                          // lane quadrant x column half; ~200 registers each for deep tcgen05.ld pipelining
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 320
 // The two single-thread roles get the HIGHEST warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
 // issuer (or weight producer) stalls the whole pair (measured: 2x slower issue as warp 1 behind four epilogue warps).
-constexpr int W_PRODUCER = N_EPI_WARPS;                 // warp 16 (scheduler 0)
-constexpr int W_MMA = N_EPI_WARPS + 1;                  // warp 17 (scheduler 1)
+constexpr int W_PRODUCER = N_EPI_WARPS;                 // warp 8 (scheduler 0)
+constexpr int W_MMA = N_EPI_WARPS + 1;                  // warp 9 (scheduler 1)
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_PHASES = 10;
 
@@ -73,6 +76,7 @@ struct Phase {
   int n_pad;        // MMA N (multiple of 16)
   int acc;          // 1: accumulate onto what the previous phase left in TMEM
   int epi;          // EpiKind
+  int merged;       // 1: all nkb K blocks of this (narrow) layer travel as ONE ring chunk [rank][kb][n_pad/2 rows x 128 B]
   uint32_t w_off;   // byte offset of the first chunk in the weight image
 };
 
@@ -92,6 +96,8 @@ struct Params {
   float* out;
   int head_lo[4];
   int head_act[3];
+  int shift;                    // phases slot 1 runs behind slot 0 (0 = in step)
+  int split;                    // 1: hidden epilogues publish their first K block early (two-step operand hand-over)
   int* error_flag;
   long long* timeline;          // debug: leader CTA of cluster 0 stamps clock64() of its second iteration
 };
@@ -134,8 +140,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug must not hang the GPU (it traps and reports instead).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+// Spin with a watchdog: a protocol bug must not hang the GPU (it traps and reports instead).  The first probe is inline
+// (it usually succeeds); the spin loop with the watchdog lives out of line to keep the role loops compact.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) {
@@ -144,6 +151,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, code);
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -226,11 +236,15 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
 __device__ __forceinline__ uint32_t a_chunk_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
+// Operand-buffer stores.  No "memory" clobber on purpose: these only ever write the A operand buffers, which no C++-level
+// access touches, and a clobber would pin every bias load (plain shared-memory reads) behind the previous store -- one
+// exposed LDS latency per 16-byte chunk.  Ordering against the tensor-core proxy comes from fence_proxy_async() (a
+// volatile asm WITH a clobber) in publish().
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a));
 }
 
 // two floats -> packed f16x2 (lo in the low half), saturating to the largest finite half
@@ -273,49 +287,67 @@ __device__ __forceinline__ float head_apply_fast(float v, int kind) {
   return v;
 }
 
-// Element k (0..63) of the padded frequency encoding gamma_10(x) = [x, sin(2^l x), cos(2^l x)]_{l<10}, 0
-// (helpers.py:666-671).  One exact range reduction in turns (x * 2^l / 2pi, power-of-two scaling is exact), then the SFU.
-template <int K>
-__device__ __forceinline__ float encode_elem(const float* x) {
-  if (K < 3) return x[K];
-  if (K >= 63) return 0.f;
-  constexpr int j = (K >= 3 ? K - 3 : 0);
-  constexpr int l = j / 6, rem = j % 6, c = rem % 3;
-  constexpr bool is_cos = rem >= 3;
-  float t = x[c] * 0.15915494309189535f * (float)(1 << l);
-  t -= rintf(t);
-  if (is_cos) { t += 0.25f; }                            // cos(a) = sin(a + pi/2); |t| <= 0.75, still SFU-accurate
-  return __sinf(t * 6.283185307179586f);
-}
-// 16 consecutive elements [16*CG, 16*CG+16) as 8 packed half pairs
-template <int CG>
-__device__ __forceinline__ void encode16(const float* x, uint32_t* w) {
-#define PN_E(i) encode_elem<16 * CG + (i)>(x)
-  w[0] = pack_h2(PN_E(0), PN_E(1));   w[1] = pack_h2(PN_E(2), PN_E(3));
-  w[2] = pack_h2(PN_E(4), PN_E(5));   w[3] = pack_h2(PN_E(6), PN_E(7));
-  w[4] = pack_h2(PN_E(8), PN_E(9));   w[5] = pack_h2(PN_E(10), PN_E(11));
-  w[6] = pack_h2(PN_E(12), PN_E(13)); w[7] = pack_h2(PN_E(14), PN_E(15));
-#undef PN_E
+// The padded frequency encoding gamma_10(x) = [x, sin(2^l x), cos(2^l x)]_{l<10}, 0 (helpers.py:666-671), 64 elements per
+// point; element k >= 3 is (l, sin|cos, coordinate) = ((k-3)/6, ((k-3)%6)/3, (k-3)%3).  Thread (row, CH) produces elements
+// [32 CH, 32 CH + 32): octaves 0..4 (CH = 0) or 4..9 (CH = 1).  Per coordinate ONE exact range reduction in turns
+// (x * 2^l / 2pi; the power-of-two scaling is exact) and one SFU sin/cos at the first octave, then the double-angle
+// recurrence sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a: the error doubles per octave (<= 2^5 * 4e-7), far below
+// fp16 resolution, and the SFU work drops from 60 to 6 operations per point.
+template <int CH>
+__device__ __forceinline__ void encode32(const float* x, uint32_t* w) {
+  constexpr int L0 = CH ? 4 : 0, NL = CH ? 6 : 5;
+  float sn[3][NL], cs[3][NL];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t = x[c] * 0.15915494309189535f * (float)(1 << L0);
+    t -= rintf(t);
+    sn[c][0] = __sinf(t * 6.283185307179586f);
+    cs[c][0] = __cosf(t * 6.283185307179586f);
+#pragma unroll
+    for (int i = 1; i < NL; ++i) {
+      sn[c][i] = 2.f * sn[c][i - 1] * cs[c][i - 1];
+      cs[c][i] = fmaf(-2.f * sn[c][i - 1], sn[c][i - 1], 1.f);
+    }
+  }
+  float e[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = 32 * CH + i;
+    if (k < 3) e[i] = x[k];
+    else if (k >= 63) e[i] = 0.f;
+    else {
+      const int j = k - 3, l = j / 6, rem = j % 6, c = rem % 3;
+      e[i] = rem >= 3 ? cs[c][l - L0] : sn[c][l - L0];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_h2(e[2 * i], e[2 * i + 1]);
 }
 
+#ifndef PN_TC_TIMELINE
+#define PN_TC_TIMELINE 0          // build with -DPN_TC_TIMELINE=1 (PN_TC_TIMELINE=1 python -m pronerf_b200.build) to compile the stamps in
+#endif
+constexpr bool kTimeline = PN_TC_TIMELINE != 0;
 __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// 32 accumulator columns -> bias + activation -> fp16 -> 4 x 16 B of this thread's row in the next layer's operand.
-// The TMEM load and the 8 bias loads are issued together (volatile asm keeps them ahead of the wait), so one latency is
-// exposed per call and the other epilogue warps of the scheduler fill it.  row_base = block + row offset, xr = (r & 7) << 4.
+// 64 accumulator columns (already in registers) -> bias + activation -> fp16 -> one K block of the next layer's operand
+// (8 x 16 B of this thread's row).  row_base = block + row offset, xr = (r & 7) << 4 (the 128B swizzle).
+// ptxas cannot tell the bias reads from the operand stores apart (both shared memory), so it never hoists a bias load
+// above an earlier store: the loads are issued by hand two chunks ahead (volatile asm keeps the order).
 template <int ACT>
-__device__ __forceinline__ void epilogue_half(uint32_t taddr, uint32_t bias_addr, uint32_t row_base, uint32_t xr, int c0) {
-  float v[32];
-  float4 b[8];
-  tmem_ld32(taddr, v);
+__device__ __forceinline__ void epilogue_store64(const float* v, uint32_t bias_addr, uint32_t row_base, uint32_t xr, long long* tl = nullptr) {
+  float4 b[20];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = ld_shared_v4f(bias_addr + 16u * i);
-  tmem_wait_ld();
+  for (int i = 0; i < 4; ++i) b[i] = ld_shared_v4f(bias_addr + 16u * i);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
+    if (c + 2 < 8) {
+      b[2 * c + 4] = ld_shared_v4f(bias_addr + 16u * (2 * c + 4));
+      b[2 * c + 5] = ld_shared_v4f(bias_addr + 16u * (2 * c + 5));
+    }
     const float4 ba = b[2 * c], bb = b[2 * c + 1];
     const float* x = v + 8 * c;
     float y[8];
@@ -326,7 +358,8 @@ __device__ __forceinline__ void epilogue_half(uint32_t taddr, uint32_t bias_addr
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : pack_h2_elu(y[2 * u], y[2 * u + 1]);
-    st_shared_v4(row_base + ((uint32_t)((c0 + c) << 4) ^ xr), w[0], w[1], w[2], w[3]);
+    st_shared_v4(row_base + ((uint32_t)(c << 4) ^ xr), w[0], w[1], w[2], w[3]);
+    if (kTimeline && tl) tl[c] = clock64();
   }
 }
 
@@ -335,12 +368,14 @@ constexpr int TL_MMA0 = 0;       // MMA thread: operand-ready wait satisfied
 constexpr int TL_MMA1 = 20;      // MMA thread: last MMA of the phase issued
 constexpr int TL_ACC = 40;       // epilogue warp 0: accumulator-full observed
 constexpr int TL_ARR = 60;       // epilogue warp 0: arrived on operand-ready
-constexpr int TL_ARRL = 80;      // epilogue warp 15: arrived on operand-ready
-constexpr int TL_EPI = 100;     // epilogue warp 0, phase 2 slot 0: [0] first half stored, [1] second half stored, [2] proxy fence done
+constexpr int TL_ARRL = 80;      // epilogue warp 7: arrived on operand-ready
+constexpr int TL_EPI = 100;      // epilogue warp 0, phase 2 slot 0: [0] first 64 columns stored, [1] second 64 columns stored
+constexpr int TL_FACC = 150;     // follower CTA, epilogue warp 0: accumulator-full observed
+constexpr int TL_FARR = 170;     // follower CTA, epilogue warp 0: arrived on operand-ready
 constexpr int TL_SYNC = 140;    // clock64() right after the setup cluster barrier: [0] leader, [1] follower (per-SM clock offset)
 constexpr int TL_N = 208;
 __device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
-  if (tl && on) tl[slot] = clock64();
+  if (kTimeline && tl && on) tl[slot] = clock64();
 }
 
 // ACT: 0 ReLU / 1 ELU.  MODE: InputMode.
@@ -354,8 +389,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   const uint32_t bar0 = base + OFF_BAR;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (N_RING + s); };
-  auto bar_aready = [&](int t) { return bar0 + 8u * (2 * N_RING + t); };
-  auto bar_accfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 2 + t); };
+  auto bar_aready = [&](int t, int h) { return bar0 + 8u * (2 * N_RING + 2 * t + h); };   // h = 0: K blocks {0,1} + accumulator drained; 1: K blocks {2,3}
+  auto bar_accfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 4 + t); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,7 +403,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   // ---- one-time setup ----
   if (warp == W_MMA && lane == 0) {
     for (int s = 0; s < N_RING; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_aready(t), 2 * N_EPI_WARPS); mbar_init(bar_accfull(t), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_aready(t, 0), 2 * N_EPI_WARPS); mbar_init(bar_aready(t, 1), 2 * N_EPI_WARPS); mbar_init(bar_accfull(t), 1);
+    }
     fence_barrier_init();
   }
   if (warp == W_PRODUCER) tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
@@ -380,149 +417,255 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
+  if (kTimeline && p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
+
+  // Every role walks the same (slot, phase) sequence: the two slots alternate, slot 1 running `shift` phases (half a
+  // network) behind slot 0, so that one slot's narrow first/last layers and tile hand-over overlap the other slot's
+  // full-width layers and the tensor pipe always has a 2048-cycle block of MMAs queued.
+  struct Cursor {
+    long long n_pairs, stride, tile0, tile1;
+    int np, delay, ph0, ph1;
+    __device__ __forceinline__ long long tile(int t) const { return t ? tile1 : tile0; }
+    __device__ __forceinline__ int ph(int t) const { return t ? ph1 : ph0; }
+    __device__ __forceinline__ bool live(int t) const { return tile(t) < n_pairs; }
+    __device__ __forceinline__ bool has_next(int t) const { return tile(t) + stride < n_pairs; }
+    __device__ __forceinline__ void advance(int t) {
+      if (t) { if (++ph1 == np) { ph1 = 0; tile1 += stride; } }
+      else   { if (++ph0 == np) { ph0 = 0; tile0 += stride; } }
+    }
+  };
+  Cursor cur;
+  cur.n_pairs = n_pairs; cur.stride = 2 * n_clusters; cur.np = p.n_phases;
+  cur.ph0 = cur.ph1 = 0;
+  cur.tile0 = 2 * cluster_id; cur.tile1 = 2 * cluster_id + 1;
+  cur.delay = cur.live(1) ? p.shift : 0;
+  const long long tl_tile0 = 2 * cluster_id + cur.stride;           // timeline: the second tile of slot 0 / slot 1
+  // run body(0), body(1) alternately until both slots are out of tiles.  ONE copy of the body (the slot index is a
+  // run-time value): two inlined copies of the epilogue overflow the instruction cache.
+#define PN_WALK(body)                                                        \
+  for (;;) {                                                                 \
+    bool any = false;                                                        \
+    _Pragma("unroll 1")                                                      \
+    for (int t_ = 0; t_ < 2; ++t_) {                                         \
+      if (t_ == 1 && cur.delay > 0) { --cur.delay; any = true; continue; }   \
+      if (!cur.live(t_)) continue;                                           \
+      any = true;                                                            \
+      body(t_);                                                              \
+      cur.advance(t_);                                                       \
+    }                                                                        \
+    if (!any) break;                                                         \
+  }
 
   if (warp == W_PRODUCER) {
     // =============================== weight producer (both CTAs) ===============================
     if (lane == 0) {
       uint32_t slot = 0, ring_par = 1;                       // empty barriers: the first pass over the ring is free
-      for (long long it = 0; pair0(it) < n_pairs; ++it) {
-        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
-        for (int ph = 0; ph < p.n_phases; ++ph) {
-          const int nkb = p.ph[ph].nkb;
-          const uint32_t half_bytes = (uint32_t)p.ph[ph].n_pad * 64u;
-          const uint8_t* src0 = p.wimg + p.ph[ph].w_off + rank * half_bytes;
-          for (int t = 0; t < nv; ++t) {
-            const uint8_t* src = src0;
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(bar_empty(slot), ring_par, p.error_flag, 1);
-              mbar_arrive_expect_tx(bar_full(slot), half_bytes);
-              bulk_copy_g2s(base + OFF_RING + slot * RING_SLOT_BYTES, src, half_bytes, bar_full(slot));
-              src += 2 * half_bytes;
-              if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
-            }
-          }
+      auto body = [&](int t) {
+        const int ph = cur.ph(t);
+        const bool merged = p.ph[ph].merged != 0;
+        const int nchunks = merged ? 1 : p.ph[ph].nkb;
+        const uint32_t bytes = (uint32_t)p.ph[ph].n_pad * 64u * (merged ? (uint32_t)p.ph[ph].nkb : 1u);   // this CTA's share of a chunk
+        const uint8_t* src = p.wimg + p.ph[ph].w_off + rank * bytes;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar_empty(slot), ring_par, p.error_flag, 1);
+          mbar_arrive_expect_tx(bar_full(slot), bytes);
+          bulk_copy_g2s(base + OFF_RING + slot * RING_SLOT_BYTES, src, bytes, bar_full(slot));
+          src += 2 * bytes;
+          if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
         }
-      }
+      };
+      PN_WALK(body)
     }
   } else if (warp == W_MMA) {
     if (lane == 0 && rank != 0) {
       // =============================== follower: weights-landed relay ===============================
       uint32_t slot = 0, ring_par = 0;
-      for (long long it = 0; pair0(it) < n_pairs; ++it) {
-        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
-        for (int ph = 0; ph < p.n_phases; ++ph) {
-          const int n = nv * p.ph[ph].nkb;
-          for (int i = 0; i < n; ++i) {
-            mbar_wait(bar_full(slot), ring_par, p.error_flag, 5);
-            mbar_arrive_cluster(bar_full(slot), 0);
-            if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
-          }
+      auto body = [&](int t) {
+        const int ph = cur.ph(t);
+        const int n = p.ph[ph].merged ? 1 : p.ph[ph].nkb;
+        for (int i = 0; i < n; ++i) {
+          mbar_wait(bar_full(slot), ring_par, p.error_flag, 5);
+          mbar_arrive_cluster(bar_full(slot), 0);
+          if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
         }
-      }
+      };
+      PN_WALK(body)
     } else if (rank == 0) {
       // =============================== leader: MMA issuer ===============================
       // The whole warp walks the loop convergently (waits included) and one elected lane issues: with warp-uniform
       // control flow every tcgen05 operand lives in uniform registers.  A single thread retires one dependent
       // instruction every ~5 cycles, so this loop is kept to a few dozen instructions per K block (4 MMAs = 512 cycles).
       uint32_t slot = 0, ring_par = 0;
-      uint32_t ar_par = 0;                                   // bit t = parity to wait for on a_ready[t]
+      uint32_t ar_par = 0;                                   // bit 2t+h = parity to wait for on a_ready[t][h]
       constexpr uint32_t kDescHi = 0x40004040u;              // SBO 1024 B | descriptor version 1 | SWIZZLE_128B
       const uint32_t a_lo0 = (((base + OFF_A) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t b_lo0 = (((base + OFF_RING) >> 4) & 0x3FFFu) | (1u << 16);
-      for (long long it = 0; pair0(it) < n_pairs; ++it) {
-        const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
-        const bool tl_on = blockIdx.x == 0 && it == 1 && lane == 0;
-        for (int ph = 0; ph < p.n_phases; ++ph) {
-          const int nkb = p.ph[ph].nkb, k16_last = p.ph[ph].k16_last;
-          const uint32_t acc0 = (uint32_t)p.ph[ph].acc;
-          const uint32_t idesc = umma_idesc(p.ph[ph].n_pad);
-          for (int t = 0; t < nv; ++t) {
-            mbar_wait(bar_aready(t), (ar_par >> t) & 1u, p.error_flag, 2);
-            ar_par ^= 1u << t;
+      // 4 MMAs over one 64-wide K block: a_lo / b_lo are the low descriptor words of the block's first K = 16 step
+      auto issue_block = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc_first) {
+        const uint64_t a_desc = ((uint64_t)kDescHi << 32) | a_lo;
+        const uint64_t b_desc = ((uint64_t)kDescHi << 32) | b_lo;
+        umma_f16_pair(d_tmem, a_desc, b_desc, idesc, acc_first);       // K = 16 per instruction: +32 bytes = +2 in descriptor units
+        umma_f16_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+        umma_f16_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+        umma_f16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+      };
+      auto ring_next = [&]() { if (++slot == N_RING) { slot = 0; ring_par ^= 1u; } };
+      auto body = [&](int t) {
+        const int ph = cur.ph(t);
+        const bool tl_on = kTimeline && blockIdx.x == 0 && cur.tile(t) == tl_tile0 + t && lane == 0;
+        const int nkb = p.ph[ph].nkb, k16_last = p.ph[ph].k16_last;
+        const uint32_t acc0 = (uint32_t)p.ph[ph].acc;
+        const uint32_t idesc = umma_idesc(p.ph[ph].n_pad);
+        const bool merged = p.ph[ph].merged != 0;
+        const uint32_t par0 = (ar_par >> (2 * t)) & 1u, par1 = (ar_par >> (2 * t + 1)) & 1u;
+        ar_par ^= 3u << (2 * t);
+        const uint32_t d_tmem = tmem_base + (uint32_t)t * kHidden;
+        const uint32_t a_lo_t = a_lo0 + (uint32_t)t * (A_SLOT_BYTES >> 4);
+        constexpr uint32_t kBlk = A_BLOCK_BYTES >> 4, kRing = RING_SLOT_BYTES >> 4;
+        // operand halves: [0] = K blocks {0,1} written and the accumulator drained, [1] = K blocks {2,3} written
+        mbar_wait(bar_aready(t, 0), par0, p.error_flag, 2);
+        tc_fence_after();
+        tl_mark(p.timeline, tl_on, TL_MMA0 + ph * 2 + t);
+        if (nkb == 4 && k16_last == 4 && !merged) {
+          // the standard full-width layer: straight-line issue, 2 K blocks per operand half
+          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          tc_fence_after();
+          if (elect_one()) { issue_block(d_tmem, a_lo_t, b_lo0 + slot * kRing, idesc, acc0); umma_commit_pair(bar_empty(slot)); }
+          __syncwarp();
+          ring_next();
+          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          tc_fence_after();
+          if (elect_one()) { issue_block(d_tmem, a_lo_t + kBlk, b_lo0 + slot * kRing, idesc, 1u); umma_commit_pair(bar_empty(slot)); }
+          __syncwarp();
+          ring_next();
+          mbar_wait(bar_aready(t, 1), par1, p.error_flag, 2);
+          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          tc_fence_after();
+          if (elect_one()) { issue_block(d_tmem, a_lo_t + 2 * kBlk, b_lo0 + slot * kRing, idesc, 1u); umma_commit_pair(bar_empty(slot)); }
+          __syncwarp();
+          ring_next();
+          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_block(d_tmem, a_lo_t + 3 * kBlk, b_lo0 + slot * kRing, idesc, 1u);
+            umma_commit_pair(bar_empty(slot));
+            umma_commit_pair(bar_accfull(t));
+          }
+          __syncwarp();
+          ring_next();
+        } else {
+          // first layer (1..4 K blocks, last one possibly short) and the narrow output layer (one merged ring chunk)
+          mbar_wait(bar_aready(t, 1), par1, p.error_flag, 2);
+          const uint32_t half16 = (uint32_t)p.ph[ph].n_pad * 4u;      // one K block of this CTA's weight half, in 16-byte units
+          uint32_t a_lo = a_lo_t;
+          if (merged) {
+            mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
             tc_fence_after();
-            tl_mark(p.timeline, tl_on, TL_MMA0 + ph * 2 + t);
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * kHidden;
-            uint32_t a_lo = a_lo0 + (uint32_t)t * (A_SLOT_BYTES >> 4);
+            if (elect_one()) {
+              uint32_t b_lo = b_lo0 + slot * kRing;
+              for (int kb = 0; kb < nkb; ++kb) {
+                issue_block(d_tmem, a_lo, b_lo, idesc, acc0 | (uint32_t)kb);
+                a_lo += kBlk;
+                b_lo += half16;
+              }
+              umma_commit_pair(bar_empty(slot));
+            }
+            __syncwarp();
+            ring_next();
+          } else {
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
               tc_fence_after();
-              const uint64_t a_desc = ((uint64_t)kDescHi << 32) | a_lo;
-              const uint64_t b_desc = ((uint64_t)kDescHi << 32) | (b_lo0 + slot * (RING_SLOT_BYTES >> 4));
               if (elect_one()) {
-                if (kb + 1 < nkb || k16_last == 4) {         // K = 16 per instruction: +32 bytes = +2 in descriptor units
-                  umma_f16_pair(d_tmem, a_desc, b_desc, idesc, acc0 | (uint32_t)kb);
-                  umma_f16_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                  umma_f16_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                  umma_f16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                const uint32_t b_lo = b_lo0 + slot * kRing;
+                if (kb + 1 < nkb || k16_last == 4) {
+                  issue_block(d_tmem, a_lo, b_lo, idesc, acc0 | (uint32_t)kb);
                 } else {
+                  const uint64_t a_desc = ((uint64_t)kDescHi << 32) | a_lo, b_desc = ((uint64_t)kDescHi << 32) | b_lo;
                   for (int s2 = 0; s2 < k16_last; ++s2) umma_f16_pair(d_tmem, a_desc + 2u * s2, b_desc + 2u * s2, idesc, acc0 | (uint32_t)(kb | s2));
                 }
                 umma_commit_pair(bar_empty(slot));           // ring slot is free (in both CTAs) once these MMAs have read it
               }
               __syncwarp();
-              a_lo += A_BLOCK_BYTES >> 4;
-              if (++slot == N_RING) { slot = 0; ring_par ^= 1u; }
+              a_lo += kBlk;
+              ring_next();
             }
-            if (elect_one()) umma_commit_pair(bar_accfull(t));
-            __syncwarp();
-            tl_mark(p.timeline, tl_on, TL_MMA1 + ph * 2 + t);
           }
+          if (elect_one()) umma_commit_pair(bar_accfull(t));
+          __syncwarp();
         }
-      }
+        tl_mark(p.timeline, tl_on, TL_MMA1 + ph * 2 + t);
+      };
+      PN_WALK(body)
     }
   } else {
     // =============================== epilogue / operand producers (both CTAs) ===============================
     const int ew = warp;
-    const int cg = ew >> 2;                                // 64-column group = K block of the next layer's operand
+    const int ch = ew >> 2;                                // column interleave: this warp drains columns [64ch,+64) and [128+64ch,+64)
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                           // row of the tile owned by this thread
     const uint32_t a_base = base + OFF_A;
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), xr = (uint32_t)(r & 7) << 4;
     uint32_t acc_par = 0;
+    constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER);
+    constexpr bool kNerf = (MODE == IN_ENCODE || MODE == IN_LOAD2);
+    constexpr int kXin = (MODE == IN_ENCODE) ? 3 : 6;
+    const int kb_first = p.ph[0].nkb;                      // K blocks of the first phase (<= 4)
 
-    // global row of this thread in slot t of iteration it
-    auto row_of = [&](long long it, int t) { return (pair0(it) + t) * PAIR_M + (long long)rank * TILE_M + r; };
+    // global row of this thread in pair tile `tile`
+    auto row_of = [&](long long tile) { return tile * PAIR_M + (long long)rank * TILE_M + r; };
 
-    // --- first-layer operand, "compute" modes: 16 elements per thread, computed ahead of time into `pre` ---
-    auto precompute_input = [&](long long row, uint32_t* pre) {
+    // --- first-layer operand, "compute" modes.  The raw inputs of the NEXT tile are fetched one phase early into
+    //     registers (xin), turned into 32 packed operand elements (pre) while waiting for the output layer, and stored
+    //     as soon as the slot's operand buffer is free. ---
+    auto fetch_input = [&](long long row, float* xin) {
+#pragma unroll
+      for (int i = 0; i < kXin; ++i) xin[i] = 0.f;
+      if (row < p.M) {
+        const float* src = p.in0 + row * (MODE == IN_ENCODE ? 3 : p.in_stride);
+#pragma unroll
+        for (int i = 0; i < kXin; ++i) xin[i] = __ldg(src + i);
+      }
+    };
+    auto precompute_input = [&](const float* xin, bool row_live, uint32_t* pre) {
       if (MODE == IN_ENCODE) {
-        float x[3] = {0.f, 0.f, 0.f};
-        if (row < p.M) { x[0] = __ldg(p.in0 + row * 3); x[1] = __ldg(p.in0 + row * 3 + 1); x[2] = __ldg(p.in0 + row * 3 + 2); }
-        switch (cg) {
-          case 0: encode16<0>(x, pre); break;
-          case 1: encode16<1>(x, pre); break;
-          case 2: encode16<2>(x, pre); break;
-          default: encode16<3>(x, pre); break;
-        }
+        if (ch == 0) encode32<0>(xin, pre);
+        else encode32<1>(xin, pre);
       } else if (MODE == IN_PLUECKER) {
         // the 6 Pluecker features of the ray; the sampler's P replicated copies are folded into the weights
-        // (W_eff = sum over copies, tc_load_net), so the operand is 6 wide
+        // (W_eff = sum over copies, tc_load_net), so the operand is 6 wide: one K = 16 step, written by the ch = 0 warps
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pre[i] = 0u;
-        if (cg == 0 && row < p.M) {
-          const float* ray = p.in0 + row * p.in_stride;
+        for (int i = 0; i < 16; ++i) pre[i] = 0u;
+        if (ch == 0 && row_live) {
           float f6[6];
-          pluecker6(__ldg(ray), __ldg(ray + 1), __ldg(ray + 2), __ldg(ray + 3), __ldg(ray + 4), __ldg(ray + 5), f6);
+          pluecker6(xin[0], xin[1], xin[2], xin[3], xin[4], xin[5], f6);
           pre[0] = pack_h2(f6[0], f6[1]); pre[1] = pack_h2(f6[2], f6[3]); pre[2] = pack_h2(f6[4], f6[5]);
         }
       }
     };
     auto store_pre = [&](int t, const uint32_t* pre) {
-      const uint32_t dst = a_base + t * A_SLOT_BYTES;      // block 0
-      st_shared_v4(dst + a_chunk_off(r, 2 * cg), pre[0], pre[1], pre[2], pre[3]);
-      st_shared_v4(dst + a_chunk_off(r, 2 * cg + 1), pre[4], pre[5], pre[6], pre[7]);
+      const uint32_t dst = a_base + t * A_SLOT_BYTES + row_off;      // block 0
+      if (MODE == IN_PLUECKER) {
+        if (ch == 0) {
+          st_shared_v4(dst + (0u ^ xr), pre[0], pre[1], pre[2], pre[3]);
+          st_shared_v4(dst + (16u ^ xr), 0u, 0u, 0u, 0u);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          st_shared_v4(dst + ((uint32_t)((4 * ch + c) << 4) ^ xr), pre[4 * c], pre[4 * c + 1], pre[4 * c + 2], pre[4 * c + 3]);
+      }
     };
-    // --- first-layer operand, "load" modes: warp (q, cg) loads rows q*32 + cg*8 .. +7 of K blocks [kb_lo, kb_lo+nblk) ---
-    auto load_input = [&](long long it, int t, int kb_lo, int nblk) {
-      const long long row_base = (pair0(it) + t) * PAIR_M + (long long)rank * TILE_M;
+    // --- first-layer operand, "load" modes: warp (q, ch) loads rows q*32 + ch*16 .. +15 of K blocks [kb_lo, kb_lo+nblk) ---
+    auto load_input = [&](long long tile, int t, int kb_lo, int nblk) {
+      const long long row_base = tile * PAIR_M + (long long)rank * TILE_M;
       const int k0 = p.k0;
       for (int kb = 0; kb < nblk; ++kb) {
         const uint32_t dst = a_base + t * A_SLOT_BYTES + kb * A_BLOCK_BYTES;
         const int k = (kb_lo + kb) * 64 + 2 * lane;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int trow = q * 32 + cg * 8 + i;
+        for (int i = 0; i < 16; ++i) {
+          const int trow = q * 32 + ch * 16 + i;
           const long long grow = row_base + trow;
           float v0 = 0.f, v1 = 0.f;
           if (grow < p.M) {
@@ -534,105 +677,150 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         }
       }
     };
-    constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER);
-    const int kb_first = p.ph[0].nkb;                      // K blocks of the first phase (<= 4)
-    auto publish = [&](int t, long long* tl = nullptr) {   // operand of slot t is complete (from this warp's side)
+    // publish this warp's share of slot t's operand: half 0 (its first K block; also "my accumulator reads are done"),
+    // half 1 (its second K block), or both at once (first-layer operands)
+    auto publish = [&](int t, int halves) {
       fence_proxy_async();
-      if (tl) *tl = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar_aready(t), 0);
+      if (lane == 0) {
+        if (halves & 1) mbar_arrive_cluster(bar_aready(t, 0), 0);
+        if (halves & 2) mbar_arrive_cluster(bar_aready(t, 1), 0);
+      }
+    };
+    auto fetch_dterm = [&](long long row) {
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.M) {
+        const long long idx = (p.M < 0x7fffffffLL) ? (long long)((uint32_t)row / (uint32_t)p.dir_div) : row / p.dir_div;
+        d = __ldg(reinterpret_cast<const float4*>(p.dirterm) + idx);
+      }
+      return d;
     };
 
-    // prologue: first unit's operands
-    if (pair0(0) < n_pairs) {
-      const int nv = (pair0(0) + 1 < n_pairs) ? 2 : 1;
-      for (int t = 0; t < nv; ++t) {
-        if (kCompute) {
-          uint32_t pre[8];
-          precompute_input(row_of(0, t), pre);
-          store_pre(t, pre);
-        } else {
-          load_input(0, t, 0, kb_first);
-        }
-        publish(t);
+    // prologue: first operands of both slots
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (!cur.live(t)) continue;
+      if (kCompute) {
+        float xin[6];
+        uint32_t pre[16];
+        const long long row = row_of(cur.tile(t));
+        fetch_input(row, xin);
+        precompute_input(xin, row < p.M, pre);
+        store_pre(t, pre);
+      } else {
+        load_input(cur.tile(t), t, 0, kb_first);
       }
+      publish(t, 3);
     }
 
-    for (long long it = 0; pair0(it) < n_pairs; ++it) {
-      const int nv = (pair0(it) + 1 < n_pairs) ? 2 : 1;
-      const bool tl_on = blockIdx.x == 0 && it == 1 && lane == 0;
-      for (int ph = 0; ph < p.n_phases; ++ph) {
-        const Phase& P = p.ph[ph];
-        for (int t = 0; t < nv; ++t) {
-          // does slot t have a tile in the next iteration?
-          const bool has_next = (P.epi == EPI_OUT) && (pair0(it + 1) + t < n_pairs);
-          uint32_t pre[8];
-          if (kCompute && has_next) precompute_input(row_of(it + 1, t), pre);   // overlaps the wait below
-          float4 dterm = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((MODE == IN_ENCODE || MODE == IN_LOAD2) && P.epi == EPI_OUT && cg == 0) {
-            const long long row = row_of(it, t);
-            if (row < p.M) dterm = __ldg(reinterpret_cast<const float4*>(p.dirterm) + row / p.dir_div);
-          }
-          mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
-          acc_par ^= 1u << t;
-          tc_fence_after();
-          tl_mark(p.timeline, tl_on && ew == 0, TL_ACC + ph * 2 + t);
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * kHidden;
-          if (P.epi == EPI_HIDDEN) {
-            long long* tl = (p.timeline && tl_on && ew == 0 && ph == 2 && t == 0) ? p.timeline + TL_EPI : nullptr;
-            const uint32_t bias_addr = base + OFF_BIAS + (uint32_t)(P.layer * kHidden + cg * 64) * 4u;
-            const uint32_t row_base = a_base + t * A_SLOT_BYTES + cg * A_BLOCK_BYTES + row_off;
-            epilogue_half<ACT>(taddr + cg * 64, bias_addr, row_base, xr, 0);
-            if (tl) tl[0] = clock64();
-            epilogue_half<ACT>(taddr + cg * 64 + 32, bias_addr + 128u, row_base, xr, 4);
-            if (tl) tl[1] = clock64();
-          } else if (P.epi == EPI_MORE) {
-            // first layer wider than 256: the remaining K blocks replace the ones just consumed
-            load_input(it, t, kb_first, p.ph[ph + 1].nkb);
-          } else {
-            if (cg == 0) {
-              // output layer: n_out <= 48 columns of the accumulator
-              const long long row = row_of(it, t);
-              const bool live = row < p.M;
-              float v[48];
-              tmem_ld16(taddr, v);
-              if (P.n_pad > 16) tmem_ld16(taddr + 16, v + 16);
-              if (P.n_pad > 32) tmem_ld16(taddr + 32, v + 32);
-              tmem_wait_ld();
-              const float* bo = s_bias + P.layer * kHidden;
-              if (MODE == IN_ENCODE || MODE == IN_LOAD2) {
-                // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
-                if (live)
-                  *reinterpret_cast<float4*>(p.out + row * 4) =
-                      make_float4(v[0] + bo[0] + dterm.x, v[1] + bo[1] + dterm.y, v[2] + bo[2] + dterm.z, v[3] + bo[3] + dterm.w);
-              } else if (live) {
-                float* orow = p.out + row * p.n_out;
+    // per slot: raw inputs of the next tile and the view-direction term, fetched one phase ahead (two register copies,
+    // selected by the run-time slot index)
+    float xin0[kXin], xin1[kXin];
+    float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
 #pragma unroll
-                for (int o = 0; o < 48; ++o) {
-                  if (o < p.n_out) {
-                    int kind = HEAD_NONE;
+    for (int i = 0; i < kXin; ++i) { xin0[i] = 0.f; xin1[i] = 0.f; }
+    auto body = [&](int t) {
+      const int ph = cur.ph(t);
+      const int epi = p.ph[ph].epi, layer = p.ph[ph].layer;
+      const long long tile = cur.tile(t);
+      const bool tl_on = kTimeline && blockIdx.x == 0 && tile == tl_tile0 + t && lane == 0;
+      const bool has_next = (epi == EPI_OUT) && cur.has_next(t);
+      if (ph == cur.np - 2) {
+        // one phase before the output layer: start the global loads the output epilogue will need
+        if (kCompute && cur.has_next(t)) {
+          float xin[kXin];
+          fetch_input(row_of(tile + cur.stride), xin);
 #pragma unroll
-                    for (int gq = 0; gq < 3; ++gq)
-                      if (o >= p.head_lo[gq] && o < p.head_lo[gq + 1]) kind = p.head_act[gq];
-                    orow[o] = head_apply_fast(v[o] + bo[o], kind);
-                  }
-                }
-              }
-            }
-            // the slot's operand buffer is free (all MMAs of this tile are complete): next tile's first-layer operand
-            if (has_next) {
-              if (kCompute) store_pre(t, pre);
-              else load_input(it + 1, t, 0, kb_first);
-            }
-          }
-          publish(t, (p.timeline && tl_on && ew == 0 && ph == 2 && t == 0) ? p.timeline + TL_EPI + 2 : nullptr);
-          tl_mark(p.timeline, tl_on && ew == 0, TL_ARR + ph * 2 + t);
-          tl_mark(p.timeline, tl_on && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+          for (int i = 0; i < kXin; ++i) { if (t) xin1[i] = xin[i]; else xin0[i] = xin[i]; }
+        }
+        if (kNerf && ch == 0) {
+          const float4 d = fetch_dterm(row_of(tile));
+          if (t) dterm1 = d; else dterm0 = d;
         }
       }
-    }
+      uint32_t pre[16];
+      if (kCompute && has_next) {                            // overlaps the wait below
+        float xin[kXin];
+#pragma unroll
+        for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
+        precompute_input(xin, row_of(tile + cur.stride) < p.M, pre);
+      }
+      mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+      acc_par ^= 1u << t;
+      tc_fence_after();
+      tl_mark(p.timeline, tl_on && ew == 0, TL_ACC + ph * 2 + t);
+      tl_mark(p.timeline, kTimeline && blockIdx.x == 1 && tile == tl_tile0 + t && threadIdx.x == 0, TL_FACC + ph * 2 + t);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * kHidden;
+      if (epi == EPI_HIDDEN) {
+        // 128 columns per thread, in two 64-column groups: the second group's tcgen05.ld is in flight while the first
+        // group is converted and stored
+        // this thread's columns: [64 ch, +64) -> K block ch, then [128 + 64 ch, +64) -> K block 2 + ch, so the warps'
+        // first groups together complete K blocks {0,1} (operand half 0) and their second groups {2,3} (half 1)
+        const uint32_t bias_addr = base + OFF_BIAS + (uint32_t)(layer * kHidden + ch * 64) * 4u;
+        const uint32_t row_base = a_base + t * A_SLOT_BYTES + ch * A_BLOCK_BYTES + row_off;
+        float v[128];
+        tmem_ld32(taddr + ch * 64, v);
+        tmem_ld32(taddr + ch * 64 + 32, v + 32);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 128 + ch * 64, v + 64);
+        tmem_ld32(taddr + 128 + ch * 64 + 32, v + 96);
+        epilogue_store64<ACT>(v, bias_addr, row_base, xr);
+        tmem_wait_ld();                                      // every accumulator column of this thread is in registers
+        if (p.split) publish(t, 1);                          // K blocks {0,1} are ready: the next layer's MMAs may start
+        epilogue_store64<ACT>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
+        publish(t, p.split ? 2 : 3);
+      } else if (epi == EPI_MORE) {
+        // first layer wider than 256: the remaining K blocks replace the ones just consumed
+        load_input(tile, t, kb_first, p.ph[ph + 1].nkb);
+        publish(t, 3);
+      } else {
+        // Output layer.  Order matters: the accumulator is pulled into registers, the next tile's first-layer operand
+        // is written and the slot is PUBLISHED before anything goes to global memory -- the proxy fence in publish()
+        // is a CTA-wide memory barrier, and behind a global store it would wait for the store's L2 round trip.
+        const long long row = row_of(tile);
+        const bool live = row < p.M;
+        float v[48];
+        if (ch == 0) {
+          const int n_pad = p.ph[ph].n_pad;
+          tmem_ld16(taddr, v);
+          if (n_pad > 16) tmem_ld16(taddr + 16, v + 16);
+          if (n_pad > 32) tmem_ld16(taddr + 32, v + 32);
+          tmem_wait_ld();
+        }
+        if (has_next) {
+          if (kCompute) store_pre(t, pre);
+          else load_input(tile + cur.stride, t, 0, kb_first);
+        }
+        publish(t, 3);
+        if (ch == 0 && live) {
+          const float* bo = s_bias + layer * kHidden;
+          if (kNerf) {
+            // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
+            const float4 d = t ? dterm1 : dterm0;
+            *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
+          } else {
+            float* orow = p.out + row * p.n_out;
+#pragma unroll
+            for (int o = 0; o < 48; ++o) {
+              if (o < p.n_out) {
+                int kind = HEAD_NONE;
+#pragma unroll
+                for (int gq = 0; gq < 3; ++gq)
+                  if (o >= p.head_lo[gq] && o < p.head_lo[gq + 1]) kind = p.head_act[gq];
+                orow[o] = head_apply_fast(v[o] + bo[o], kind);
+              }
+            }
+          }
+        }
+      }
+      tl_mark(p.timeline, tl_on && ew == 0, TL_ARR + ph * 2 + t);
+      tl_mark(p.timeline, tl_on && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+      tl_mark(p.timeline, kTimeline && blockIdx.x == 1 && tile == tl_tile0 + t && threadIdx.x == 0, TL_FARR + ph * 2 + t);
+    };
+    PN_WALK(body)
   }
+#undef PN_WALK
 
   // ---- teardown: nobody may leave while the peer can still touch this CTA's shared memory or barriers ----
   tc_fence_before();
@@ -643,10 +831,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // W [out][in] fp32 -> stream of K-block chunks.  A chunk holds n_pad rows x 64 k fp16 as [CTA-0 half][CTA-1 half],
-// each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout.  fold > 1: input column k stands for the sum of
+// each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout (narrow output layers: one chunk per layer, see below).  fold > 1: input column k stands for the sum of
 // columns k, k + fold_stride, ... (the sampler's P replicated Pluecker blocks).
 __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int fold, int fold_stride, int n_pad,
-                               int kblocks, uint8_t* __restrict__ dst) {
+                               int kblocks, int merged, uint8_t* __restrict__ dst) {
   const int total = kblocks * n_pad * 64;
   const int half_rows = n_pad / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -658,8 +846,9 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_
     if (n < out_dim && ks < k_used)
       for (int f = 0; f < fold; ++f) v += W[(size_t)n * in_dim + ks + f * fold_stride];
     const int h = n / half_rows, rr = n - h * half_rows;
-    const size_t off = (size_t)kb * n_pad * 128 + (size_t)h * half_rows * 128 + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 +
-                       (((k >> 3) ^ (rr & 7)) << 4) + (k & 7) * 2;
+    // plain: [kb][rank][rows];  merged (narrow layers, one chunk per layer): [rank][kb][rows]
+    const size_t blk = merged ? ((size_t)h * kblocks + kb) : ((size_t)kb * 2 + h);
+    const size_t off = blk * half_rows * 128 + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((k >> 3) ^ (rr & 7)) << 4) + (k & 7) * 2;
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
   }
 }
@@ -723,6 +912,7 @@ struct TcLayout {
   int n_pad[kMaxLayers];
   int k_used[kMaxLayers];
   size_t chunk_off[kMaxLayers];
+  bool merged[kMaxLayers];       // narrow layer whose K blocks all fit one ring slot: streamed as a single chunk
   bool has_fold;                 // sampler: a second, folded image of layer 0 (6 inputs) for the in-kernel Pluecker operand
   size_t fold_off;
   size_t img_bytes, bias_off, wdir_off, total;
@@ -739,6 +929,7 @@ static TcLayout tc_layout(int net_id, int n_layers, const int* in_dims, const in
     L.kblocks[l] = (k_used + 63) / 64;
     L.n_pad[l] = last ? (out_dims[l] + 15) / 16 * 16 : kHidden;
     L.chunk_off[l] = off;
+    L.merged[l] = last && (size_t)L.kblocks[l] * L.n_pad[l] * 64 <= (size_t)tc::RING_SLOT_BYTES;
     off += (size_t)L.kblocks[l] * L.n_pad[l] * 128;
   }
   L.has_fold = net_id == PN_NET_SAMPLER && in_dims[0] % 6 == 0;
@@ -777,13 +968,13 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   for (int l = 0; l < n_layers; ++l) {
     int total = L.kblocks[l] * L.n_pad[l] * 64;
     tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[l], out_dims[l], in_dims[l], L.k_used[l], 1, 0, L.n_pad[l], L.kblocks[l],
-                                                                 blob + L.chunk_off[l]);
+                                                                 L.merged[l] ? 1 : 0, blob + L.chunk_off[l]);
     PN_LAUNCH_OK("pack_tc_kernel");
     tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden);
     PN_LAUNCH_OK("pack_tc_bias_kernel");
   }
   if (L.has_fold) {
-    tc::pack_tc_kernel<<<(kHidden * 64 + 255) / 256, 256, 0, stream>>>(W[0], out_dims[0], in_dims[0], 6, in_dims[0] / 6, 6, kHidden, 1,
+    tc::pack_tc_kernel<<<(kHidden * 64 + 255) / 256, 256, 0, stream>>>(W[0], out_dims[0], in_dims[0], 6, in_dims[0] / 6, 6, kHidden, 1, 0,
                                                                         blob + L.fold_off);
     PN_LAUNCH_OK("pack_tc_kernel(fold)");
   }
@@ -831,14 +1022,21 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   for (int i = 0; i < 3; ++i) p.head_act[i] = Lc.head_act[i];
   p.error_flag = n.error_flag;
   p.timeline = g_tc_timeline;
+  {
+    // schedule knobs (defaults = the measured best; the environment overrides are a tuning aid)
+    static const int env_shift = getenv("PN_TC_SHIFT") ? atoi(getenv("PN_TC_SHIFT")) : -1;
+    static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
+    p.split = env_split >= 0 ? (env_split != 0) : 0;
+    p.shift = env_shift;   // resolved after the phase table is built
+  }
   if (Lc.input_mode == IN_PLUECKER) {
     if (6 * Lc.P != n.in_dim[0] || !L.has_fold) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
   }
   // phase table: layer 0 (possibly split when wider than 256 inputs, or folded), hidden layers, output layer
   int np = 0;
-  auto add_phase = [&](int layer, int nkb, int k16_last, int n_pad, int acc, int epi, size_t w_off) {
+  auto add_phase = [&](int layer, int nkb, int k16_last, int n_pad, int acc, int epi, size_t w_off, bool merged = false) {
     tc::Phase& P = p.ph[np++];
-    P.layer = layer; P.nkb = nkb; P.k16_last = k16_last; P.n_pad = n_pad; P.acc = acc; P.epi = epi; P.w_off = (uint32_t)w_off;
+    P.layer = layer; P.nkb = nkb; P.k16_last = k16_last; P.n_pad = n_pad; P.acc = acc; P.epi = epi; P.merged = merged ? 1 : 0; P.w_off = (uint32_t)w_off;
   };
   const int last = n.n_layers - 1;
   if (Lc.input_mode == IN_PLUECKER) {
@@ -854,8 +1052,10 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     }
   }
   for (int l = 1; l < last; ++l) add_phase(l, 4, 4, kHidden, 0, tc::EPI_HIDDEN, L.chunk_off[l]);
-  add_phase(last, 4, 4, L.n_pad[last], 0, tc::EPI_OUT, L.chunk_off[last]);
+  add_phase(last, 4, 4, L.n_pad[last], 0, tc::EPI_OUT, L.chunk_off[last], L.merged[last]);
   p.n_phases = np;
+  if (p.shift < 0) p.shift = 0;
+  if (p.shift > np - 1) p.shift = np - 1;
 
   // NeRF: view-direction term of the last layer, fp32, one row per ray (run_network) or per sample (forward)
   if (n.net_id == PN_NET_NERF) {

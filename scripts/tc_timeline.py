@@ -30,5 +30,9 @@ print(f"[{which}] phase slot: mma_start mma_issued | acc_seen(w2) arrive(w2) arr
 for ph in range(nph):
     for s in range(2):
         i = ph * 2 + s
-        print(f"  ph {ph} slot {s}: {rel(i)} {rel(20 + i)} | {rel(40 + i)} {rel(60 + i)} {rel(80 + i)}")
+        off = (t[141] - t[140]) if (t[140] and t[141]) else 0
+        fr = lambda j: (t[j] - off - t0) if t[j] else None
+        print(f"  ph {ph} slot {s}: {rel(i)} {rel(20 + i)} | {rel(40 + i)} {rel(60 + i)} {rel(80 + i)} | follower acc_seen {fr(150 + i)} arrive {fr(170 + i)}")
 print("epilogue warp 0, phase 2 slot 0: acc seen", rel(40 + 4), " ld done", rel(100), " stores done", rel(101), " fence done", rel(102), " arrived", rel(60 + 4))
+print("  first-group wait done", rel(109), " chunk stores", [rel(110 + c) for c in range(8)])
+print("  second-group wait done", rel(118), " chunk stores", [rel(119 + c) for c in range(8)])
