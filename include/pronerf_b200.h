@@ -139,6 +139,20 @@ int pn_project_gather(const float* texels, const int* tex_index_host, int NN, in
                       const float* ro_w, const float* rd_w, int ray_stride, const float* depth3d, int64_t N, int S,
                       float* epi, int epi_stride, int epi_col0, int32_t* x0y0, pn_stream_t stream);
 
+/* trt.py:631-661 fused, for the PN_PREC_BF16 tier (S in {4, 8, 16}): pn_sort_lift + pn_refine_pluecker +
+ * pn_project_gather in one kernel.  heads [N, >=3S] = sampler output; rays / or_rays [N, ray_stride] = NDC / world
+ * ray batches (cols 0..7 / 0..5 used).  Outputs: depth, add, mul [N,S] (sorted, fp32) and refine_in_f16
+ * [N, 6S+3*NN*S] = torch.cat([plucker_embed, epi_features]) (trt.py:661) rounded to IEEE fp16, 16-byte aligned,
+ * which pn_refine_forward_f16 / the fused render path consume.  Optional x0y0 [NN*S, N, 2] int32 as in pn_warp. */
+int pn_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
+                        const float* texels, const int* tex_index_host, int NN, int H, int W, const float* project_mat,
+                        int64_t N, int S, float* depth, float* add, float* mul, void* refine_in_f16, int32_t* x0y0,
+                        pn_stream_t stream);
+
+/* pn_refine_forward on the tensor-core tier with the fp16 input rows of pn_refine_input_f16:
+ * x_f16 [N, 6S+3*NN*S] fp16 (dense, 16-byte aligned, row length a multiple of 8) -> out [N, 4S+3] fp32. */
+int pn_refine_forward_f16(pn_ctx_t* ctx, const void* x_f16, int64_t N, int S, float* out, pn_stream_t stream);
+
 /* trt.py:656-658: per-sample Pluecker features of (o + d*depth_s, d) into out[:, 0:6S] (row stride out_stride). */
 int pn_refine_pluecker(const float* rays, int ray_stride, const float* depth, int64_t N, int S, float* out,
                        int out_stride, pn_stream_t stream);

@@ -235,6 +235,19 @@ int pn_refine_forward(pn_ctx_t* c, const float* x, int64_t N, int S, float* out,
   return run_mlp(c, PN_NET_REFINE, L, precision, as_stream(stream));
 }
 
+int pn_refine_forward_f16(pn_ctx_t* c, const void* x_f16, int64_t N, int S, float* out, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && x_f16 && out && N >= 0 && S >= 1, "pn_refine_forward_f16: bad arguments");
+  const NetF32& n = c->f32[PN_NET_REFINE];
+  PN_REQUIRE(!n.loaded || n.out_dim[n.n_layers - 1] == 4 * S + 3, "pn_refine_forward_f16: net output width %d != 4S+3 (S=%d)",
+             n.out_dim[n.n_layers - 1], S);
+  MlpLaunch L{};
+  L.act = 1; L.input_mode = IN_LOAD16; L.in0 = reinterpret_cast<const float*>(x_f16); L.in1 = nullptr; L.in_stride = n.in_dim[0];
+  L.S = S; L.P = 0; L.M = N; L.out = out;
+  heads_refine(L, S);
+  return run_mlp(c, PN_NET_REFINE, L, PN_PREC_BF16, as_stream(stream));
+}
+
 static int check_nerf(const NetF32& n) {
   if (!n.loaded) return PN_OK;   // run_mlp reports it
   PN_REQUIRE(n.in_dim[0] == 63 && n.in_dim[n.n_layers - 1] == kHidden + 27 && n.out_dim[n.n_layers - 1] == 4,
@@ -325,6 +338,16 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
     if (rc != PN_OK) return rc;
   }
   PN_STAGE_MARK(1);
+  // fp16 tier: sort/lift + Pluecker + project/gather run as ONE kernel that writes the refine input as fp16 rows,
+  // which the refine MLP's first-layer operand loads chunk for chunk (timed as the project_gather stage)
+  const bool fused_input = f->precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported;
+  if (fused_input) {
+    PN_STAGE_MARK(2);
+    PN_STAGE_MARK(3);
+    rc = pn_refine_input_f16(heads, hs, f->rays, f->or_rays, 11, f->texels, f->tex_index, NN, f->H, f->W, f->project_mat, N, S, depth,
+                             add, mul, rin, nullptr, stream);
+    if (rc != PN_OK) return rc;
+  } else {
   // (2) sort + lift  trt.py:631-637
   rc = pn_sort_lift(heads, hs, f->rays, 11, N, S, depth, add, mul, nullptr, depth3d, stream);
   if (rc != PN_OK) return rc;
@@ -336,11 +359,12 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   rc = pn_project_gather(f->texels, f->tex_index, NN, f->H, f->W, f->project_mat, f->or_rays, f->or_rays + 3, 11, depth3d, N, S, rin, ri,
                          6 * S, nullptr, stream);
   if (rc != PN_OK) return rc;
+  }
   PN_STAGE_MARK(4);
   // (4) refine MLP  trt.py:668
   {
     MlpLaunch L{};
-    L.act = 1; L.input_mode = IN_LOAD; L.in0 = rin; L.in_stride = ri; L.S = S; L.P = 0; L.M = N; L.out = rout;
+    L.act = 1; L.input_mode = fused_input ? IN_LOAD16 : IN_LOAD; L.in0 = rin; L.in_stride = ri; L.S = S; L.P = 0; L.M = N; L.out = rout;
     heads_refine(L, S);
     rc = run_mlp(c, PN_NET_REFINE, L, f->precision, st);
     if (rc != PN_OK) return rc;

@@ -55,6 +55,7 @@ enum InputMode : int {
   IN_LOAD2 = 1,       // DoNeRFTRT.forward: [M,63] embedded + [M,27] embedded_dirs (joins at the last layer)
   IN_ENCODE = 2,      // run_network: [M,3] points + per-ray [M/S,3] view dirs, encoded in-kernel
   IN_PLUECKER = 3,    // sampler: rays [N, stride] -> 6P Pluecker features generated in-kernel
+  IN_LOAD16 = 4,      // rows come from a dense fp16 [M, K0] tensor (K0 % 8 == 0, 16-byte aligned): refine_input from pn_refine_input_f16
 };
 
 // Output-head activations, applied per column range of the last layer.
@@ -64,7 +65,7 @@ struct MlpLaunch {
   const NetF32* net;
   int act;                 // 0 = ReLU (NeRF), 1 = ELU (sampler / refine)
   int input_mode;
-  const float* in0;        // IN_LOAD: x; IN_LOAD2: embedded; IN_ENCODE: pts; IN_PLUECKER: rays
+  const float* in0;        // IN_LOAD: x; IN_LOAD2: embedded; IN_ENCODE: pts; IN_PLUECKER: rays; IN_LOAD16: fp16 x (cast)
   const float* in1;        // IN_LOAD2: embedded_dirs; IN_ENCODE: viewdirs
   int in_stride;           // row stride of in0 in floats
   int in1_stride;          // row stride of in1 in floats (IN_ENCODE: viewdirs; 3 dense, 11 inside a ray batch)

@@ -20,6 +20,8 @@
 // reference views (12 MB at 504x378) stay L2-resident.  One thread handles one (ray, sample) and loops
 // over the NN views so the ray and depth are loaded once; the 3*NN results of a thread are written
 // straight into the refine network's input row.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pn {
@@ -129,6 +131,103 @@ project_gather_kernel(const float4* __restrict__ texels, TexIndex tex, int NNr, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused form for the fp16 tensor-core tier: trt.py:631-661 in ONE pass over the sampler heads.
+//   scale + stable sort + gather add/mul + depth lift (631-637)  ->  per-sample Pluecker features (656-658)
+//   ->  projection + bilinear fetch (649-655)  ->  refine_input row [6S + 3*NN*S] written as fp16.
+// One thread per (ray, sample); the S lanes of a ray rank their depths with shuffles (rank = position in torch's
+// stable ascending sort, NaN last), so thread (ray, i) simply becomes sorted sample rho(i).  The refine-input rows
+// of a block (256/S rays, contiguous in memory) are staged in shared memory and leave as 16-byte coalesced stores;
+// the fp16 rows are what the refine MLP's first-layer operand consumes (mlp_tc.cu, IN_LOAD16), chunk for chunk.
+// Same projection arithmetic as project_gather_kernel: floor(ix), floor(iy) stay bit-exact.
+__device__ __forceinline__ bool sort_after(float a, float b) { return (a > b) || (isnan(a) && !isnan(b)); }
+
+template <int S, int NN_T>
+__global__ void __launch_bounds__(256)
+refine_input_kernel(const float* __restrict__ heads, int head_stride, const float* __restrict__ rays,
+                    const float* __restrict__ or_rays, int rs, const float4* __restrict__ texels, TexIndex tex, int NNr,
+                    int H, int W, const float* __restrict__ pm, int64_t N, float* __restrict__ depth,
+                    float* __restrict__ add, float* __restrict__ mul, __half* __restrict__ rin, int32_t* __restrict__ x0y0) {
+  constexpr int RPB = 256 / S;                              // rays per block
+  constexpr int KMAX = 6 * S + 3 * 8 * S;
+  __shared__ float sM[8 * 12];
+  __shared__ __align__(16) __half stage[RPB * KMAX];
+  const int NN = NN_T > 0 ? NN_T : NNr;
+  const int K0 = 6 * S + 3 * NN * S;
+  for (int i = threadIdx.x; i < NN * 12; i += blockDim.x) sM[i] = pm[i];
+  __syncthreads();
+  const int64_t ray0 = (int64_t)blockIdx.x * RPB;
+  const int rl = threadIdx.x / S, i = threadIdx.x % S;
+  const int64_t r_raw = ray0 + rl;
+  const bool live = r_raw < N;
+  const int64_t r = live ? r_raw : N - 1;
+  const float* h = heads + r * head_stride;
+  const float* ray = rays + r * rs;
+  const float near_ = ray[6], far_ = ray[7];
+  const float v = __fadd_rn(__fmul_rn(h[i], __fsub_rn(far_, near_)), near_);   // depth * (far - near) + near   trt.py:631
+  int rho = 0;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const float vj = __shfl_sync(0xffffffffu, v, j, S);
+    rho += (sort_after(v, vj) || (!sort_after(vj, v) && j < i)) ? 1 : 0;
+  }
+  if (live) {
+    depth[r * S + rho] = v;
+    add[r * S + rho] = h[S + i];
+    mul[r * S + rho] = h[2 * S + i];
+  }
+  __half* srow = stage + rl * K0;
+  {
+    // Pluecker features of (o + d * depth, d)   trt.py:656-658
+    float f[6];
+    pluecker6(__fadd_rn(ray[0], __fmul_rn(ray[3], v)), __fadd_rn(ray[1], __fmul_rn(ray[4], v)),
+              __fadd_rn(ray[2], __fmul_rn(ray[5], v)), ray[3], ray[4], ray[5], f);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) srow[6 * rho + j] = __float2half_rn(f[j]);
+  }
+  // lift (trt.py:637) and project into the NN neighbour views
+  const float d3 = __fdiv_rn(1.f, __fsub_rn(__fsub_rn(1.f, v), 1e-5f));
+  const float* orr = or_rays + r * rs;
+  const float w0 = __fadd_rn(orr[0], __fmul_rn(orr[3], d3));
+  const float w1 = __fadd_rn(orr[1], __fmul_rn(orr[4], d3));
+  const float w2 = __fadd_rn(orr[2], __fmul_rn(orr[5], d3));
+  const float w3 = __fadd_rn(1.f, __fmul_rn(0.f, d3));
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const float wh = wm1 / 2.f, hh = hm1 / 2.f;
+#pragma unroll
+  for (int k = 0; k < (NN_T > 0 ? NN_T : 8); ++k) {
+    if (k >= NN) break;
+    Tap tp = project_point(sM + 12 * k, w0, w1, w2, w3, wm1, hm1, wh, hh);
+    Bilin b = bilinear_setup(tp, W, H);
+    const float4* img = texels + (int64_t)tex.v[k] * H * W;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* row0 = img + (int64_t)b.y0 * W + b.x0;
+    const float4* row1 = row0 + W;
+    const bool v00 = b.vx0 && b.vy0, v01 = b.vx1 && b.vy0, v10 = b.vx0 && b.vy1, v11 = b.vx1 && b.vy1;
+    float4 c00 = v00 ? __ldg(row0) : z4;
+    float4 c01 = v01 ? __ldg(row0 + 1) : z4;
+    float4 c10 = v10 ? __ldg(row1) : z4;
+    float4 c11 = v11 ? __ldg(row1 + 1) : z4;
+    float nw = v00 ? b.nw : 0.f, ne = v01 ? b.ne : 0.f, sw = v10 ? b.sw : 0.f, se = v11 ? b.se : 0.f;
+    __half* o = srow + 6 * S + (k * S + rho) * 3;
+    o[0] = __float2half_rn(c00.x * nw + c01.x * ne + c10.x * sw + c11.x * se);
+    o[1] = __float2half_rn(c00.y * nw + c01.y * ne + c10.y * sw + c11.y * se);
+    o[2] = __float2half_rn(c00.z * nw + c01.z * ne + c10.z * sw + c11.z * se);
+    if (x0y0 && live) {
+      int64_t b_idx = ((int64_t)(k * S + rho) * N + r) * 2;
+      x0y0[b_idx] = clamp_index(tp.x0f);
+      x0y0[b_idx + 1] = clamp_index(tp.y0f);
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out of the block's rows (contiguous in global memory; K0 * 2 bytes per row is a multiple of 16)
+  const int64_t live_rays = (N - ray0) < RPB ? (N - ray0) : RPB;
+  const int chunks = (int)(live_rays * K0 * 2 / 16);
+  const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+  uint4* g4 = reinterpret_cast<uint4*>(rin + ray0 * K0);
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) g4[c] = s4[c];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Drop-in form: planar img [B,C,H,W], per-batch depth [B,N], rays [*,4,N] with a batch stride, w2c [B,3,4].
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ img, int B, int C, int H, int W, const float* __restrict__ depth,
@@ -194,6 +293,36 @@ int pn_project_gather(const float* texels, const int* tex_index_host, int NN, in
     project_gather_kernel<0><<<nb, 256, 0, as_stream(stream)>>>(tx, ti, NN, H, W, project_mat, ro_w, rd_w, ray_stride, depth3d, N, S, epi,
                                                                epi_stride, epi_col0, x0y0);
   PN_LAUNCH_OK("pn_project_gather");
+  return PN_OK;
+}
+
+int pn_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
+                        const float* texels, const int* tex_index_host, int NN, int H, int W, const float* project_mat,
+                        int64_t N, int S, float* depth, float* add, float* mul, void* refine_in_f16, int32_t* x0y0,
+                        pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(heads && rays && or_rays && texels && project_mat && depth && add && mul && refine_in_f16,
+             "pn_refine_input_f16: null pointer");
+  PN_REQUIRE(NN >= 1 && NN <= 8 && H >= 2 && W >= 2 && N >= 0 && ray_stride >= 8 && head_stride >= 3 * S,
+             "pn_refine_input_f16: bad shape (NN=%d H=%d W=%d S=%d)", NN, H, W, S);
+  PN_REQUIRE(S == 4 || S == 8 || S == 16, "pn_refine_input_f16: S=%d unsupported (4, 8, 16); use the per-stage entry points", S);
+  PN_REQUIRE((reinterpret_cast<uintptr_t>(refine_in_f16) & 15) == 0, "pn_refine_input_f16: refine_in_f16 must be 16-byte aligned");
+  TexIndex ti;
+  for (int k = 0; k < 8; ++k) ti.v[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
+  for (int k = 0; k < NN; ++k) PN_REQUIRE(ti.v[k] >= 0, "pn_refine_input_f16: negative texel image index");
+  const float4* tx = reinterpret_cast<const float4*>(texels);
+  __half* rin = reinterpret_cast<__half*>(refine_in_f16);
+  cudaStream_t st = as_stream(stream);
+#define PN_RI(SS, NT)                                                                                                    \
+  refine_input_kernel<SS, NT><<<(unsigned)((N + (256 / SS) - 1) / (256 / SS)), 256, 0, st>>>(                            \
+      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, N, depth, add, mul, rin, x0y0)
+  if (NN == 4) {
+    if (S == 4) PN_RI(4, 4); else if (S == 8) PN_RI(8, 4); else PN_RI(16, 4);
+  } else {
+    if (S == 4) PN_RI(4, 0); else if (S == 8) PN_RI(8, 0); else PN_RI(16, 0);
+  }
+#undef PN_RI
+  PN_LAUNCH_OK("pn_refine_input_f16");
   return PN_OK;
 }
 

@@ -57,7 +57,8 @@ constexpr int N_BARS = 2 * N_RING + 6;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B (swizzle atom)
-constexpr int N_EPI_WARPS = 8;                          // lane quadrant x column half; ~200 registers each for deep tcgen05.ld pipelining
+constexpr int N_EPI_WARPS = 8;                          // lane quadrant x column half.  Register budget: the register file is per SM
+                                                        // sub-partition (16 K), and with 10 warps one sub-partition holds 3 -> 168 per thread
 constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 320
 // The two single-thread roles get the HIGHEST warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
 // issuer (or weight producer) stalls the whole pair (measured: 2x slower issue as warp 1 behind four epilogue warps).
@@ -677,6 +678,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         }
       }
     };
+    // --- first-layer operand, fp16 "load" mode: the tile's rows are one contiguous range of 16-byte chunks (8 halves);
+    //     chunk g of the range -> (row, chunk-in-row) -> the swizzled operand position.  Up to kPf chunks per thread are
+    //     fetched into registers BEFORE the accumulator wait of the output phase (the loads do not depend on it) and
+    //     stored once the slot's operand buffer is free. ---
+    constexpr int kPf = 9;                                 // 128 rows x 144 halves = 2304 chunks = 9 per thread
+    const int cpr = p.k0 >> 3;                             // real chunks per row
+    struct Range16 { int c_lo, w, total; };
+    auto range16 = [&](int kb_lo, int nblk) {
+      Range16 R;
+      R.c_lo = kb_lo * 8;
+      int c_hi = (kb_lo + nblk) * 8;
+      if (c_hi >= cpr) c_hi = (cpr + 1) & ~1;              // last block: pad to a whole K = 16 step with zero chunks
+      R.w = c_hi - R.c_lo;
+      R.total = TILE_M * R.w;
+      return R;
+    };
+    auto fetch16 = [&](long long tile, const Range16& R, int g, uint4& v) {
+      v = make_uint4(0u, 0u, 0u, 0u);
+      if (g < R.total) {
+        const int row = g / R.w, c = R.c_lo + (g - row * R.w);
+        const long long grow = tile * PAIR_M + (long long)rank * TILE_M + row;
+        if (grow < p.M && c < cpr) v = __ldg(reinterpret_cast<const uint4*>(p.in0) + grow * cpr + c);
+      }
+    };
+    auto store16 = [&](int t, const Range16& R, int g, const uint4& v) {
+      if (g < R.total) {
+        const int row = g / R.w, cc = g - row * R.w;       // chunk within the range: block cc >> 3, chunk cc & 7
+        st_shared_v4(a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7), v.x, v.y, v.z, v.w);
+      }
+    };
+    auto prefetch16 = [&](long long tile, int kb_lo, int nblk, uint4* pf) {
+      const Range16 R = range16(kb_lo, nblk);
+#pragma unroll
+      for (int u = 0; u < kPf; ++u) fetch16(tile, R, (int)threadIdx.x + u * (N_EPI_WARPS * 32), pf[u]);
+    };
+    // store the prefetched chunks, then load + store whatever the range holds beyond them
+    auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk, const uint4* pf, bool have_pf) {
+      const Range16 R = range16(kb_lo, nblk);
+      constexpr int NT = N_EPI_WARPS * 32;
+      if (have_pf) {
+#pragma unroll
+        for (int u = 0; u < kPf; ++u) store16(t, R, (int)threadIdx.x + u * NT, pf[u]);
+      }
+      for (int g0 = have_pf ? kPf * NT : 0; g0 < R.total; g0 += 4 * NT) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fetch16(tile, R, g0 + (int)threadIdx.x + u * NT, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) store16(t, R, g0 + (int)threadIdx.x + u * NT, v[u]);
+      }
+    };
     // publish this warp's share of slot t's operand: half 0 (its first K block; also "my accumulator reads are done"),
     // half 1 (its second K block), or both at once (first-layer operands)
     auto publish = [&](int t, int halves) {
@@ -708,6 +760,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         fetch_input(row, xin);
         precompute_input(xin, row < p.M, pre);
         store_pre(t, pre);
+      } else if (MODE == IN_LOAD16) {
+        load_input16(cur.tile(t), t, 0, kb_first, nullptr, false);
       } else {
         load_input(cur.tile(t), t, 0, kb_first);
       }
@@ -726,6 +780,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       const long long tile = cur.tile(t);
       const bool tl_on = kTimeline && blockIdx.x == 0 && tile == tl_tile0 + t && lane == 0;
       const bool has_next = (epi == EPI_OUT) && cur.has_next(t);
+      if (MODE == IN_LOAD16 && ph == cur.np - 2 && threadIdx.x == 0 && cur.has_next(t)) {
+        // one phase ahead: pull the next tile's rows (one contiguous range) towards L2
+        const long long row0 = row_of(tile + cur.stride) - r;
+        long long nrow = p.M - row0;
+        if (nrow > TILE_M) nrow = TILE_M;
+        if (nrow > 0) {
+          const uint32_t bytes = (uint32_t)(nrow * (long long)p.k0 * 2);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const __half*>(p.in0) + row0 * p.k0), "r"(bytes) : "memory");
+        }
+      }
       if (ph == cur.np - 2) {
         // one phase before the output layer: start the global loads the output epilogue will need
         if (kCompute && cur.has_next(t)) {
@@ -746,6 +810,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
         precompute_input(xin, row_of(tile + cur.stride) < p.M, pre);
       }
+      uint4 pf[kPf];
+      if (MODE == IN_LOAD16 && has_next) prefetch16(tile + cur.stride, 0, kb_first, pf);   // in flight across the wait below
       mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
       acc_par ^= 1u << t;
       tc_fence_after();
@@ -772,7 +838,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         publish(t, p.split ? 2 : 3);
       } else if (epi == EPI_MORE) {
         // first layer wider than 256: the remaining K blocks replace the ones just consumed
-        load_input(tile, t, kb_first, p.ph[ph + 1].nkb);
+        if (MODE == IN_LOAD16) load_input16(tile, t, kb_first, p.ph[ph + 1].nkb, nullptr, false);
+        else load_input(tile, t, kb_first, p.ph[ph + 1].nkb);
         publish(t, 3);
       } else {
         // Output layer.  Order matters: the accumulator is pulled into registers, the next tile's first-layer operand
@@ -790,6 +857,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         }
         if (has_next) {
           if (kCompute) store_pre(t, pre);
+          else if (MODE == IN_LOAD16) load_input16(tile + cur.stride, t, 0, kb_first, pf, true);
           else load_input(tile + cur.stride, t, 0, kb_first);
         }
         publish(t, 3);
@@ -1029,6 +1097,12 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     p.split = env_split >= 0 ? (env_split != 0) : 0;
     p.shift = env_shift;   // resolved after the phase table is built
   }
+  if (Lc.input_mode == IN_LOAD16) {
+    if (p.k0 % 8 != 0 || Lc.in_stride != p.k0 || (reinterpret_cast<uintptr_t>(Lc.in0) & 15) != 0) {
+      set_error("tc fp16 input: needs a dense, 16-byte aligned [M, K0] fp16 tensor with K0 %% 8 == 0 (K0 = %d, stride %d)", p.k0, Lc.in_stride);
+      return PN_EINVAL;
+    }
+  }
   if (Lc.input_mode == IN_PLUECKER) {
     if (6 * Lc.P != n.in_dim[0] || !L.has_fold) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
   }
@@ -1093,6 +1167,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   else if (Lc.act == 0 && Lc.input_mode == IN_LOAD2) PN_TC_LAUNCH(0, IN_LOAD2);
   else if (Lc.act == 1 && Lc.input_mode == IN_PLUECKER) PN_TC_LAUNCH(1, IN_PLUECKER);
   else if (Lc.act == 1 && Lc.input_mode == IN_LOAD) PN_TC_LAUNCH(1, IN_LOAD);
+  else if (Lc.act == 1 && Lc.input_mode == IN_LOAD16) PN_TC_LAUNCH(1, IN_LOAD16);
   else { set_error("tc: unsupported (activation, input mode) = (%d, %d)", Lc.act, Lc.input_mode); return PN_EINVAL; }
 #undef PN_TC_LAUNCH
   PN_LAUNCH_OK("mlp_tc_kernel");

@@ -108,6 +108,16 @@ class Context:
                                           stream_ptr(x.device)), "pn_refine_forward")
         return out
 
+    def refine_forward_f16(self, x16, S):
+        """Tensor-core refine MLP on the fp16 rows written by ``refine_input_f16`` -> [N, 4S+3] fp32."""
+        if x16.dtype != torch.float16:
+            raise TypeError("x16 must be torch.float16")
+        out = _empty((x16.shape[0], 4 * S + 3), x16)
+        with _cuda_guard(x16):
+            check(lib().pn_refine_forward_f16(self.handle, dptr(x16, "x16", torch.float16), x16.shape[0], S, dptr(out),
+                                              stream_ptr(x16.device)), "pn_refine_forward_f16")
+        return out
+
     def nerf_forward(self, embedded, embedded_dirs, precision="fp32"):
         e, g = as_f32c(embedded), as_f32c(embedded_dirs)
         if e.shape[-1] != 63 or g.shape[-1] != 27 or e.shape[0] != g.shape[0]:
@@ -286,6 +296,28 @@ def project_gather(texels, project_mat, ro_w, rd_w, depth3d, out=None, col0: int
                                       col0, idx.data_ptr() if want_index else None, stream_ptr(d3.device)),
               "pn_project_gather")
     return (out, idx) if want_index else out
+
+
+def refine_input_f16(heads, rays, or_rays, texels, project_mat, S, tex_index=None, want_index: bool = False):
+    """trt.py:631-661 in one kernel (fp16 tier): -> depth, add, mul [N,S] fp32 (sorted), refine_input [N, 6S+3*NN*S] fp16
+    (+ int32 floor indices [NN*S, N, 2])."""
+    heads, rays, or_rays = as_f32c(heads), as_f32c(rays), as_f32c(or_rays)
+    if rays.shape[1] != or_rays.shape[1]:
+        raise ValueError("rays and or_rays must share a row stride")
+    pm = as_f32c(project_mat)
+    NN = pm.shape[0]
+    _, H, W, _ = texels.shape
+    N = heads.shape[0]
+    depth, add, mul = (_empty((N, S), heads) for _ in range(3))
+    rin = _empty((N, 6 * S + 3 * NN * S), heads, torch.float16)
+    idx = _empty((NN * S, N, 2), heads, torch.int32) if want_index else None
+    ti = (C.c_int * NN)(*[int(v) for v in tex_index]) if tex_index is not None else None
+    with _cuda_guard(heads):
+        check(lib().pn_refine_input_f16(dptr(heads, "heads"), heads.shape[1], dptr(rays, "rays"), dptr(or_rays, "or_rays"),
+                                        rays.shape[1], dptr(texels, "texels"), ti, NN, H, W, dptr(pm, "project_mat"), N, S,
+                                        dptr(depth), dptr(add), dptr(mul), rin.data_ptr(), idx.data_ptr() if want_index else None,
+                                        stream_ptr(heads.device)), "pn_refine_input_f16")
+    return (depth, add, mul, rin, idx) if want_index else (depth, add, mul, rin)
 
 
 def refine_pluecker(rays, depth, out=None):

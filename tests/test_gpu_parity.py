@@ -358,6 +358,64 @@ def test_mlps_bf16_vs_reference(ops, which, golden_small_random, golden_small_ca
             assert mx < 5e-2 and rms < 1.5e-2, (mx, rms)
 
 
+@pytest.mark.parametrize("S", [4, 8, 16])
+def test_refine_input_f16_fused(ops, S, golden_small_calibrated):
+    """trt.py:631-661 as ONE kernel (fp16 tier) against the oracle's three stages on identical sampler heads:
+    sorted depth / add / mul and the projected tap indices BIT-EXACT; the refine-input row == the oracle's fp32 row
+    rounded to fp16 (<= 1 fp16 ulp: the bilinear blend may differ by an fp32 rounding before the conversion)."""
+    g = golden_small_calibrated
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    images = scene.images_ref[g["ref_nos"]]
+    rays, or_rays = T(g["rays"]), T(g["or_rays"])
+    N = rays.shape[0]
+    gen = torch.Generator().manual_seed(100 + S)
+    heads = torch.rand(N, 3 * S + 3, generator=gen)
+    heads[:40, 1] = heads[:40, 0]                        # exact ties: the rank must be the stable one
+    heads[40:60, :S] = 0.5
+    heads[60:70, 2] = 0.999999                           # lifted depth ~ 1e5: taps far outside the image
+    heads[:, S:3 * S] = torch.randn(N, 2 * S, generator=gen)
+    pm = T(g["project_mat"])
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    d_ref, a_ref, m_ref, _, d3_ref = O.sort_lift(heads[:, :S], heads[:, S:2 * S], heads[:, 2 * S:3 * S], near, far)
+    pg = O.project_gather(images, pm, or_rays[:, 0:3], or_rays[:, 3:6], d3_ref)
+    rin_ref = O.refine_input(rays[:, 0:3], rays[:, 3:6], d_ref, pg["epi"])
+    tex = ops.pack_images(T(images, DEV))
+    d, a, m, rin, idx = ops.refine_input_f16(heads.to(DEV), rays.to(DEV), or_rays.to(DEV), tex, pm.to(DEV), S, want_index=True)
+    assert torch.equal(d.cpu(), d_ref) and torch.equal(a.cpu(), a_ref) and torch.equal(m.cpu(), m_ref)
+    idx = idx.cpu().long()
+    big = 2 ** 30
+    assert torch.equal(idx[..., 0], pg["x0"].clamp(-big, big)) and torch.equal(idx[..., 1], pg["y0"].clamp(-big, big))
+    assert rin.dtype == torch.float16 and rin.shape == rin_ref.shape
+    want = rin_ref.to(torch.float16).float().numpy()
+    got = rin.cpu().float().numpy()
+    ulp = np.maximum(np.abs(want), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(got - want) <= ulp), np.abs(got - want).max()
+    assert (got == want).mean() > 0.999
+    # ragged tail: any prefix of the batch gives the same rows
+    for n in (1, 31, 33, 257):
+        d2, a2, m2, rin2 = ops.refine_input_f16(heads[:n].to(DEV), rays[:n].to(DEV), or_rays[:n].to(DEV), tex, pm.to(DEV), S)
+        assert torch.equal(d2, d[:n]) and torch.equal(rin2, rin[:n]) and torch.equal(a2, a[:n]) and torch.equal(m2, m[:n])
+
+
+def test_refine_forward_f16_input(ops, golden_small_calibrated):
+    """The refine MLP fed fp16 rows (IN_LOAD16: register-prefetched 16-byte chunks) == the same kernel fed the fp32 tensor
+    (both round the operand to fp16 with the same rounding), for ragged row counts around the 128-row tile."""
+    _bf16_ready(ops)
+    g = golden_small_calibrated
+    sd = synth.make_weights(seed=0, calibrated=True)
+    _, _, refn = make_modules(sd, DEV, precision="bf16")
+    x = T(g["refine_input"], DEV)
+    x = torch.cat([x, x.flip(0) * 0.5, x * 0.25], 0)        # > 2 row tiles per CTA pair
+    ctx = refn._ctx()
+    full = ctx.refine_forward(x, 8, precision="bf16")
+    for n in (x.shape[0], 1, 127, 129, 512, 513, 1500):
+        a = ctx.refine_forward_f16(x[:n].to(torch.float16).contiguous(), 8)
+        assert torch.equal(a, full[:n]), (n, (a - full[:n]).abs().max().item())
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        ctx.refine_forward_f16(x.to(torch.float16).reshape(-1)[4:4 + 144 * 8].reshape(8, 144), 8)
+
+
 @pytest.mark.parametrize("which", ["random", "calibrated"])
 def test_render_bf16_delta_psnr(ops, which, golden_fern):
     """BASELINE frame in the bf16 tier: |PSNR(ours, gt) - PSNR(fp32 tier, gt)| <= 0.05 dB (north-star bound);
