@@ -271,6 +271,14 @@ __device__ __forceinline__ uint32_t pack_h2_elu(float lo, float hi) {
   asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h), "r"(n));
   return r;
 }
+// ELU in fp32: max(y, 2^(-|y| log2 e) - 1).  For y <= 0 that is e^y - 1 (>= y); for y > 0 the right side is negative.  The
+// -|.| rides on the MUFU operand modifiers, and FMUL / FADD / FMNMX issue at twice the rate of the packed-half ops
+// (measured: scripts/ubench/alu_rate.cu), so this beats the f16x2 form (whose ex2 is two MUFU ops anyway) and is exact to fp32.
+__device__ __forceinline__ float elu_f32(float y) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(y * 1.4426950408889634f)));
+  return fmaxf(y, e - 1.f);
+}
 // packed fp32x2 add (Blackwell FADD2): {o0,o1} = {x0,x1} + {b0,b1}
 __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, float& o0, float& o1) {
   asm("{\n\t.reg .b64 a, b, c;\n\t"
@@ -358,7 +366,7 @@ __device__ __forceinline__ void epilogue_store64(const float* v, uint32_t bias_a
     add2(x[6], x[7], bb.z, bb.w, y[6], y[7]);
     uint32_t w[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : pack_h2_elu(y[2 * u], y[2 * u + 1]);
+    for (int u = 0; u < 4; ++u) w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : pack_h2(elu_f32(y[2 * u]), elu_f32(y[2 * u + 1]));
     st_shared_v4(row_base + ((uint32_t)(c << 4) ^ xr), w[0], w[1], w[2], w[3]);
     if (kTimeline && tl) tl[c] = clock64();
   }
@@ -768,101 +776,148 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       publish(t, 3);
     }
 
-    // per slot: raw inputs of the next tile and the view-direction term, fetched one phase ahead (two register copies,
-    // selected by the run-time slot index)
-    float xin0[kXin], xin1[kXin];
+    // The epilogue warps are the busiest resource of the kernel and a lone warp retires one DEPENDENT instruction every
+    // ~5 cycles, so their control flow is spelled out as plain nested loops (iteration -> phase -> slot; the two slots run
+    // in step) with everything per-phase hoisted, instead of the generic cursor walk of the single-thread roles.
+    float xin0[kXin], xin1[kXin];                          // raw inputs of each slot's NEXT tile, fetched one phase ahead
     float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
 #pragma unroll
     for (int i = 0; i < kXin; ++i) { xin0[i] = 0.f; xin1[i] = 0.f; }
-    auto body = [&](int t) {
-      const int ph = cur.ph(t);
-      const int epi = p.ph[ph].epi, layer = p.ph[ph].layer;
-      const long long tile = cur.tile(t);
-      const bool tl_on = kTimeline && blockIdx.x == 0 && tile == tl_tile0 + t && lane == 0;
-      const bool has_next = (epi == EPI_OUT) && cur.has_next(t);
-      if (MODE == IN_LOAD16 && ph == cur.np - 2 && threadIdx.x == 0 && cur.has_next(t)) {
-        // one phase ahead: pull the next tile's rows (one contiguous range) towards L2
-        const long long row0 = row_of(tile + cur.stride) - r;
-        long long nrow = p.M - row0;
-        if (nrow > TILE_M) nrow = TILE_M;
-        if (nrow > 0) {
-          const uint32_t bytes = (uint32_t)(nrow * (long long)p.k0 * 2);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const __half*>(p.in0) + row0 * p.k0), "r"(bytes) : "memory");
-        }
-      }
-      if (ph == cur.np - 2) {
-        // one phase before the output layer: start the global loads the output epilogue will need
-        if (kCompute && cur.has_next(t)) {
-          float xin[kXin];
-          fetch_input(row_of(tile + cur.stride), xin);
-#pragma unroll
-          for (int i = 0; i < kXin; ++i) { if (t) xin1[i] = xin[i]; else xin0[i] = xin[i]; }
-        }
-        if (kNerf && ch == 0) {
-          const float4 d = fetch_dterm(row_of(tile));
-          if (t) dterm1 = d; else dterm0 = d;
-        }
-      }
-      uint32_t pre[16];
-      if (kCompute && has_next) {                            // overlaps the wait below
-        float xin[kXin];
-#pragma unroll
-        for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
-        precompute_input(xin, row_of(tile + cur.stride) < p.M, pre);
-      }
-      uint4 pf[kPf];
-      if (MODE == IN_LOAD16 && has_next) prefetch16(tile + cur.stride, 0, kb_first, pf);   // in flight across the wait below
-      mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
-      acc_par ^= 1u << t;
-      tc_fence_after();
-      tl_mark(p.timeline, tl_on && ew == 0, TL_ACC + ph * 2 + t);
-      tl_mark(p.timeline, kTimeline && blockIdx.x == 1 && tile == tl_tile0 + t && threadIdx.x == 0, TL_FACC + ph * 2 + t);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * kHidden;
-      if (epi == EPI_HIDDEN) {
-        // 128 columns per thread, in two 64-column groups: the second group's tcgen05.ld is in flight while the first
-        // group is converted and stored
-        // this thread's columns: [64 ch, +64) -> K block ch, then [128 + 64 ch, +64) -> K block 2 + ch, so the warps'
-        // first groups together complete K blocks {0,1} (operand half 0) and their second groups {2,3} (half 1)
-        const uint32_t bias_addr = base + OFF_BIAS + (uint32_t)(layer * kHidden + ch * 64) * 4u;
-        const uint32_t row_base = a_base + t * A_SLOT_BYTES + ch * A_BLOCK_BYTES + row_off;
-        float v[128];
-        tmem_ld32(taddr + ch * 64, v);
-        tmem_ld32(taddr + ch * 64 + 32, v + 32);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 128 + ch * 64, v + 64);
-        tmem_ld32(taddr + 128 + ch * 64 + 32, v + 96);
-        epilogue_store64<ACT>(v, bias_addr, row_base, xr);
-        tmem_wait_ld();                                      // every accumulator column of this thread is in registers
-        if (p.split) publish(t, 1);                          // K blocks {0,1} are ready: the next layer's MMAs may start
-        epilogue_store64<ACT>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
-        publish(t, p.split ? 2 : 3);
-      } else if (epi == EPI_MORE) {
+    const int np = p.n_phases;
+    const bool more = p.ph[0].epi == EPI_MORE;
+    const long long stride = cur.stride;
+    const uint32_t bias_base = base + OFF_BIAS + (uint32_t)(ch * 64) * 4u;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row = a_base + row_off;
+    int it_idx = 0;
+    for (long long T0 = 2 * cluster_id; T0 < n_pairs; T0 += stride, ++it_idx) {
+      const int nslots = (T0 + 1 < n_pairs) ? 2 : 1;
+      const bool tl_it = kTimeline && blockIdx.x == 0 && it_idx == 1 && lane == 0;
+      const bool tl_f = kTimeline && blockIdx.x == 1 && it_idx == 1 && threadIdx.x == 0;
+      int ph = 0;
+      if (more) {
         // first layer wider than 256: the remaining K blocks replace the ones just consumed
-        if (MODE == IN_LOAD16) load_input16(tile, t, kb_first, p.ph[ph + 1].nkb, nullptr, false);
-        else load_input(tile, t, kb_first, p.ph[ph + 1].nkb);
-        publish(t, 3);
-      } else {
-        // Output layer.  Order matters: the accumulator is pulled into registers, the next tile's first-layer operand
-        // is written and the slot is PUBLISHED before anything goes to global memory -- the proxy fence in publish()
-        // is a CTA-wide memory barrier, and behind a global store it would wait for the store's L2 round trip.
+#pragma unroll 1
+        for (int t = 0; t < nslots; ++t) {
+          mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+          acc_par ^= 1u << t;
+          tc_fence_after();
+          if (MODE == IN_LOAD16) load_input16(T0 + t, t, kb_first, p.ph[1].nkb, nullptr, false);
+          else load_input(T0 + t, t, kb_first, p.ph[1].nkb);
+          publish(t, 3);
+        }
+        ph = 1;
+      }
+      // ---------------- hidden phases ----------------
+#pragma unroll 1
+      for (; ph < np - 1; ++ph) {
+        const uint32_t bias_addr = bias_base + (uint32_t)p.ph[ph].layer * (uint32_t)(kHidden * 4);
+        const bool last_hidden = ph == np - 2;
+#pragma unroll 1
+        for (int t = 0; t < nslots; ++t) {
+          const bool tl_e = tl_it && ew == 0 && ph == 2 && t == 0;      // fine-grained stamps of one hidden epilogue
+          tl_mark(p.timeline, tl_e, TL_EPI + 0);
+          if (last_hidden) {
+            // one phase before the output layer: start the global loads the output epilogue will need.  Each slot's
+            // registers are written directly (no select on the loaded values: that would wait for the loads here).
+            const long long tile = T0 + t;
+            const bool nxt = tile + stride < n_pairs;
+            if (kCompute && nxt) {
+              if (t == 0) fetch_input(row_of(tile + stride), xin0);
+              else fetch_input(row_of(tile + stride), xin1);
+            }
+            if (kNerf && ch == 0) {
+              if (t == 0) dterm0 = fetch_dterm(row_of(tile));
+              else dterm1 = fetch_dterm(row_of(tile));
+            }
+            if (MODE == IN_LOAD16 && threadIdx.x == 0 && nxt) {
+              // pull the next tile's rows (one contiguous range) towards L2
+              const long long row0 = row_of(tile + stride) - r;
+              long long nrow = p.M - row0;
+              if (nrow > TILE_M) nrow = TILE_M;
+              if (nrow > 0) {
+                const uint32_t bytes = (uint32_t)(nrow * (long long)p.k0 * 2);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const __half*>(p.in0) + row0 * p.k0), "r"(bytes) : "memory");
+              }
+            }
+          }
+          tl_mark(p.timeline, tl_e, TL_EPI + 1);
+          mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+          acc_par ^= 1u << t;
+          tc_fence_after();
+          tl_mark(p.timeline, tl_it && ew == 0, TL_ACC + ph * 2 + t);
+          tl_mark(p.timeline, tl_f, TL_FACC + ph * 2 + t);
+          // 128 columns per thread, in two 64-column groups: the second group's tcgen05.ld is in flight while the first
+          // group is converted and stored.  This thread's columns: [64 ch, +64) -> K block ch, then [128 + 64 ch, +64)
+          // -> K block 2 + ch, so the warps' first groups together complete K blocks {0,1} (operand half 0) and their
+          // second groups {2,3} (half 1)
+          const uint32_t taddr = tmem_lane + (uint32_t)t * kHidden + ch * 64;
+          const uint32_t row_base = a_row + t * A_SLOT_BYTES + ch * A_BLOCK_BYTES;
+          float v[128];
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + 32, v + 32);
+          tmem_wait_ld();
+          tl_mark(p.timeline, tl_e, TL_EPI + 2);
+          tmem_ld32(taddr + 128, v + 64);
+          tmem_ld32(taddr + 128 + 32, v + 96);
+          epilogue_store64<ACT>(v, bias_addr, row_base, xr);
+          tl_mark(p.timeline, tl_e, TL_EPI + 3);
+          tmem_wait_ld();                                      // every accumulator column of this thread is in registers
+          tl_mark(p.timeline, tl_e, TL_EPI + 4);
+          if (p.split) publish(t, 1);                          // K blocks {0,1} are ready: the next layer's MMAs may start
+          epilogue_store64<ACT>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
+          tl_mark(p.timeline, tl_e, TL_EPI + 5);
+          publish(t, p.split ? 2 : 3);
+          tl_mark(p.timeline, tl_e, TL_EPI + 6);
+          tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
+          tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+          tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
+        }
+      }
+      // ---------------- output phase ----------------
+      // Order matters: the accumulator is pulled into registers, the next tile's first-layer operand is written and the
+      // slot is PUBLISHED before anything goes to global memory -- the proxy fence in publish() is a CTA-wide memory
+      // barrier, and behind a global store it would wait for the store's L2 round trip.
+      const int layer_out = p.ph[np - 1].layer, n_pad_out = p.ph[np - 1].n_pad;
+#pragma unroll 1
+      for (int t = 0; t < nslots; ++t) {
+        const long long tile = T0 + t;
+        const bool has_next = tile + stride < n_pairs;
+        uint32_t pre[16];
+        if (kCompute && has_next) {                            // overlaps the wait below
+          float xin[kXin];
+#pragma unroll
+          for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
+          precompute_input(xin, row_of(tile + stride) < p.M, pre);
+        }
+        uint4 pf[kPf];
+        if (MODE == IN_LOAD16 && has_next) prefetch16(tile + stride, 0, kb_first, pf);   // in flight across the wait below
+        mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+        acc_par ^= 1u << t;
+        tc_fence_after();
+        tl_mark(p.timeline, tl_it && ew == 0, TL_ACC + ph * 2 + t);
+        tl_mark(p.timeline, tl_f, TL_FACC + ph * 2 + t);
+        const uint32_t taddr = tmem_lane + (uint32_t)t * kHidden;
         const long long row = row_of(tile);
         const bool live = row < p.M;
         float v[48];
         if (ch == 0) {
-          const int n_pad = p.ph[ph].n_pad;
           tmem_ld16(taddr, v);
-          if (n_pad > 16) tmem_ld16(taddr + 16, v + 16);
-          if (n_pad > 32) tmem_ld16(taddr + 32, v + 32);
+          if (n_pad_out > 16) tmem_ld16(taddr + 16, v + 16);
+          if (n_pad_out > 32) tmem_ld16(taddr + 32, v + 32);
           tmem_wait_ld();
         }
         if (has_next) {
           if (kCompute) store_pre(t, pre);
-          else if (MODE == IN_LOAD16) load_input16(tile + cur.stride, t, 0, kb_first, pf, true);
-          else load_input(tile + cur.stride, t, 0, kb_first);
+          else if (MODE == IN_LOAD16) load_input16(tile + stride, t, 0, kb_first, pf, true);
+          else load_input(tile + stride, t, 0, kb_first);
         }
         publish(t, 3);
+        tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
+        tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+        tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
         if (ch == 0 && live) {
-          const float* bo = s_bias + layer * kHidden;
+          const float* bo = s_bias + layer_out * kHidden;
           if (kNerf) {
             // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
             const float4 d = t ? dterm1 : dterm0;
@@ -882,11 +937,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           }
         }
       }
-      tl_mark(p.timeline, tl_on && ew == 0, TL_ARR + ph * 2 + t);
-      tl_mark(p.timeline, tl_on && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
-      tl_mark(p.timeline, kTimeline && blockIdx.x == 1 && tile == tl_tile0 + t && threadIdx.x == 0, TL_FARR + ph * 2 + t);
-    };
-    PN_WALK(body)
+    }
   }
 #undef PN_WALK
 
@@ -1095,7 +1146,8 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     static const int env_shift = getenv("PN_TC_SHIFT") ? atoi(getenv("PN_TC_SHIFT")) : -1;
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
     p.split = env_split >= 0 ? (env_split != 0) : 0;
-    p.shift = env_shift;   // resolved after the phase table is built
+    p.shift = 0;           // the two slots run in step (the epilogue warps' loops assume it)
+    (void)env_shift;
   }
   if (Lc.input_mode == IN_LOAD16) {
     if (p.k0 % 8 != 0 || Lc.in_stride != p.k0 || (reinterpret_cast<uintptr_t>(Lc.in0) & 15) != 0) {

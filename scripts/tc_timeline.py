@@ -16,6 +16,9 @@ if which == "nerf":
 elif which == "refine":
     x = torch.randn(M, 144, device=dev) * 0.5
     ctx = refn._ctx(); run = lambda: ctx.refine_forward(x, 8, "bf16"); nph = 7
+elif which == "refine16":
+    x = (torch.randn(M, 144, device=dev) * 0.5).to(torch.float16)
+    ctx = refn._ctx(); run = lambda: ctx.refine_forward_f16(x, 8); nph = 7
 else:
     x = torch.randn(M, 288, device=dev) * 0.5
     ctx = samp._ctx(); run = lambda: ctx.sampler_forward(x, 8, "bf16"); nph = 8
@@ -33,6 +36,6 @@ for ph in range(nph):
         off = (t[141] - t[140]) if (t[140] and t[141]) else 0
         fr = lambda j: (t[j] - off - t0) if t[j] else None
         print(f"  ph {ph} slot {s}: {rel(i)} {rel(20 + i)} | {rel(40 + i)} {rel(60 + i)} {rel(80 + i)} | follower acc_seen {fr(150 + i)} arrive {fr(170 + i)}")
-print("epilogue warp 0, phase 2 slot 0: acc seen", rel(40 + 4), " ld done", rel(100), " stores done", rel(101), " fence done", rel(102), " arrived", rel(60 + 4))
-print("  first-group wait done", rel(109), " chunk stores", [rel(110 + c) for c in range(8)])
-print("  second-group wait done", rel(118), " chunk stores", [rel(119 + c) for c in range(8)])
+names = ["body entry", "before acc wait", "first 64 cols loaded", "first store64 done", "second wait_ld done", "second store64 done", "published", "body exit"]
+print("epilogue warp 0, phase 2 slot 0 (acc seen %s):" % rel(40 + 4), ", ".join(f"{n} {rel(100 + k)}" for k, n in enumerate(names)))
+print("  prev arrive (ph1 s1)", rel(60 + 3), " next acc seen (ph2 s1)", rel(40 + 5))
