@@ -37,11 +37,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from pronerf_b200 import synth                                     # noqa: E402
-from pronerf_b200.engine import flops_per_ray, gather_bytes_per_ray  # noqa: E402
+from pronerf_b200.engine import flops_per_ray, gather_bytes_per_ray, refine_input_bytes_per_ray  # noqa: E402
 
 METRIC = "rendered Mrays/s @504x378, 8 samples/ray"
 UNIT = "Mrays/s"
 S, P, NN = 8, 48, 4
+# kernels launched by one pn_render_rays call: bf16 tier = sampler MLP, fused refine-input, refine MLP, interval refine,
+# dirterm pre-pass, NeRF MLP, composite; fp32 tier = 8 stage kernels + one extra gather per additional view
+LAUNCHES_PER_STEP = {"bf16": 7, "fp32": 10}
+# dram__bytes_read.sum + dram__bytes_write.sum of the NeRF kernel from the committed ncu --set full capture, per ray
+NERF_DRAM_BYTES_PER_RAY = (22.24e6 + 0.11e6) / 190512
+NERF_TRAFFIC_SOURCE = "profiles/r01_c0_ncu_summary.md (ncu --set full, one 504x378 view: 22.2 MB read + 0.1 MB written)"
 
 
 def load_peaks():
@@ -208,20 +214,18 @@ def main():
     n_rays_step = len(views) * H * W
     R = Renderer(weights, scene.images_ref, scene.poses_ref, scene.K, H, W, S=S, P=P, num_neighbor=NN, precision=precision,
                  device=dev)
-    preps = [R.prepare_view(c) for c in views]
+    batch = R.prepare_views(views)                 # the step's rays, stacked view after view (render_path's loop as one pass)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     images_pinned = torch.from_numpy(np.ascontiguousarray(scene.images_ref)).pin_memory()
-    rgb_host = [torch.empty((H * W, 3), dtype=torch.float32).pin_memory() for _ in views]
-    depth_host = [torch.empty((H * W,), dtype=torch.float32).pin_memory() for _ in views]
+    rgb_host = torch.empty((n_rays_step, 3), dtype=torch.float32).pin_memory()
+    depth_host = torch.empty((n_rays_step,), dtype=torch.float32).pin_memory()
 
     def step_resident():
-        for p in preps:
-            R.render_prepared(p)
+        R.render_prepared(batch)
 
     def step_e2e():
         R.set_images(images_pinned, non_blocking=True)
-        for i, c in enumerate(views):
-            R.render_view_host(c, rgb_host[i], depth_host[i])
+        R.render_views_host(views, rgb_host, depth_host)
 
     def barrier():
         if dist is not None:
@@ -287,22 +291,27 @@ def main():
     peaks = load_peaks()
     fl = flops_per_ray(S, P, NN)
     stage_avg = {s: float(np.mean([f[s] for f in stage_frames])) for s in ops.Context.STAGES} if stage_frames else {}
-    nerf_ms = stage_avg.get("nerf_mlp")
+    nerf_ms = stage_avg.get("nerf_mlp")            # one launch = the whole step (all views)
     roof = None
     if nerf_ms:
-        achieved = fl["nerf"] * H * W / (nerf_ms / 1e3) / 1e12
-        peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        roof = {"kernel": "nerf_mlp (encode + 8-layer 256-wide MLP, " + precision + ")", "bound": "tensor",
+        achieved = fl["nerf"] * n_rays_step / (nerf_ms / 1e3) / 1e12
+        # the timed region is a short burst at full SM clock (see "clocks"), so the denominator is the burst cuBLAS figure
+        peak = peaks["bf16_tflops"]
+        sus = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        roof = {"kernel": "nerf_mlp (encode + 8-layer 256-wide MLP, fp16 operands / fp32 accumulate)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "frac_of_burst": achieved / peaks["bf16_tflops"],
-                "traffic": None, "avg_launch_ms": nerf_ms,
-                "algorithmic_flops_per_launch": fl["nerf"] * H * W, "share_of_step": nerf_ms * len(views) / ms_per_step}
+                "peak_kind": "burst bf16 cuBLAS 8192^3, " + peaks["source"], "frac_of_sustained": achieved / sus,
+                "traffic": NERF_DRAM_BYTES_PER_RAY * n_rays_step, "traffic_source": NERF_TRAFFIC_SOURCE, "avg_launch_ms": nerf_ms,
+                "algorithmic_flops_per_launch": fl["nerf"] * n_rays_step, "share_of_step": nerf_ms / ms_per_step}
     g_ms = stage_avg.get("project_gather")
     gather = None
     if g_ms:
-        gb = gather_bytes_per_ray(S, NN, H, W) * H * W / (g_ms / 1e3) / 1e9
-        gather = {"kernel": "project_gather", "bound": "hbm", "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": gb / peaks["hbm_gbs"], "avg_launch_ms": g_ms, "algorithmic_bytes_per_ray": gather_bytes_per_ray(S, NN, H, W)}
+        fused = precision == "bf16"
+        bpr = refine_input_bytes_per_ray(S, NN, H, W) if fused else gather_bytes_per_ray(S, NN, H, W)
+        gb = bpr * n_rays_step / (g_ms / 1e3) / 1e9
+        gather = {"kernel": "refine_input (sort/lift + Pluecker + project/gather, fp16 rows out)" if fused else "project_gather",
+                  "bound": "hbm", "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": gb / peaks["hbm_gbs"], "avg_launch_ms": g_ms, "algorithmic_bytes_per_ray": bpr}
     mlp_total_ms = sum(stage_avg.get(k, 0.0) for k in ("sampler_mlp", "refine_mlp", "nerf_mlp"))
 
     # ---- CPU baseline (bounded sample, rank 0 only) ------------------------------------------------
@@ -321,15 +330,16 @@ def main():
         "config": {"workload": "ProNeRF stage-2 infer, fern-shaped 504x378, 3 test views (571536 rays/step), S=8, P=48, NN=4, "
                                "random-init sampler+refine+DoNeRFTRT", "precision": precision,
                    "l2": "flushed before every timed step (256 MiB memset outside the step events)",
+                   "batching": "the 3 views of a step are stacked into one pass (pn_frame_t.n_views = 3): one launch per stage",
                    "parallelism": f"view-parallel x{world} (every rank renders the batch; no data-path collective)"},
         "fps_504x378": value * 1e6 / n_view, "ms_per_view": ms_per_step / len(views),
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R.image_bytes + len(views) * (12 + 12 * NN) * 4),
                 "d2h_bytes_per_step": int(len(views) * n_view * 16), "ms_per_step": e2e_step_ms,
-                "api": "Renderer.set_images (pinned H2D + pack) + Renderer.render_view_host -> pn_render_view_host per view"},
-        "gpu_launches": int(args.steps * len(views) * 8),
+                "api": "Renderer.set_images (pinned H2D + pack) + Renderer.render_views_host -> pn_render_views_host (all views of the step in one pass)"},
+        "gpu_launches": int(args.steps * LAUNCHES_PER_STEP[precision]),
         "roofline": roof, "roofline_gather": gather,
-        "stage_ms_per_view": stage_avg,
+        "stage_ms_per_view": {k: v / len(views) for k, v in stage_avg.items()},
         "mlp_tflops_all_three": (fl["total"] * n_view / (mlp_total_ms / 1e3) / 1e12) if mlp_total_ms else None,
         "algorithmic_flops_per_ray": fl,
         "cpu_baseline": cpu, "clocks": clock_info,

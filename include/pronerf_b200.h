@@ -190,7 +190,15 @@ typedef struct pn_frame {
   int precision;              /* PN_PREC_*                                                              */
   float* rgb;                 /* device [N,3]  out                                                      */
   float* depth;               /* device [N]    out                                                      */
+  /* Multi-view batches -- render_path's loop over poses (trt.py:236-332) as ONE pass: rays of view v occupy rows
+   * [v*rays_per_view, (v+1)*rays_per_view), N = n_views*rays_per_view, project_mat is [n_views,NN,3,4] and
+   * tex_index_views (HOST ints [n_views][NN], NULL = tex_index for every view) holds each view's ref_nos order.
+   * n_views = 0 or 1: a single view, exactly the fields above.  At most PN_MAX_VIEWS views per batch. */
+  int n_views;
+  int64_t rays_per_view;
+  const int* tex_index_views;
 } pn_frame_t;
+#define PN_MAX_VIEWS 16
 
 /* render_rays (trt.py:599-696): sampler -> sort/lift -> project+gather -> refine -> interval refinement
  * -> encode + NeRF MLP -> composite, all on `stream`, scratch owned by ctx (grown on demand). */
@@ -203,6 +211,15 @@ int pn_render_view_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doubl
                         const float* c2w_host, const float* texels, const int* tex_index_host,
                         const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
                         float* rgb_host, float* depth_host, pn_stream_t stream);
+
+/* render_path (trt.py:223-363) for n_views poses in one pass, HOST buffers: c2w_host [n_views,3,4], tex_index_host
+ * [n_views,NN] (NULL = identity), project_mat_host [n_views,NN,3,4]; full frames; rgb_host [n_views*H*W,3] and
+ * depth_host [n_views*H*W] (ideally pinned).  Uploads poses + matrices, generates all rays on the device, runs ONE
+ * pn_render_rays over the n_views*H*W rays, downloads the frames and synchronises the stream. */
+int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                         const float* c2w_host, const float* texels, const int* tex_index_host,
+                         const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
+                         float* depth_host, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

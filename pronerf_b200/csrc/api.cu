@@ -37,7 +37,7 @@ struct pn_ctx {
   // per-view buffers for pn_render_view_host
   float* view_buf = nullptr;
   size_t view_floats = 0;
-  float* pm_dev = nullptr;
+  float* pm_dev = nullptr;         // projection matrices of the host-buffer entry points: [kMaxViews][8][12]
   // stage timing ring (pn_ctx_profile)
   bool profile = false;
   std::vector<cudaEvent_t> ev;      // PN_PROFILE_RING * (PN_N_STAGES + 1), created lazily
@@ -90,7 +90,7 @@ int pn_ctx_create(int device, pn_ctx_t** out) {
   PN_CUDA_OK(cudaSetDevice(device));
   pn_ctx* c = new pn_ctx();
   c->device = device;
-  cudaError_t e = cudaMalloc((void**)&c->pm_dev, 8 * 12 * sizeof(float));
+  cudaError_t e = cudaMalloc((void**)&c->pm_dev, (size_t)kMaxViews * 8 * 12 * sizeof(float));
   if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc(pm_dev)"); }
   *out = c;
   return PN_OK;
@@ -290,6 +290,14 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
              "pn_render_rays: bad frame shape");
   const int64_t N = f->N;
   const int S = f->S, NN = f->NN, P = f->P;
+  const int nv = f->n_views > 1 ? f->n_views : 1;
+  PN_REQUIRE(nv <= kMaxViews, "pn_render_rays: n_views=%d exceeds PN_MAX_VIEWS=%d", nv, kMaxViews);
+  PN_REQUIRE(nv == 1 || (f->rays_per_view >= 1 && f->rays_per_view * nv == N),
+             "pn_render_rays: N=%lld is not n_views=%d x rays_per_view=%lld", (long long)N, nv, (long long)f->rays_per_view);
+  const int64_t rpv = nv > 1 ? f->rays_per_view : N;
+  int tix[kMaxViews * 8];
+  for (int v = 0; v < nv; ++v)
+    for (int k = 0; k < NN; ++k) tix[v * NN + k] = (nv > 1 && f->tex_index_views) ? f->tex_index_views[v * NN + k] : f->tex_index[k];
   PN_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = as_stream(stream);
   const NetF32& ns = c->f32[PN_NET_SAMPLER];
@@ -344,8 +352,8 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   if (fused_input) {
     PN_STAGE_MARK(2);
     PN_STAGE_MARK(3);
-    rc = pn_refine_input_f16(heads, hs, f->rays, f->or_rays, 11, f->texels, f->tex_index, NN, f->H, f->W, f->project_mat, N, S, depth,
-                             add, mul, rin, nullptr, stream);
+    rc = launch_refine_input_f16(heads, hs, f->rays, f->or_rays, 11, f->texels, tix, nv, rpv, NN, f->H, f->W, f->project_mat, N, S,
+                                 depth, add, mul, rin, nullptr, st);
     if (rc != PN_OK) return rc;
   } else {
   // (2) sort + lift  trt.py:631-637
@@ -356,9 +364,12 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   rc = pn_refine_pluecker(f->rays, 11, depth, N, S, rin, ri, stream);
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(3);
-  rc = pn_project_gather(f->texels, f->tex_index, NN, f->H, f->W, f->project_mat, f->or_rays, f->or_rays + 3, 11, depth3d, N, S, rin, ri,
-                         6 * S, nullptr, stream);
-  if (rc != PN_OK) return rc;
+  for (int v = 0; v < nv; ++v) {       // one gather per view: each has its own matrices and neighbour ordering
+    const int64_t o = v * rpv;
+    rc = pn_project_gather(f->texels, tix + v * NN, NN, f->H, f->W, f->project_mat + (size_t)v * NN * 12, f->or_rays + o * 11,
+                           f->or_rays + o * 11 + 3, 11, depth3d + o * S, rpv, S, rin + o * ri, ri, 6 * S, nullptr, stream);
+    if (rc != PN_OK) return rc;
+  }
   }
   PN_STAGE_MARK(4);
   // (4) refine MLP  trt.py:668
@@ -412,6 +423,42 @@ int pn_render_view_host(pn_ctx_t* c, int H, int W, double fx, double fy, double 
   f.rays = rays; f.or_rays = or_rays; f.mm_input = nullptr; f.texels = texels; f.project_mat = c->pm_dev;
   for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
   f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
+  rc = pn_render_rays(c, &f, stream);
+  if (rc != PN_OK) return rc;
+  PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PN_CUDA_OK(cudaMemcpyAsync(depth_host, depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PN_CUDA_OK(cudaStreamSynchronize(st));
+  return PN_OK;
+}
+
+int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                         const float* c2w_host, const float* texels, const int* tex_index_host,
+                         const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
+                         float* depth_host, pn_stream_t stream) {
+  PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host, "pn_render_views_host: null pointer");
+  PN_REQUIRE(NN >= 1 && NN <= 8 && n_views >= 0 && n_views <= kMaxViews && H >= 2 && W >= 2,
+             "pn_render_views_host: bad shape (n_views=%d, at most %d per batch)", n_views, kMaxViews);
+  if (n_views == 0) return PN_OK;
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = as_stream(stream);
+  const int64_t npv = (int64_t)H * W, n = npv * n_views;
+  int rc = ensure(&c->view_buf, &c->view_floats, (size_t)n * (11 + 11 + 3 + 1));
+  if (rc != PN_OK) return rc;
+  float* rays = c->view_buf;
+  float* or_rays = rays + n * 11;
+  float* rgb = or_rays + n * 11;
+  float* depth = rgb + n * 3;
+  PN_CUDA_OK(cudaMemcpyAsync(c->pm_dev, project_mat_host, (size_t)n_views * NN * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+  for (int v = 0; v < n_views; ++v) {
+    rc = pn_raygen(H, W, fx, fy, cx, cy, c2w_host + 12 * v, 0.f, 1.f, 1.f, 10.f, 0, H, rays + v * npv * 11, or_rays + v * npv * 11, stream);
+    if (rc != PN_OK) return rc;
+  }
+  pn_frame_t f;
+  memset(&f, 0, sizeof(f));
+  f.rays = rays; f.or_rays = or_rays; f.mm_input = nullptr; f.texels = texels; f.project_mat = c->pm_dev;
+  for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
+  f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
+  f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host;
   rc = pn_render_rays(c, &f, stream);
   if (rc != PN_OK) return rc;
   PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -32,6 +32,7 @@ inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStrea
 
 constexpr int kHidden = 256;          // width of every trunk layer (netwidth / mmnetwidth = 256)
 constexpr int kMaxLayers = 8;
+constexpr int kMaxViews = 16;        // views per multi-view batch (pn_frame_t.n_views)
 constexpr int kOutPad = 96;           // padded width of an output layer (4S+3 = 67 at S = 16)
 
 // ---------------------------------------------------------------------------------------------
@@ -80,6 +81,12 @@ struct MlpLaunch {
 int launch_mlp_f32(const MlpLaunch& L, cudaStream_t stream);
 int pack_layer_f32(const float* W, const float* b, int out_dim, int in_dim, int k_pad, int n_pad, float* wt,
                    float* bias, int bias_pad, cudaStream_t stream);
+
+// fused sort/lift + Pluecker + project/gather -> fp16 refine input (gather.cu); multi-view form of pn_refine_input_f16
+int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
+                            const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,
+                            int W, const float* project_mat, int64_t N, int S, float* depth, float* add, float* mul,
+                            void* refine_in_f16, int32_t* x0y0, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Accurate fp32 helpers shared by kernels.  Nothing here may be compiled with --use_fast_math.

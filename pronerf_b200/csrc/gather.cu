@@ -27,6 +27,7 @@
 namespace pn {
 
 struct TexIndex { int v[8]; };
+struct TexIndexViews { int v[kMaxViews][8]; };
 
 struct Tap {
   float ix, iy;
@@ -144,16 +145,17 @@ __device__ __forceinline__ bool sort_after(float a, float b) { return (a > b) ||
 template <int S, int NN_T>
 __global__ void __launch_bounds__(256)
 refine_input_kernel(const float* __restrict__ heads, int head_stride, const float* __restrict__ rays,
-                    const float* __restrict__ or_rays, int rs, const float4* __restrict__ texels, TexIndex tex, int NNr,
-                    int H, int W, const float* __restrict__ pm, int64_t N, float* __restrict__ depth,
-                    float* __restrict__ add, float* __restrict__ mul, __half* __restrict__ rin, int32_t* __restrict__ x0y0) {
+                    const float* __restrict__ or_rays, int rs, const float4* __restrict__ texels, TexIndexViews tex, int NNr,
+                    int H, int W, const float* __restrict__ pm, int n_views, int64_t rays_per_view, int64_t N,
+                    float* __restrict__ depth, float* __restrict__ add, float* __restrict__ mul, __half* __restrict__ rin,
+                    int32_t* __restrict__ x0y0) {
   constexpr int RPB = 256 / S;                              // rays per block
   constexpr int KMAX = 6 * S + 3 * 8 * S;
-  __shared__ float sM[8 * 12];
+  __shared__ float sM[kMaxViews * 8 * 12];
   __shared__ __align__(16) __half stage[RPB * KMAX];
   const int NN = NN_T > 0 ? NN_T : NNr;
   const int K0 = 6 * S + 3 * NN * S;
-  for (int i = threadIdx.x; i < NN * 12; i += blockDim.x) sM[i] = pm[i];
+  for (int i = threadIdx.x; i < n_views * NN * 12; i += blockDim.x) sM[i] = pm[i];
   __syncthreads();
   const int64_t ray0 = (int64_t)blockIdx.x * RPB;
   const int rl = threadIdx.x / S, i = threadIdx.x % S;
@@ -162,6 +164,11 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
   const int64_t r = live ? r_raw : N - 1;
   const float* h = heads + r * head_stride;
   const float* ray = rays + r * rs;
+  // multi-view batches: rays of view `view` occupy rows [view * rays_per_view, +rays_per_view); each view has its own
+  // neighbour ordering (texel indices) and projection matrices (trt.py:281-294)
+  int view = 0;
+  if (n_views > 1) { view = (int)(r / rays_per_view); view = view < n_views ? view : n_views - 1; }
+  const float* vM = sM + view * NN * 12;
   const float near_ = ray[6], far_ = ray[7];
   const float v = __fadd_rn(__fmul_rn(h[i], __fsub_rn(far_, near_)), near_);   // depth * (far - near) + near   trt.py:631
   int rho = 0;
@@ -196,9 +203,9 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
 #pragma unroll
   for (int k = 0; k < (NN_T > 0 ? NN_T : 8); ++k) {
     if (k >= NN) break;
-    Tap tp = project_point(sM + 12 * k, w0, w1, w2, w3, wm1, hm1, wh, hh);
+    Tap tp = project_point(vM + 12 * k, w0, w1, w2, w3, wm1, hm1, wh, hh);
     Bilin b = bilinear_setup(tp, W, H);
-    const float4* img = texels + (int64_t)tex.v[k] * H * W;
+    const float4* img = texels + (int64_t)tex.v[view][k] * H * W;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* row0 = img + (int64_t)b.y0 * W + b.x0;
     const float4* row1 = row0 + W;
@@ -265,6 +272,40 @@ warp_kernel(const float* __restrict__ img, int B, int C, int H, int W, const flo
   }
 }
 
+// tex_index_host: [n_views][NN] ints (NULL = identity for every view); project_mat: device [n_views][NN][12]
+int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
+                            const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,
+                            int W, const float* project_mat, int64_t N, int S, float* depth, float* add, float* mul,
+                            void* refine_in_f16, int32_t* x0y0, cudaStream_t st) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(heads && rays && or_rays && texels && project_mat && depth && add && mul && refine_in_f16,
+             "pn_refine_input_f16: null pointer");
+  PN_REQUIRE(NN >= 1 && NN <= 8 && H >= 2 && W >= 2 && N >= 0 && ray_stride >= 8 && head_stride >= 3 * S,
+             "pn_refine_input_f16: bad shape (NN=%d H=%d W=%d S=%d)", NN, H, W, S);
+  PN_REQUIRE(n_views >= 1 && n_views <= kMaxViews && (n_views == 1 || rays_per_view >= 1),
+             "pn_refine_input_f16: n_views=%d unsupported (1..%d)", n_views, kMaxViews);
+  PN_REQUIRE(S == 4 || S == 8 || S == 16, "pn_refine_input_f16: S=%d unsupported (4, 8, 16); use the per-stage entry points", S);
+  PN_REQUIRE((reinterpret_cast<uintptr_t>(refine_in_f16) & 15) == 0, "pn_refine_input_f16: refine_in_f16 must be 16-byte aligned");
+  TexIndexViews ti;
+  for (int v = 0; v < kMaxViews; ++v)
+    for (int k = 0; k < 8; ++k) ti.v[v][k] = (tex_index_host && v < n_views && k < NN) ? tex_index_host[v * NN + k] : k;
+  for (int v = 0; v < n_views; ++v)
+    for (int k = 0; k < NN; ++k) PN_REQUIRE(ti.v[v][k] >= 0, "pn_refine_input_f16: negative texel image index");
+  const float4* tx = reinterpret_cast<const float4*>(texels);
+  __half* rin = reinterpret_cast<__half*>(refine_in_f16);
+#define PN_RI(SS, NT)                                                                                                    \
+  refine_input_kernel<SS, NT><<<(unsigned)((N + (256 / SS) - 1) / (256 / SS)), 256, 0, st>>>(                            \
+      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, n_views, rays_per_view, N, depth, add, mul, rin, x0y0)
+  if (NN == 4) {
+    if (S == 4) PN_RI(4, 4); else if (S == 8) PN_RI(8, 4); else PN_RI(16, 4);
+  } else {
+    if (S == 4) PN_RI(4, 0); else if (S == 8) PN_RI(8, 0); else PN_RI(16, 0);
+  }
+#undef PN_RI
+  PN_LAUNCH_OK("pn_refine_input_f16");
+  return PN_OK;
+}
+
 }  // namespace pn
 
 using namespace pn;
@@ -300,30 +341,8 @@ int pn_refine_input_f16(const float* heads, int head_stride, const float* rays, 
                         const float* texels, const int* tex_index_host, int NN, int H, int W, const float* project_mat,
                         int64_t N, int S, float* depth, float* add, float* mul, void* refine_in_f16, int32_t* x0y0,
                         pn_stream_t stream) {
-  if (N == 0) return PN_OK;            // empty batch
-  PN_REQUIRE(heads && rays && or_rays && texels && project_mat && depth && add && mul && refine_in_f16,
-             "pn_refine_input_f16: null pointer");
-  PN_REQUIRE(NN >= 1 && NN <= 8 && H >= 2 && W >= 2 && N >= 0 && ray_stride >= 8 && head_stride >= 3 * S,
-             "pn_refine_input_f16: bad shape (NN=%d H=%d W=%d S=%d)", NN, H, W, S);
-  PN_REQUIRE(S == 4 || S == 8 || S == 16, "pn_refine_input_f16: S=%d unsupported (4, 8, 16); use the per-stage entry points", S);
-  PN_REQUIRE((reinterpret_cast<uintptr_t>(refine_in_f16) & 15) == 0, "pn_refine_input_f16: refine_in_f16 must be 16-byte aligned");
-  TexIndex ti;
-  for (int k = 0; k < 8; ++k) ti.v[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
-  for (int k = 0; k < NN; ++k) PN_REQUIRE(ti.v[k] >= 0, "pn_refine_input_f16: negative texel image index");
-  const float4* tx = reinterpret_cast<const float4*>(texels);
-  __half* rin = reinterpret_cast<__half*>(refine_in_f16);
-  cudaStream_t st = as_stream(stream);
-#define PN_RI(SS, NT)                                                                                                    \
-  refine_input_kernel<SS, NT><<<(unsigned)((N + (256 / SS) - 1) / (256 / SS)), 256, 0, st>>>(                            \
-      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, N, depth, add, mul, rin, x0y0)
-  if (NN == 4) {
-    if (S == 4) PN_RI(4, 4); else if (S == 8) PN_RI(8, 4); else PN_RI(16, 4);
-  } else {
-    if (S == 4) PN_RI(4, 0); else if (S == 8) PN_RI(8, 0); else PN_RI(16, 0);
-  }
-#undef PN_RI
-  PN_LAUNCH_OK("pn_refine_input_f16");
-  return PN_OK;
+  return launch_refine_input_f16(heads, head_stride, rays, or_rays, ray_stride, texels, tex_index_host, 1, N, NN, H, W,
+                                 project_mat, N, S, depth, add, mul, refine_in_f16, x0y0, as_stream(stream));
 }
 
 int pn_warp(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,

@@ -95,6 +95,23 @@ class Renderer:
                                     self.H, self.W, tex_index=prep["tex_index"], precision=self.precision,
                                     out_rgb=prep["rgb"], out_depth=prep["depth"])
 
+    # -- batches of views (render_path's loop over poses as one pass) --------------------------------
+    def prepare_views(self, c2ws):
+        """Device-resident inputs of a batch of full views, rays stacked view after view."""
+        preps = [self.prepare_view(c) for c in c2ws]
+        n = sum(p["rays"].shape[0] for p in preps)
+        return dict(rays=torch.cat([p["rays"] for p in preps], 0), or_rays=torch.cat([p["or_rays"] for p in preps], 0),
+                    project_mat=torch.stack([p["project_mat"] for p in preps], 0), tex_index=[p["tex_index"] for p in preps],
+                    rgb=torch.empty((n, 3), device=self.device), depth=torch.empty((n,), device=self.device))
+
+    def render_views_host(self, c2ws, rgb_host=None, depth_host=None):
+        """End to end with HOST buffers for a batch of poses: one upload of poses + matrices, ONE pass, one download."""
+        params = [self.view_params(c) for c in c2ws]
+        return self.ctx.render_views_host(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
+                                          np.stack([p[2] for p in params], 0), self.S, self.P,
+                                          tex_index=[p[1] for p in params], precision=self.precision, rgb_host=rgb_host,
+                                          depth_host=depth_host)
+
     def render_view(self, c2w, row0: int = 0, nrows=None):
         return self.render_prepared(self.prepare_view(c2w, row0, nrows))
 
@@ -119,3 +136,10 @@ def gather_bytes_per_ray(S: int = 8, NN: int = 4, H: int = 378, W: int = 504, n_
     """Compulsory bytes of the gather kernel: depth3d + world ray + written features + the texel set once."""
     n_rays = H * W if n_rays is None else n_rays
     return 4.0 * S + 24.0 + 4.0 * 3 * NN * S + NN * H * W * 16.0 / n_rays
+
+
+def refine_input_bytes_per_ray(S: int = 8, NN: int = 4, H: int = 378, W: int = 504, n_rays=None) -> float:
+    """Compulsory bytes of the fused refine-input kernel (fp16 tier): sampler heads in (3S+3 floats), the used ray columns
+    (8 NDC + 6 world floats), sorted depth/add/mul out (3S floats), the fp16 refine-input row out, the texel set once."""
+    n_rays = H * W if n_rays is None else n_rays
+    return 4.0 * (3 * S + 3) + 4.0 * 14 + 4.0 * 3 * S + 2.0 * (6 * S + 3 * NN * S) + NN * H * W * 16.0 / n_rays

@@ -141,9 +141,12 @@ class Context:
     # -- whole path -------------------------------------------------------------------------------
     def render_rays(self, rays, or_rays, texels, project_mat, S, P, H, W, mm_input=None, tex_index=None,
                     precision="fp32", out_rgb=None, out_depth=None):
+        """``project_mat`` [NN,3,4] for one view, or [V,NN,3,4] for a batch of V views whose rays are stacked view after
+        view (then ``tex_index`` is a [V][NN] table)."""
         rays, or_rays = as_f32c(rays), as_f32c(or_rays)
         N = rays.shape[0]
-        NN = project_mat.shape[0]
+        n_views = project_mat.shape[0] if project_mat.dim() == 4 else 1
+        NN = project_mat.shape[-3]
         rgb = out_rgb if out_rgb is not None else _empty((N, 3), rays)
         depth = out_depth if out_depth is not None else _empty((N,), rays)
         f = _abi.Frame()
@@ -152,7 +155,14 @@ class Context:
         f.texels = dptr(texels, "texels")
         f.project_mat = dptr(as_f32c(project_mat), "project_mat")
         idx = list(range(8))
-        if tex_index is not None:
+        keep = None
+        if n_views > 1:
+            if N % n_views:
+                raise ValueError(f"{N} rays do not split into {n_views} views")
+            table = [[int(v) for v in row] for row in tex_index] if tex_index is not None else [list(range(NN))] * n_views
+            keep = (C.c_int * (n_views * NN))(*[v for row in table for v in row])
+            f.n_views, f.rays_per_view, f.tex_index_views = n_views, N // n_views, keep
+        elif tex_index is not None:
             for k, v in enumerate(tex_index):
                 idx[k] = int(v)
         f.tex_index = (C.c_int * 8)(*idx)
@@ -162,6 +172,30 @@ class Context:
         with _cuda_guard(rays):
             check(lib().pn_render_rays(self.handle, C.byref(f), stream_ptr(rays.device)), "pn_render_rays")
         return rgb, depth
+
+    def render_views_host(self, H, W, K, c2ws, texels, project_mats_host, S, P, tex_index=None, precision="fp32",
+                          rgb_host=None, depth_host=None):
+        """render_path for V poses in one pass, HOST buffers: c2ws [V,3,4], project_mats_host [V,NN,3,4], tex_index [V][NN]
+        -> pinned rgb [V*H*W,3], depth [V*H*W] (synchronous)."""
+        import numpy as np
+        c2ws = np.ascontiguousarray(np.asarray(c2ws, dtype=np.float32)[:, :3, :4])
+        pms = np.ascontiguousarray(np.asarray(project_mats_host, dtype=np.float32))
+        V, NN = pms.shape[0], pms.shape[1]
+        n = V * H * W
+        if rgb_host is None:
+            rgb_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        if depth_host is None:
+            depth_host = torch.empty((n,), dtype=torch.float32).pin_memory()
+        ti = None
+        if tex_index is not None:
+            ti = (C.c_int * (V * NN))(*[int(v) for row in tex_index for v in row])
+        with torch.cuda.device(self.device):
+            check(lib().pn_render_views_host(self.handle, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), V,
+                                             c2ws.ctypes.data_as(C.POINTER(C.c_float)), dptr(texels, "texels"), ti,
+                                             pms.ctypes.data_as(C.POINTER(C.c_float)), NN, S, P, PRECISIONS[precision],
+                                             rgb_host.data_ptr(), depth_host.data_ptr(), stream_ptr(self.device)),
+                  "pn_render_views_host")
+        return rgb_host, depth_host
 
     def render_view_host(self, H, W, K, c2w, texels, project_mat_host, S, P, tex_index=None, precision="fp32",
                          row0=0, nrows=None, rgb_host=None, depth_host=None):

@@ -448,6 +448,33 @@ def test_render_bf16_delta_psnr(ops, which, golden_fern):
         assert psnr(out["bf16"][0].reshape(-1, 3)[idx], g["rgb_subset"]) >= 38.0          # vs the reference's own render
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_multi_view_batch(ops, precision):
+    """render_path's loop over poses as ONE pass (pn_frame_t.n_views): stacking the rays of three views, each with its own
+    neighbour ordering and projection matrices, gives bit-identical frames to three single-view calls -- device-resident
+    and through the host-buffer entry point."""
+    if precision == "bf16":
+        _bf16_ready(ops)
+    from pronerf_b200.engine import Renderer
+    scene = synth.make_small_scene(H=20, W=28)
+    sd = synth.make_weights(seed=3, calibrated=True)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision=precision, device=DEV)
+    views = [scene.poses[i] for i in (0, 8, 16)]
+    orders = [R.view_params(c)[1] for c in views]
+    assert len({tuple(o) for o in orders}) > 1, "the test views must differ in neighbour ordering"
+    singles = [R.render_view(c) for c in views]
+    singles = [(r.clone(), d.clone()) for r, d in singles]
+    batch = R.prepare_views(views)
+    rgb, depth = R.render_prepared(batch)
+    n = scene.H * scene.W
+    for v, (r1, d1) in enumerate(singles):
+        assert torch.equal(rgb[v * n:(v + 1) * n], r1) and torch.equal(depth[v * n:(v + 1) * n], d1)
+    rgb_h, depth_h = R.render_views_host(views)
+    assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(depth_h, depth.cpu())
+    r1h, d1h = R.render_view_host(views[1])
+    assert torch.equal(r1h, singles[1][0].cpu()) and torch.equal(d1h, singles[1][1].cpu())
+
+
 def test_bf16_edge_cases(ops):
     _bf16_ready(ops)
     scene = synth.make_small_scene(H=16, W=20)
