@@ -46,8 +46,8 @@ S, P, NN = 8, 48, 4
 # dirterm pre-pass, NeRF MLP, composite; fp32 tier = 8 stage kernels + one extra gather per additional view
 LAUNCHES_PER_STEP = {"bf16": 7, "fp32": 10}
 # dram__bytes_read.sum + dram__bytes_write.sum of the NeRF kernel from the committed ncu --set full capture, per ray
-NERF_DRAM_BYTES_PER_RAY = (22.24e6 + 0.11e6) / 190512
-NERF_TRAFFIC_SOURCE = "profiles/r01_c0_ncu_summary.md (ncu --set full, one 504x378 view: 22.2 MB read + 0.1 MB written)"
+NERF_DRAM_BYTES_PER_RAY = (65.40e6 + 31.92e6) / 571536
+NERF_TRAFFIC_SOURCE = "profiles/r01_c4_summary.md (ncu --set full, one 3-view launch: 65.4 MB read + 31.9 MB written)"
 
 
 def load_peaks():
@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
