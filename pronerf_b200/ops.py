@@ -92,17 +92,26 @@ class Context:
         return [{s: buf[i * k + j] for j, s in enumerate(self.STAGES)} for i in range(n)]
 
     # -- MLP forwards -----------------------------------------------------------------------------
-    def sampler_forward(self, x, S, precision="fp32"):
+    @staticmethod
+    def _out(out, shape, like):
+        """A caller-owned dense fp32 output of the right shape (the engine objects keep persistent ones), or a new tensor."""
+        if out is None:
+            return _empty(shape, like)
+        if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != like.device:
+            raise ValueError(f"out must be a dense fp32 tensor of shape {tuple(shape)} on {like.device}")
+        return out
+
+    def sampler_forward(self, x, S, precision="fp32", out=None):
         x = as_f32c(x)
-        out = _empty((x.shape[0], 3 * S + 3), x)
+        out = self._out(out, (x.shape[0], 3 * S + 3), x)
         with _cuda_guard(x):
             check(lib().pn_sampler_forward(self.handle, dptr(x, "x"), x.shape[0], S, dptr(out), PRECISIONS[precision],
                                            stream_ptr(x.device)), "pn_sampler_forward")
         return out
 
-    def refine_forward(self, x, S, precision="fp32"):
+    def refine_forward(self, x, S, precision="fp32", out=None):
         x = as_f32c(x)
-        out = _empty((x.shape[0], 4 * S + 3), x)
+        out = self._out(out, (x.shape[0], 4 * S + 3), x)
         with _cuda_guard(x):
             check(lib().pn_refine_forward(self.handle, dptr(x, "x"), x.shape[0], S, dptr(out), PRECISIONS[precision],
                                           stream_ptr(x.device)), "pn_refine_forward")
@@ -118,11 +127,11 @@ class Context:
                                               stream_ptr(x16.device)), "pn_refine_forward_f16")
         return out
 
-    def nerf_forward(self, embedded, embedded_dirs, precision="fp32"):
+    def nerf_forward(self, embedded, embedded_dirs, precision="fp32", out=None):
         e, g = as_f32c(embedded), as_f32c(embedded_dirs)
         if e.shape[-1] != 63 or g.shape[-1] != 27 or e.shape[0] != g.shape[0]:
             raise ValueError(f"DoNeRFTRT expects [M,63] and [M,27], got {tuple(e.shape)} and {tuple(g.shape)}")
-        out = _empty((e.shape[0], 4), e)
+        out = self._out(out, (e.shape[0], 4), e)
         with _cuda_guard(e):
             check(lib().pn_nerf_forward(self.handle, dptr(e, "embedded"), dptr(g, "embedded_dirs"), e.shape[0], dptr(out),
                                         PRECISIONS[precision], stream_ptr(e.device)), "pn_nerf_forward")

@@ -140,12 +140,13 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
 
     ``ray_batch`` [N,11] = (o_ndc, d_ndc, near, far, viewdir); ``or_ray_batch`` [N,11] its world-space twin.
     Consumed kwargs: ``mm_input`` (optional here: generated in-kernel from the rays when absent),
-    ``num_neighbor``, ``texels``+``project_mat`` or ``ref_rgb``+``ref_pose``, ``use_trt`` (must be False),
+    ``num_neighbor``, ``texels``+``project_mat`` or ``ref_rgb``+``ref_pose``, ``use_trt`` (+ ``mm_engine``,
+    ``refine_engine``, ``nerf_engine``: the reference's engine seam, served by ``pronerf_b200.trt_infer_v2``),
     ``precision`` ('fp32' | 'bf16', default = the modules' ``precision``), ``fused`` (default True).
     """
-    if kwargs.get('use_trt'):
-        raise NotImplementedError("use_trt=True selects the reference's TensorRT engines, which are out of scope; "
-                                  "the B200 kernels are the engine here")
+    use_trt = bool(kwargs.get('use_trt'))
+    if use_trt and any(kwargs.get(k) is None for k in ('mm_engine', 'refine_engine', 'nerf_engine')):
+        raise ValueError("use_trt=True needs 'mm_engine', 'refine_engine' and 'nerf_engine' (pronerf_b200.trt_infer_v2)")
     if ray_batch.shape[-1] <= 8:
         raise ValueError("ray_batch must carry view directions ([N,11]); run_network needs them")
     S = N_samples
@@ -156,7 +157,7 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
     ray_batch = ops.as_f32c(ray_batch)
     or_ray_batch = ops.as_f32c(or_ray_batch)
 
-    if ours and stock_query and kwargs.get('fused', True):
+    if ours and stock_query and kwargs.get('fused', True) and not use_trt:
         tex, pm, tex_index = _texels_from_kwargs(kwargs, S)
         ctx = _fused_engine(min_max_ray_net, refine_net, network_fine)
         _, H, W, _ = tex.shape
@@ -172,9 +173,13 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
         if hasattr(m, 'precision') and kwargs.get('precision'):
             m.precision = precision
     mm_input = kwargs.get('mm_input')
-    if mm_input is None:
+    if mm_input is None and not use_trt:
         mm_input = ops.sampler_input(ray_batch, N_point_ray_enc)
-    if isinstance(min_max_ray_net, MinMaxRaySamplerTRT_Net):
+    if use_trt:
+        # the engine seam (trt.py:625-626): static inputs were bound by prepare_view / render_path (trt.py:306-319)
+        _, a_, m_, d_ = kwargs['mm_engine'].run()
+        heads = torch.cat([d_, a_, m_], -1)
+    elif isinstance(min_max_ray_net, MinMaxRaySamplerTRT_Net):
         heads = min_max_ray_net.forward_heads(mm_input)                                    # trt.py:628
     else:
         _, a_, m_, d_ = min_max_ray_net(mm_input)
@@ -189,13 +194,22 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
     else:
         raise ValueError("render_rays needs 'texels'+'project_mat' or 'ref_rgb'+'ref_pose' in the kwargs")
     ops.refine_pluecker(ray_batch, depth_values, out=refine_input)                          # trt.py:656-661
-    if isinstance(refine_net, MinMaxRayEpiSamplerTRT_Net):
+    if use_trt:
+        kwargs['refine_engine'].bind_input(refine_input)                                    # trt.py:664-666
+        rd_, _, off_ = kwargs['refine_engine'].run()
+        rout = torch.cat([rd_, off_], -1)
+    elif isinstance(refine_net, MinMaxRayEpiSamplerTRT_Net):
         rout = refine_net.forward_heads(refine_input)                                       # trt.py:668
     else:
         rd_, _, off_ = refine_net(refine_input)
         rout = torch.cat([rd_, off_], -1)
     epi_z_vals, query_points_nerf = ops.interval_refine(ray_batch, depth_values, rout, S)   # trt.py:671-681
-    raw = network_query_fn(query_points_nerf, viewdirs, network_fine)                       # trt.py:691
+    if use_trt:
+        embed_xyz = embed_fn(query_points_nerf.view(-1, 3)).flatten()                       # trt.py:684-689
+        kwargs['nerf_engine'].bind_input(embed_xyz)
+        raw = kwargs['nerf_engine'].run().view(N_rays, N_samples, -1)
+    else:
+        raw = network_query_fn(query_points_nerf, viewdirs, network_fine)                   # trt.py:691
     rgb_map, _, _, _, depth_map = raw2outputs(raw, epi_z_vals, ray_batch[:, 3:6], raw_noise_std, white_bkgd, pytest=pytest,
                                               mm_density_add=mm_density_add, mm_density_mul=mm_density_mul, iter=1e6)
     return {'rgb_map0': rgb_map, 'rgb_map1': rgb_map, 'depth_map': depth_map}
@@ -252,10 +266,24 @@ def prepare_view(c2w, hwf, K, render_kwargs, near=0., far=1., or_near=1., or_far
         render_kwargs['_texel_set'] = cached
     render_kwargs['texels'] = cached[1]
     render_kwargs['tex_index'] = [int(i) for i in ref_nos]
-    if render_kwargs.get('materialize_mm_input'):
+    if render_kwargs.get('materialize_mm_input') or render_kwargs.get('use_trt'):
         render_kwargs['mm_input'] = ops.sampler_input(rays, render_kwargs['N_point_ray_enc'])
     else:
         render_kwargs['mm_input'] = None
+    if render_kwargs.get('use_trt'):
+        # engines keep persistent device buffers: bind the static inputs once per view (trt.py:306-319)
+        S_ = render_kwargs['N_samples']
+        viewdirs = rays[:, 8:11]
+        input_dirs_flat = viewdirs[:, None].repeat(1, S_, 1).view(-1, 3)
+        embedded_dirs = render_kwargs['embeddirs_fn'](input_dirs_flat)
+        render_kwargs['nerf_engine'].bind_input_dir(embedded_dirs.cpu().numpy())
+        input_holder = torch.zeros(embedded_dirs.shape[0], 63, device=dev).flatten()
+        render_kwargs['nerf_engine'].bind_input(input_holder, warmup=True)
+        _ = render_kwargs['nerf_engine'].run()
+        render_kwargs['mm_engine'].bind_input(render_kwargs['mm_input'].cpu().numpy())
+        refine_input_holder = torch.zeros(rays.shape[0], 3 * render_kwargs['num_neighbor'] * S_ + 6 * S_, device=dev)
+        render_kwargs['refine_engine'].bind_input(refine_input_holder, warmup=True)
+        _ = render_kwargs['refine_engine'].run()
     return rays, or_rays, sh
 
 
@@ -410,8 +438,6 @@ def create_nerf(args):
     optimizer_nerf)``; the optimisers are ``None`` (training is out of scope).  ONNX export and TensorRT
     engine creation (trt.py:483-497) are not performed.
     """
-    if args.use_trt:
-        raise NotImplementedError("--use_trt selects TensorRT engines; pronerf_b200's CUDA kernels replace them")
     if str(args.mm_emb).lower() not in ('false', '0', 'none'):
         raise NotImplementedError("mm_emb=True is a training-time variant and is not built")
     dev = _device()
@@ -460,10 +486,20 @@ def create_nerf(args):
         'white_bkgd': args.white_bkgd, 'raw_noise_std': args.raw_noise_std, 'min_max_ray_net': model_mmray,
         'refine_net': model_refine, 'N_point_ray_enc': args.N_point_ray_enc, 'embed_fn': embed_fn,
         'embeddirs_fn': embeddirs_fn, 'embed_rays': Pluecker(), 'randomize': True, 'nerf_engine': None,
-        'mm_engine': None, 'refine_engine': None, 'num_neighbor': args.num_neighbor, 'use_trt': False,
+        'mm_engine': None, 'refine_engine': None, 'num_neighbor': args.num_neighbor, 'use_trt': bool(args.use_trt),
         'count_flops': False, 'precision': getattr(args, 'precision', 'fp32'),
         'timing_repeats': getattr(args, 'timing_repeats', 20),
     }
+    if args.use_trt:
+        # the reference deserialises three .trt files here (trt.py:490-498); the engine objects of this package wrap the
+        # same networks' B200 kernels behind the same bind_input / run protocol
+        from .trt_infer_v2 import MMEngine, NeRFEngine, RefineEngine
+        prec = getattr(args, 'precision', 'fp32')
+        cap = int(getattr(args, 'engine_batch', 756 * 1008))
+        render_kwargs_train['nerf_engine'] = NeRFEngine(model_fine, batch=cap * args.N_samples, precision=prec)
+        render_kwargs_train['mm_engine'] = MMEngine(model_mmray, batch=cap, in_ch=6 * args.N_point_ray_enc, precision=prec)
+        render_kwargs_train['refine_engine'] = RefineEngine(model_refine, batch=cap, precision=prec,
+                                                            in_ch=3 * args.num_neighbor * args.N_samples + 6 * args.N_samples)
     if args.dataset_type != 'llff' or args.no_ndc:
         raise NotImplementedError("only the NDC / LLFF forward-facing configuration of the release is built")
     render_kwargs_test = dict(render_kwargs_train)

@@ -291,7 +291,7 @@ def test_edge_cases(ops):
     ctx = ops.Context(DEV)
     with pytest.raises(RuntimeError, match="not loaded"):
         ctx.sampler_forward(torch.zeros(4, 288, device=DEV), 8)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="mm_engine"):                          # use_trt without engine objects
         render(rays, or_rays, sh, **dict(ck, use_trt=True))
 
 
@@ -311,6 +311,56 @@ def test_other_sample_counts(ops):
         ref = O.render_rays(sd, pv["rays"], pv["mm_input"], images, pv["project_mat"], pv["ro_w"], pv["rd_w"], S=S, keep=False)
         np.testing.assert_allclose(rgb.reshape(-1, 3).cpu().numpy(), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
         np.testing.assert_allclose(depth.reshape(-1).cpu().numpy(), ref["depth_map"].numpy(), atol=1e-3, rtol=0)
+
+
+def test_engine_protocol_use_trt(ops, golden_small_calibrated):
+    """MMEngine / RefineEngine / NeRFEngine objects (trt_infer_v2.py:149-394) driven through the reference's
+    ``use_trt`` seam (trt.py:306-319, 625-628, 664-668, 684-691) give exactly the staged route's frame, and keep the
+    reference's ownership rules (persistent outputs, adopted inputs)."""
+    from pronerf_b200.render import prepare_view, render
+    from pronerf_b200.trt_infer_v2 import MMEngine, NeRFEngine, RefineEngine
+    g = golden_small_calibrated
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    nets = make_modules(sd, DEV)
+    n = H * W
+    engines = dict(nerf_engine=NeRFEngine(sd, batch=n * 8), mm_engine=MMEngine(nets[1], batch=n),
+                   refine_engine=RefineEngine(sd["refine_net_state_dict"], batch=n))
+    kw_ref = make_kwargs(nets, scene, DEV, fused=False)
+    kw_trt = make_kwargs(nets, scene, DEV, use_trt=True, **engines)
+    c2w = g["c2w"]
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(c2w, scene.hwf, scene.K, kw_ref)
+        want_rgb, _, want_depth, _ = render(rays, or_rays, sh, **call_kwargs(kw_ref))
+        rays, or_rays, sh = prepare_view(c2w, scene.hwf, scene.K, kw_trt)       # binds the static engine inputs
+        got_rgb, _, got_depth, _ = render(rays, or_rays, sh, **call_kwargs(kw_trt))
+    assert torch.equal(got_rgb, want_rgb) and torch.equal(got_depth, want_depth)
+    np.testing.assert_allclose(got_rgb.reshape(-1, 3).cpu().numpy(), g["rgb"].reshape(-1, 3), atol=1e-3, rtol=0)    # the reference's own frame
+    # ownership: outputs are views of persistent buffers, rewritten by every run()
+    mm = engines["mm_engine"]
+    a = mm.run()
+    b = mm.run()
+    assert all(x.data_ptr() == y.data_ptr() for x, y in zip(a, b)) and a[3].shape == (n, 8) and a[0].shape == (n, 3)
+    # adopted inputs: warmup=True keeps the caller's tensor, warmup=False copies into it
+    re_ = engines["refine_engine"]
+    holder = torch.zeros(n, 144, device=DEV)
+    re_.bind_input(holder, warmup=True)
+    assert re_.input_gpu_host_mem is holder
+    x = T(g["refine_input"], DEV)
+    re_.bind_input(x)
+    assert torch.equal(holder, x) and re_.input_gpu_host_mem is holder
+    rd, rrgb, off = re_.run()
+    ref_rd, ref_rgb, ref_off = nets[2](x)
+    assert torch.equal(rd, ref_rd) and torch.equal(off, ref_off) and torch.equal(rrgb, ref_rgb)
+    np.testing.assert_allclose(rd.cpu().numpy(), g["refine_depth"], atol=2e-4, rtol=1e-4)
+    with pytest.raises(RuntimeError, match="Build engine failed"):
+        MMEngine(sd, batch=16, in_ch=100)
+    with pytest.raises(RuntimeError, match="view directions"):
+        ne = NeRFEngine(sd, batch=64)
+        ne.bind_input_dir(np.zeros((8, 27), np.float32))
+        ne.bind_input(torch.zeros(16 * 63, device=DEV), warmup=True)
+        ne.run()
 
 
 # ================================================================================================

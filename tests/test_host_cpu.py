@@ -177,3 +177,16 @@ def test_tile_gather_gloo(world):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_engine_shim_needs_a_gpu():
+    """The engine-protocol shim fails the way the reference's engines do: RuntimeError('Build engine failed:', ...)."""
+    import torch
+    from pronerf_b200 import synth
+    from pronerf_b200.trt_infer_v2 import MMEngine, NeRFEngine, RefineEngine
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    sd = synth.make_weights(seed=0)
+    for cls in (MMEngine, RefineEngine, NeRFEngine):
+        with pytest.raises(RuntimeError, match="Build engine failed"):
+            cls(sd, batch=16)
