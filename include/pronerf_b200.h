@@ -197,6 +197,9 @@ typedef struct pn_frame {
   int n_views;
   int64_t rays_per_view;
   const int* tex_index_views;
+  /* Optional cudaEvent_t (NULL = none): the first kernel that reads `texels` waits for it on `stream`, so the caller can
+   * upload + pack the reference views on another stream while the sampler MLP (which does not need them) runs. */
+  void* texels_ready;
 } pn_frame_t;
 #define PN_MAX_VIEWS 16
 
@@ -215,11 +218,12 @@ int pn_render_view_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doubl
 /* render_path (trt.py:223-363) for n_views poses in one pass, HOST buffers: c2w_host [n_views,3,4], tex_index_host
  * [n_views,NN] (NULL = identity), project_mat_host [n_views,NN,3,4]; full frames; rgb_host [n_views*H*W,3] and
  * depth_host [n_views*H*W] (ideally pinned).  Uploads poses + matrices, generates all rays on the device, runs ONE
- * pn_render_rays over the n_views*H*W rays, downloads the frames and synchronises the stream. */
+ * pn_render_rays over the n_views*H*W rays, downloads the frames and synchronises the stream.
+ * texels_ready_event: optional cudaEvent_t as in pn_frame_t.texels_ready (NULL = texels are ready on `stream`). */
 int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy, int n_views,
                          const float* c2w_host, const float* texels, const int* tex_index_host,
                          const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
-                         float* depth_host, pn_stream_t stream);
+                         float* depth_host, void* texels_ready_event, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ class Frame(C.Structure):
     """``pn_frame_t``."""
     _fields_ = [("rays", _p), ("or_rays", _p), ("mm_input", _p), ("texels", _p), ("tex_index", _i * 8),
                 ("project_mat", _p), ("N", _i64), ("S", _i), ("NN", _i), ("P", _i), ("H", _i), ("W", _i), ("precision", _i),
-                ("rgb", _p), ("depth", _p), ("n_views", _i), ("rays_per_view", _i64), ("tex_index_views", C.POINTER(_i))]
+                ("rgb", _p), ("depth", _p), ("n_views", _i), ("rays_per_view", _i64), ("tex_index_views", C.POINTER(_i)), ("texels_ready", _p)]
 
 
 # name -> (restype, argtypes); one entry per symbol declared in include/pronerf_b200.h
@@ -59,7 +59,7 @@ SIGNATURES = {
     "pn_raygen": (_i, [_i, _i, _d, _d, _d, _d, C.POINTER(_f), _f, _f, _f, _f, _i, _i, _p, _p, _p]),
     "pn_render_rays": (_i, [_p, C.POINTER(Frame), _p]),
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
-                                  _p, _p, _p]),
+                                  _p, _p, _p, _p]),
     "pn_render_view_host": (_i, [_p, _i, _i, _d, _d, _d, _d, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _i,
                                  _p, _p, _p]),
 }

@@ -348,6 +348,7 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   PN_STAGE_MARK(1);
   // fp16 tier: sort/lift + Pluecker + project/gather run as ONE kernel that writes the refine input as fp16 rows,
   // which the refine MLP's first-layer operand loads chunk for chunk (timed as the project_gather stage)
+  if (f->texels_ready) PN_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(f->texels_ready), 0));
   const bool fused_input = f->precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported;
   if (fused_input) {
     PN_STAGE_MARK(2);
@@ -434,7 +435,7 @@ int pn_render_view_host(pn_ctx_t* c, int H, int W, double fx, double fy, double 
 int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
                          const float* c2w_host, const float* texels, const int* tex_index_host,
                          const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
-                         float* depth_host, pn_stream_t stream) {
+                         float* depth_host, void* texels_ready_event, pn_stream_t stream) {
   PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host, "pn_render_views_host: null pointer");
   PN_REQUIRE(NN >= 1 && NN <= 8 && n_views >= 0 && n_views <= kMaxViews && H >= 2 && W >= 2,
              "pn_render_views_host: bad shape (n_views=%d, at most %d per batch)", n_views, kMaxViews);
@@ -458,7 +459,7 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
   f.rays = rays; f.or_rays = or_rays; f.mm_input = nullptr; f.texels = texels; f.project_mat = c->pm_dev;
   for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
   f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
-  f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host;
+  f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host; f.texels_ready = texels_ready_event;
   rc = pn_render_rays(c, &f, stream);
   if (rc != PN_OK) return rc;
   PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

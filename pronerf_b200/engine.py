@@ -42,6 +42,8 @@ class Renderer:
         self.load_weights(weights)
         self.texels = None
         self._staging = None
+        self._copy_stream = None
+        self._tex_event = None
         self.set_images(images_ref)
 
     # -- state ------------------------------------------------------------------------------------
@@ -64,16 +66,34 @@ class Renderer:
         self.ctx.load_net(_abi.PN_NET_NERF, *lin(n, [f"layers.{i}" for i in range(nl)]))
         torch.cuda.synchronize(self.device)
 
-    def set_images(self, images_ref, non_blocking: bool = False):
-        """Upload + pack the reference views [n_ref,H,W,3] (numpy, or a pinned CPU tensor for the async path)."""
+    def set_images(self, images_ref, non_blocking: bool = False, overlap: bool = False):
+        """Upload + pack the reference views [n_ref,H,W,3] (numpy, or a pinned CPU tensor for the async path).
+
+        ``overlap=True`` runs the upload and the packing kernel on a private copy stream and records an event that the
+        next ``render_views_host`` hands to the library (``pn_frame_t.texels_ready``): the sampler MLP, which does not read
+        the views, runs while they are still in flight."""
         t = images_ref if isinstance(images_ref, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images_ref, dtype=np.float32))
         if tuple(t.shape[1:]) != (self.H, self.W, 3):
             raise ValueError(f"images must be [n,{self.H},{self.W},3], got {tuple(t.shape)}")
         if self._staging is None or self._staging.shape != t.shape:
             self._staging = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+            self.texels = torch.empty(tuple(t.shape[:3]) + (4,), dtype=torch.float32, device=self.device)
+        self._tex_event = None
         with torch.cuda.device(self.device):
-            self._staging.copy_(t, non_blocking=non_blocking)
-            self.texels = ops.pack_images(self._staging)
+            if overlap:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(self.device)
+                    self._tex_done = torch.cuda.Event()
+                main = torch.cuda.current_stream(self.device)
+                self._copy_stream.wait_stream(main)            # earlier renders may still be reading the texels
+                with torch.cuda.stream(self._copy_stream):
+                    self._staging.copy_(t, non_blocking=True)
+                    ops.pack_images(self._staging, out=self.texels)
+                    self._tex_done.record(self._copy_stream)
+                self._tex_event = self._tex_done
+            else:
+                self._staging.copy_(t, non_blocking=non_blocking)
+                ops.pack_images(self._staging, out=self.texels)
         self.image_bytes = t.numel() * 4
 
     # -- per view ---------------------------------------------------------------------------------
@@ -110,7 +130,7 @@ class Renderer:
         return self.ctx.render_views_host(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
                                           np.stack([p[2] for p in params], 0), self.S, self.P,
                                           tex_index=[p[1] for p in params], precision=self.precision, rgb_host=rgb_host,
-                                          depth_host=depth_host)
+                                          depth_host=depth_host, texels_ready=self._tex_event)
 
     def render_view(self, c2w, row0: int = 0, nrows=None):
         return self.render_prepared(self.prepare_view(c2w, row0, nrows))

@@ -183,7 +183,7 @@ class Context:
         return rgb, depth
 
     def render_views_host(self, H, W, K, c2ws, texels, project_mats_host, S, P, tex_index=None, precision="fp32",
-                          rgb_host=None, depth_host=None):
+                          rgb_host=None, depth_host=None, texels_ready=None):
         """render_path for V poses in one pass, HOST buffers: c2ws [V,3,4], project_mats_host [V,NN,3,4], tex_index [V][NN]
         -> pinned rgb [V*H*W,3], depth [V*H*W] (synchronous)."""
         import numpy as np
@@ -202,8 +202,9 @@ class Context:
             check(lib().pn_render_views_host(self.handle, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), V,
                                              c2ws.ctypes.data_as(C.POINTER(C.c_float)), dptr(texels, "texels"), ti,
                                              pms.ctypes.data_as(C.POINTER(C.c_float)), NN, S, P, PRECISIONS[precision],
-                                             rgb_host.data_ptr(), depth_host.data_ptr(), stream_ptr(self.device)),
-                  "pn_render_views_host")
+                                             rgb_host.data_ptr(), depth_host.data_ptr(),
+                                             texels_ready.cuda_event if texels_ready is not None else None,
+                                             stream_ptr(self.device)), "pn_render_views_host")
         return rgb_host, depth_host
 
     def render_view_host(self, H, W, K, c2w, texels, project_mat_host, S, P, tex_index=None, precision="fp32",
@@ -304,13 +305,13 @@ def warp(img, depth, ro1, rd1, w2c, want_index: bool = False):
     return (out, idx) if want_index else out
 
 
-def pack_images(images_hwc: torch.Tensor) -> torch.Tensor:
+def pack_images(images_hwc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[NN,H,W,3] fp32 -> RGBA fp32 texels [NN,H,W,4] (one 128-bit load per bilinear tap)."""
     im = as_f32c(images_hwc)
     NN, H, W, c = im.shape
     if c != 3:
         raise ValueError("images must be [NN,H,W,3]")
-    tex = _empty((NN, H, W, 4), im)
+    tex = Context._out(out, (NN, H, W, 4), im)
     with _cuda_guard(im):
         check(lib().pn_pack_images(dptr(im, "images"), NN, H, W, dptr(tex), stream_ptr(im.device)), "pn_pack_images")
     return tex

@@ -523,6 +523,16 @@ def test_multi_view_batch(ops, precision):
     assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(depth_h, depth.cpu())
     r1h, d1h = R.render_view_host(views[1])
     assert torch.equal(r1h, singles[1][0].cpu()) and torch.equal(d1h, singles[1][1].cpu())
+    # reference views re-uploaded on the copy stream while the sampler runs (pn_frame_t.texels_ready): same frames,
+    # and a changed image set is really picked up
+    pinned = torch.from_numpy(np.ascontiguousarray(scene.images_ref)).pin_memory()
+    for _ in range(3):
+        R.set_images(pinned, overlap=True)
+        rgb_o, depth_o = R.render_views_host(views)
+        assert torch.equal(rgb_o, rgb_h) and torch.equal(depth_o, depth_h)
+    R.set_images((pinned * 0.5).pin_memory(), overlap=True)
+    rgb_o, _ = R.render_views_host(views)
+    assert not torch.equal(rgb_o, rgb_h)
 
 
 def test_bf16_edge_cases(ops):
