@@ -900,11 +900,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         const uint32_t taddr = tmem_lane + (uint32_t)t * kHidden;
         const long long row = row_of(tile);
         const bool live = row < p.M;
+        // output columns [48 ch, 48 ch + 48): the ch = 1 warps only have work for outputs wider than 48 (S = 16)
         float v[48];
-        if (ch == 0) {
-          tmem_ld16(taddr, v);
-          if (n_pad_out > 16) tmem_ld16(taddr + 16, v + 16);
-          if (n_pad_out > 32) tmem_ld16(taddr + 32, v + 32);
+        const int c0 = ch * 48;
+        if (c0 < n_pad_out) {
+          tmem_ld16(taddr + c0, v);
+          if (n_pad_out > c0 + 16) tmem_ld16(taddr + c0 + 16, v + 16);
+          if (n_pad_out > c0 + 32) tmem_ld16(taddr + c0 + 32, v + 32);
           tmem_wait_ld();
         }
         if (has_next) {
@@ -916,21 +918,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
         tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
         tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
-        if (ch == 0 && live) {
-          const float* bo = s_bias + layer_out * kHidden;
+        if (c0 < n_pad_out && live) {
+          const float* bo = s_bias + layer_out * kHidden + c0;
           if (kNerf) {
             // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
             const float4 d = t ? dterm1 : dterm0;
             *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
           } else {
-            float* orow = p.out + row * p.n_out;
+            float* orow = p.out + row * p.n_out + c0;
 #pragma unroll
             for (int o = 0; o < 48; ++o) {
-              if (o < p.n_out) {
+              if (c0 + o < p.n_out) {
                 int kind = HEAD_NONE;
 #pragma unroll
                 for (int gq = 0; gq < 3; ++gq)
-                  if (o >= p.head_lo[gq] && o < p.head_lo[gq + 1]) kind = p.head_act[gq];
+                  if (c0 + o >= p.head_lo[gq] && c0 + o < p.head_lo[gq + 1]) kind = p.head_act[gq];
                 orow[o] = head_apply_fast(v[o] + bo[o], kind);
               }
             }
@@ -1076,7 +1078,7 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   n.net_id = net_id;
   n.n_layers = n_layers;
   for (int l = 0; l < n_layers; ++l) { n.in_dim[l] = in_dims[l]; n.out_dim[l] = out_dims[l]; }
-  n.supported = in_dims[0] <= 8 * 64 && out_dims[n_layers - 1] <= 48;
+  n.supported = in_dims[0] <= 8 * 64 && out_dims[n_layers - 1] <= 96;
   if (!n.supported) return PN_OK;                           // fp32 tier still works; the fp16 launch reports it
   TcLayout L = tc_layout(net_id, n_layers, in_dims, out_dims);
   PN_CUDA_OK(cudaMalloc(&n.blob, L.total));
@@ -1123,7 +1125,7 @@ static int tc_max_clusters(const void* func, int* out) {
 int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   if (!n.loaded) {
     set_error(n.supported ? "PN_PREC_FP16: network weights not loaded" : "PN_PREC_FP16: this network shape is outside the tensor-core "
-              "kernel's limits (first layer <= 512 inputs, output <= 48); use PN_PREC_FP32");
+              "kernel's limits (first layer <= 512 inputs, output <= 96); use PN_PREC_FP32");
     return PN_ESTATE;
   }
   if (Lc.M == 0) return PN_OK;
