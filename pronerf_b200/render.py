@@ -427,6 +427,8 @@ def config_parser():
     p.add_argument("--timing_repeats", type=int, default=20, help="renders per view inside the timed loop (reference: 20)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--calibrated_init", action='store_true', help="synthetic weights with a wide output range")
+    p.add_argument("--engine_batch", type=int, default=756 * 1008,
+                   help="--use_trt: ray capacity of the engine objects' persistent buffers (the reference's static batch, cli.py:216-217)")
     return p
 
 
@@ -511,13 +513,26 @@ def create_nerf(args):
 
 # ----------------------------------------------------------------------------- trt.py:699-799
 def load_scene(args):
-    """``load_llff_data_infer`` stand-in: the seeded fern-shaped scene at ``--factor`` (real LLFF I/O is out of scope)."""
-    if not str(args.datadir).startswith('synthetic'):
-        raise NotImplementedError(
-            f"datadir={args.datadir!r}: the LLFF/COLMAP loader is outside the hot path this package builds (SURVEY.md "
-            "section 8, row f5). Use --datadir synthetic:fern, or call render_path() with your own images/poses.")
-    return synth.make_scene(factor=args.factor, seed=getattr(args, 'seed', 0), llffhold=args.llffhold,
-                            num_neighbor=args.num_neighbor)
+    """``load_llff_data_infer`` (trt.py:709-747): a real LLFF / COLMAP capture directory, or ``synthetic:fern`` -- the seeded
+    fern-shaped scene at ``--factor``."""
+    if str(args.datadir).startswith('synthetic'):
+        return synth.make_scene(factor=args.factor, seed=getattr(args, 'seed', 0), llffhold=args.llffhold,
+                                num_neighbor=args.num_neighbor)
+    from .llff_io import load_llff_data_infer
+    images, poses, bds, render_poses, i_test, i_ref = load_llff_data_infer(
+        args.datadir, args.factor, recenter=True, bd_factor=.75, spherify=getattr(args, 'spherify', False),
+        num_neighbor=args.num_neighbor, llffhold=args.llffhold)                   # num_neighbor passed: fixes defect Q6
+    hwf = poses[0, :3, -1]
+    H, W, focal = int(hwf[0]), int(hwf[1]), float(hwf[2])
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])          # trt.py:742-747
+    i_train = np.array([i for i in range(images.shape[0]) if i not in i_test])
+
+    class _LoadedScene(synth.Scene):
+        def gt_image(self, view):
+            return self.extras['images'][int(view)]
+    return _LoadedScene(H=H, W=W, focal=focal, poses=np.ascontiguousarray(poses[:, :3, :4]), bds=bds, K=K, i_test=i_test,
+                        i_train=i_train, i_ref=np.asarray(i_ref), images_ref=np.ascontiguousarray(images[np.asarray(i_ref)]),
+                        extras={'images': images, 'render_poses': render_poses})
 
 
 def train(argv=None):
@@ -530,7 +545,7 @@ def train(argv=None):
     hwf = [H, W, focal]
     K = scene.K
     i_test = scene.i_test
-    print('Loaded synthetic llff', (len(scene.poses), H, W, 3), hwf, args.datadir)
+    print('Loaded llff', (len(scene.poses), H, W, 3), hwf, args.datadir)
     print('NEAR FAR', 0., 1.)
     os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)
     with open(os.path.join(args.basedir, args.expname, 'args.txt'), 'w') as fh:

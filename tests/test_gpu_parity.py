@@ -6,6 +6,8 @@ Tolerances (stated per test):
 * fp32 elementwise stages: <= 2e-6 abs;   * fp32 MLP outputs: <= 2e-4 abs + 1e-4 rel (7-8 chained GEMMs);
 * end to end rgb / depth: <= 1e-3 max-abs (the north-star bound for the fp32 tier).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -361,6 +363,24 @@ def test_engine_protocol_use_trt(ops, golden_small_calibrated):
         ne.bind_input_dir(np.zeros((8, 27), np.float32))
         ne.bind_input(torch.zeros(16 * 63, device=DEV), warmup=True)
         ne.run()
+
+
+def test_infer_driver_on_llff_capture(ops, tmp_path):
+    """The infer entrypoint (``python -m pronerf.cli infer`` -> ``train()``, trt.py:699-799) on an on-disk LLFF / COLMAP
+    capture: loader (f5) -> create_nerf -> render_path -> PNGs; the ``--use_trt`` engine seam (f3) renders the same frame."""
+    from pronerf_b200.render import train
+    from tests.util import write_synthetic_llff
+    data = tmp_path / "capture"
+    write_synthetic_llff(str(data), n_views=12, H=24, W=32, factor=2, seed=0)
+    cfg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "llff", "fern", "fern_b200.txt")
+    common = ["--config", cfg, "--datadir", str(data), "--factor", "2", "--no_reload", "--render_test", "--max_images", "1",
+              "--calibrated_init", "--timing_repeats", "1", "--engine_batch", "1024", "--precision", "fp32"]
+    res = train(common + ["--basedir", str(tmp_path / "logs"), "--expname", "plain"])
+    assert res["rgbs"].shape == (1, 24, 32, 3) and np.isfinite(res["rgbs"]).all()
+    pngs = sorted(os.listdir(res["savedir"]))
+    assert pngs == ["000.png", "depth_000.png"]
+    res_trt = train(common + ["--basedir", str(tmp_path / "logs"), "--expname", "trt", "--use_trt"])
+    np.testing.assert_allclose(res_trt["rgbs"], res["rgbs"], atol=1e-5, rtol=0)
 
 
 # ================================================================================================

@@ -52,3 +52,39 @@ def call_kwargs(kw):
 def psnr(a, b):
     mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+def write_synthetic_llff(root, n_views=12, H=24, W=32, factor=2, seed=0, n_points=400):
+    """A tiny LLFF capture on disk: poses_bounds.npy, images_<factor>/*.png, sparse/0/{images,points3D}.bin (COLMAP binary
+    records with seeded random tracks).  Deterministic: the golden generator and the tests rebuild the same bytes."""
+    import os
+    import struct
+    from pronerf_b200.pngio import write_png
+    os.makedirs(os.path.join(root, f"images_{factor}"), exist_ok=True)
+    os.makedirs(os.path.join(root, "sparse", "0"), exist_ok=True)
+    pb = synth.make_poses_bounds(n_views, seed, H * factor, W * factor, synth.FERN_FOCAL_FULL * (W * factor / synth.FERN_W_FULL))
+    np.save(os.path.join(root, "poses_bounds.npy"), pb)
+    names = [f"IMG_{1000 + 7 * v:04d}.png" for v in range(n_views)]
+    for v, nm in enumerate(names):
+        write_png(os.path.join(root, f"images_{factor}", nm), synth.make_image_u8(v, H, W, seed))
+    rs = np.random.RandomState(seed + 5)
+    ids = rs.permutation(n_views) + 1                       # COLMAP image ids are not in file-name order
+    with open(os.path.join(root, "sparse", "0", "images.bin"), "wb") as fh:
+        fh.write(struct.pack("<Q", n_views))
+        for v in rs.permutation(n_views):                   # nor are the records
+            fh.write(struct.pack("<idddddddi", int(ids[v]), 1., 0., 0., 0., 0., 0., 0., 1))
+            fh.write(names[v].replace(".png", ".JPG").encode() + b"\x00")
+            n2d = int(rs.randint(0, 4))
+            fh.write(struct.pack("<Q", n2d))
+            for _ in range(n2d):
+                fh.write(struct.pack("<ddq", 1.5, 2.5, -1))
+    centre = rs.rand(n_points) * n_views
+    with open(os.path.join(root, "sparse", "0", "points3D.bin"), "wb") as fh:
+        fh.write(struct.pack("<Q", n_points))
+        for p in range(n_points):
+            fh.write(struct.pack("<QdddBBBd", p + 1, 0., 0., 1., 128, 128, 128, 0.5))
+            seen = [v for v in range(n_views) if abs(v - centre[p]) < 1.0 + 2.0 * rs.rand()]
+            fh.write(struct.pack("<Q", len(seen)))
+            for v in seen:
+                fh.write(struct.pack("<ii", int(ids[v]), 0))
+    return names
