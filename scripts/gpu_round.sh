@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 6 -c 3 -o $OUT/prof_mlp \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:refine_input_kernel -s 3 -c 1 -o $OUT/prof_gather \
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:refine_input_kernel|composite_scan_kernel|interval_refine_kernel" -s 9 -c 3 -o $OUT/prof_gather \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_gather.log 2>&1
 fi
 ls -la $OUT
