@@ -64,6 +64,15 @@ void pn_ctx_destroy(pn_ctx_t* ctx);
 int pn_ctx_load_net(pn_ctx_t* ctx, int net, int n_layers, const int* in_dims, const int* out_dims,
                     const float* const* W_device, const float* const* b_device, pn_stream_t stream);
 
+/* The classic NeRF (run_nerf_helpers.py:792-847: D=8, W=256, skips=[4], use_viewdirs, 63 + 27 encoded inputs) as the shading
+ * network of this context -- the topology stage-2 checkpoints hold under 'network_fine_state_dict' (refine2.py:360-362, 890),
+ * which the reference's own infer script cannot load into its DoNeRFTRT (trt.py:434-435, 481).  12 nn.Linear tensors in
+ * checkpoint order: pts_linears.0..7, alpha_linear, feature_linear, views_linears.0, rgb_linear.  Afterwards pn_nerf_forward,
+ * pn_run_network and pn_render_rays use it; it runs in PN_PREC_FP32 only (other precisions fail with PN_ESTATE).  Loading
+ * either kind of shading network replaces the other. */
+int pn_ctx_load_nerf_classic(pn_ctx_t* ctx, const int* in_dims, const int* out_dims, const float* const* W_device,
+                             const float* const* b_device, pn_stream_t stream);
+
 /* Stage timing for the roofline report: when enabled, pn_render_rays brackets each of its PN_N_STAGES kernels
  * with CUDA events on the launch stream (a ring of PN_PROFILE_RING frames; ~1 us per event).
  * pn_ctx_profile_read synchronises on the last recorded event, writes up to max_frames rows of

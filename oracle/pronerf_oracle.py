@@ -166,13 +166,29 @@ def nerf_forward(sd, e, g, D=8):
     return out
 
 
+def nerf_classic_forward(sd, e, g, D=8, skips=(4,)):
+    """helpers.py:825-847 NeRF.forward (use_viewdirs): ReLU trunk with ``cat([input_pts, h])`` after layer 4, then
+    alpha / feature heads, ``cat([feature, input_views])`` -> views layer (ReLU) -> rgb; returns ``cat([rgb, alpha])``."""
+    h = e
+    for i in range(D):
+        h = F.relu(_lin(sd, f"pts_linears.{i}", h))
+        if i in skips:
+            h = torch.cat([e, h], -1)
+    alpha = _lin(sd, "alpha_linear", h)
+    feature = _lin(sd, "feature_linear", h)
+    h = F.relu(_lin(sd, "views_linears.0", torch.cat([feature, g], -1)))
+    return torch.cat([_lin(sd, "rgb_linear", h), alpha], -1)
+
+
 def run_network(sd, pts, viewdirs):
-    """trt.py:195-208: encode [N,S,3] points (L=10) and per-ray view dirs (L=4), run the NeRF MLP."""
+    """trt.py:195-208: encode [N,S,3] points (L=10) and per-ray view dirs (L=4), run the NeRF MLP (DoNeRFTRT, or the
+    classic NeRF when the state_dict holds its keys -- base.py's run_network concatenates the two encodings for it)."""
     flat = pts.reshape(-1, 3)
     e = embed(flat, 10)
     dirs = viewdirs[:, None].expand(pts.shape).reshape(-1, 3)
     g = embed(dirs, 4)
-    return nerf_forward(sd, e, g).reshape(*pts.shape[:-1], 4)
+    fwd = nerf_classic_forward if "pts_linears.0.weight" in sd else nerf_forward
+    return fwd(sd, e, g).reshape(*pts.shape[:-1], 4)
 
 
 # ----------------------------------------------------------------------------- A.3 sort / lift

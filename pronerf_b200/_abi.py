@@ -40,6 +40,7 @@ SIGNATURES = {
     "pn_ctx_profile": (_i, [_p, _i]),
     "pn_ctx_profile_read": (_i, [_p, C.POINTER(_f), _i]),
     "pn_ctx_load_net": (_i, [_p, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), _p]),
+    "pn_ctx_load_nerf_classic": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), _p]),
     "pn_sampler_forward": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "pn_refine_forward": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "pn_nerf_forward": (_i, [_p, _p, _p, _i64, _p, _i, _p]),

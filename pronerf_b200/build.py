@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpronerf_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "gather.cu", "mlp_f32.cu", "mlp_tc.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "gather.cu", "mlp_f32.cu", "mlp_prog.cu", "mlp_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

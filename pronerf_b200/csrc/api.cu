@@ -31,6 +31,7 @@ struct pn_ctx {
   int device = 0;
   NetF32 f32[3];
   NetTC tc[3];
+  NetProg nerf_classic;             // classic NeRF topology (stage-2 checkpoints), fp32 layer-program tier
   // scratch for pn_render_rays, grown on demand (never shrunk)
   float* scratch = nullptr;
   size_t scratch_floats = 0;
@@ -100,6 +101,7 @@ void pn_ctx_destroy(pn_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (int i = 0; i < 3; ++i) { free_net(c->f32[i]); tc_free_net(c->tc[i]); }
+  prog_free(c->nerf_classic);
   if (c->scratch) cudaFree(c->scratch);
   if (c->view_buf) cudaFree(c->view_buf);
   if (c->pm_dev) cudaFree(c->pm_dev);
@@ -155,6 +157,7 @@ int pn_ctx_load_net(pn_ctx_t* c, int net, int n_layers, const int* in_dims, cons
   cudaStream_t st = as_stream(stream);
   NetF32& n = c->f32[net];
   free_net(n);
+  if (net == PN_NET_NERF) prog_free(c->nerf_classic);      // one shading network per context
   n.n_layers = n_layers;
   int rows = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -186,6 +189,24 @@ int pn_ctx_load_net(pn_ctx_t* c, int net, int n_layers, const int* in_dims, cons
   int rc = tc_load_net(c->tc[net], net, n_layers, in_dims, out_dims, W, b, st);
   if (rc != PN_OK) return rc;
   return PN_OK;
+}
+
+int pn_ctx_load_nerf_classic(pn_ctx_t* c, const int* in_dims, const int* out_dims, const float* const* W, const float* const* b,
+                             pn_stream_t stream) {
+  PN_REQUIRE(c && in_dims && out_dims && W && b, "pn_ctx_load_nerf_classic: null pointer");
+  for (int l = 0; l < 12; ++l) PN_REQUIRE(W[l] && b[l], "pn_ctx_load_nerf_classic: tensor %d is NULL", l);
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  free_net(c->f32[PN_NET_NERF]);                            // one shading network per context
+  tc_free_net(c->tc[PN_NET_NERF]);
+  return prog_load_nerf_classic(c->nerf_classic, in_dims, out_dims, W, b, as_stream(stream));
+}
+
+// classic topology: fp32 only in this build, and said loudly
+static int classic_precision_ok(int precision, const char* who) {
+  if (precision == PN_PREC_FP32) return PN_OK;
+  set_error("%s: the classic NeRF topology (stage-2 checkpoints) runs in PN_PREC_FP32 only in this build; "
+            "the tcgen05 tier covers DoNeRFTRT", who);
+  return PN_ESTATE;
 }
 
 // ------------------------------------------------------------------------------------------------ MLP entry points
@@ -259,6 +280,12 @@ int pn_nerf_forward(pn_ctx_t* c, const float* embedded, const float* embedded_di
                     pn_stream_t stream) {
   if (M == 0) return PN_OK;            // empty batch
   PN_REQUIRE(c && embedded && embedded_dirs && raw && M >= 0, "pn_nerf_forward: bad arguments");
+  if (c->nerf_classic.loaded) {
+    int rcp = classic_precision_ok(precision, "pn_nerf_forward");
+    if (rcp != PN_OK) return rcp;
+    PN_CUDA_OK(cudaSetDevice(c->device));
+    return prog_launch(c->nerf_classic, IN_LOAD2, embedded, embedded_dirs, 27, 1, M, raw, as_stream(stream));
+  }
   int rc = check_nerf(c->f32[PN_NET_NERF]);
   if (rc != PN_OK) return rc;
   MlpLaunch L{};
@@ -271,6 +298,12 @@ int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int vie
                    int precision, pn_stream_t stream) {
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(c && pts && viewdirs && raw && N >= 0 && S >= 1 && viewdir_stride >= 3, "pn_run_network: bad arguments");
+  if (c->nerf_classic.loaded) {
+    int rcp = classic_precision_ok(precision, "pn_run_network");
+    if (rcp != PN_OK) return rcp;
+    PN_CUDA_OK(cudaSetDevice(c->device));
+    return prog_launch(c->nerf_classic, IN_ENCODE, pts, viewdirs, viewdir_stride, S, N * S, raw, as_stream(stream));
+  }
   int rc = check_nerf(c->f32[PN_NET_NERF]);
   if (rc != PN_OK) return rc;
   MlpLaunch L{};
@@ -302,7 +335,11 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   const NetF32& ns = c->f32[PN_NET_SAMPLER];
   const NetF32& nr = c->f32[PN_NET_REFINE];
-  PN_REQUIRE(ns.loaded && nr.loaded && c->f32[PN_NET_NERF].loaded, "pn_render_rays: load all three networks first");
+  PN_REQUIRE(ns.loaded && nr.loaded && (c->f32[PN_NET_NERF].loaded || c->nerf_classic.loaded), "pn_render_rays: load all three networks first");
+  if (c->nerf_classic.loaded) {
+    int rcp = classic_precision_ok(f->precision, "pn_render_rays");
+    if (rcp != PN_OK) return rcp;
+  }
   PN_REQUIRE(ns.in_dim[0] == 6 * P && ns.out_dim[ns.n_layers - 1] == 3 * S + 3, "pn_render_rays: sampler net shape does not match P=%d S=%d", P, S);
   PN_REQUIRE(nr.in_dim[0] == 6 * S + 3 * NN * S && nr.out_dim[nr.n_layers - 1] == 4 * S + 3, "pn_render_rays: refine net shape does not match S=%d NN=%d", S, NN);
   int rc = check_nerf(c->f32[PN_NET_NERF]);

@@ -82,6 +82,28 @@ int launch_mlp_f32(const MlpLaunch& L, cudaStream_t stream);
 int pack_layer_f32(const float* W, const float* b, int out_dim, int in_dim, int k_pad, int n_pad, float* wt,
                    float* bias, int bias_pad, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------
+// fp32 layer-program tier (mlp_prog.cu): topologies outside the fused kernels, e.g. the classic NeRF of stage-2 checkpoints
+constexpr int kMaxProgSteps = 16;
+struct ProgStep {
+  int in0_off, in0_len;      // first input segment: region offset inside the activation row, length (K rows of W)
+  int in1_off, in1_len;      // optional second segment (skip / view-direction concatenations); len 0 = none
+  int out_off, n_out;        // output region and width (<= 256)
+  int act;                   // 1 = ReLU, 0 = linear
+  int w_off, b_off;          // float offsets of the k-major weights [in0_len + in1_len][n_out] and the bias in the blob
+};
+struct NetProg {
+  int n_steps = 0;
+  ProgStep st[kMaxProgSteps];
+  float* blob = nullptr;
+  bool loaded = false;
+};
+void prog_free(NetProg& n);
+int prog_load_nerf_classic(NetProg& net, const int* in_dims, const int* out_dims, const float* const* W, const float* const* b,
+                           cudaStream_t stream);
+int prog_launch(const NetProg& net, int input_mode, const float* in0, const float* in1, int in1_stride, int S, int64_t M,
+                float* out, cudaStream_t stream);
+
 // fused sort/lift + Pluecker + project/gather -> fp16 refine input (gather.cu); multi-view form of pn_refine_input_f16
 int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
                             const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,

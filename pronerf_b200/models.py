@@ -82,6 +82,54 @@ class DoNeRFTRT(_PackedNet):
         return self._ctx().nerf_forward(input_pts, input_views, precision=self.precision)
 
 
+NERF_CLASSIC_KEYS = [f"pts_linears.{i}" for i in range(8)] + ["alpha_linear", "feature_linear", "views_linears.0", "rgb_linear"]
+
+
+class NeRF(_PackedNet):
+    """The classic NeRF MLP (run_nerf_helpers.py:792-847) -- what stage 2 trains and saves as ``network_fine``
+    (run_S_eS_eN_alter_base_refine2.py:360-362, 890).  ``forward(x)`` takes ``cat([embedded_pts, embedded_views])`` like
+    the reference and returns ``cat([rgb, alpha])``.  Built for the release's shape: D=8, W=256, skips=[4], use_viewdirs,
+    63 / 27 encoded inputs; runs in the fp32 tier (the tcgen05 tier covers DoNeRFTRT)."""
+    NET_ID = _abi.PN_NET_NERF
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        if not use_viewdirs or D != 8 or W != 256 or list(skips) != [4] or input_ch != 63 or input_ch_views != 27:
+            raise NotImplementedError("NeRF: only D=8, W=256, skips=[4], use_viewdirs=True, input_ch=63, input_ch_views=27 is built")
+        self.D, self.W, self.input_ch, self.input_ch_views, self.skips, self.use_viewdirs = D, W, input_ch, input_ch_views, skips, use_viewdirs
+        self.pts_linears = nn.ModuleList([nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in skips else nn.Linear(W + input_ch, W)
+                                                                     for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+
+    def _linears(self):
+        return list(self.pts_linears) + [self.alpha_linear, self.feature_linear, self.views_linears[0], self.rgb_linear]
+
+    def _load(self, ctx: Context):
+        lin = self._linears()
+        ctx.load_nerf_classic([l.weight for l in lin], [l.bias for l in lin], key=("classic",) + _weights_key(lin))
+
+    def _ctx(self) -> Context:
+        dev = self.rgb_linear.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("NeRF must be on a CUDA device to run (pronerf_b200 has no CPU fallback); call .cuda() first")
+        ctx = self.__dict__.get("_pn_ctx")
+        if ctx is None or ctx.device != dev:
+            ctx = Context(dev)
+            self.__dict__["_pn_ctx"] = ctx
+        self._load(ctx)
+        return ctx
+
+    def load_into(self, ctx: Context):
+        self._load(ctx)
+
+    def forward(self, x):
+        input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
+        return self._ctx().nerf_forward(input_pts.contiguous(), input_views.contiguous(), precision=self.precision)
+
+
 class _SamplerBase(_PackedNet):
     def __init__(self, D=8, W=256, input_ch=3, output_ch=3, skips=[4], N_samples=8):
         super().__init__()

@@ -75,6 +75,23 @@ class Context:
             check(lib().pn_ctx_load_net(self.handle, net_id, n, ind, outd, wp, bp, stream_ptr(self.device)), "pn_ctx_load_net")
         self._keys[net_id] = key
 
+    def load_nerf_classic(self, weights, biases, key=None):
+        """The classic NeRF as this context's shading network: 12 nn.Linear tensors in checkpoint order (pts_linears.0..7,
+        alpha_linear, feature_linear, views_linears.0, rgb_linear).  fp32 tier only."""
+        if key is not None and self._keys.get(_abi.PN_NET_NERF) == key:
+            return
+        ws = [as_f32c(w.detach()) for w in weights]
+        bs = [as_f32c(b.detach()) for b in biases]
+        if len(ws) != 12 or len(bs) != 12:
+            raise ValueError("classic NeRF: expected 12 weight and 12 bias tensors")
+        ind = (C.c_int * 12)(*[int(w.shape[1]) for w in ws])
+        outd = (C.c_int * 12)(*[int(w.shape[0]) for w in ws])
+        wp = (C.c_void_p * 12)(*[dptr(w, f"weight[{i}]") for i, w in enumerate(ws)])
+        bp = (C.c_void_p * 12)(*[dptr(b, f"bias[{i}]") for i, b in enumerate(bs)])
+        with torch.cuda.device(self.device):
+            check(lib().pn_ctx_load_nerf_classic(self.handle, ind, outd, wp, bp, stream_ptr(self.device)), "pn_ctx_load_nerf_classic")
+        self._keys[_abi.PN_NET_NERF] = key
+
     STAGES = ("sampler_mlp", "sort_lift", "refine_pluecker", "project_gather", "refine_mlp", "interval_refine",
               "nerf_mlp", "composite")
 

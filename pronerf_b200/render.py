@@ -31,7 +31,7 @@ import torch
 
 from . import ops, synth
 from .helpers import Pluecker, get_embedder, img2mse, mse2psnr, to8b
-from .models import DoNeRFTRT, MinMaxRayEpiSamplerTRT_Net, MinMaxRaySamplerTRT_Net, load_state_dicts
+from .models import DoNeRFTRT, MinMaxRayEpiSamplerTRT_Net, MinMaxRaySamplerTRT_Net, NeRF, load_state_dicts
 from .pngio import write_png
 
 DEBUG = False
@@ -54,7 +54,7 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     if viewdirs is None:
         raise ValueError("run_network requires viewdirs (the reference leaves embedded_dirs unbound without them, "
                          "run_S_eS_eN_alter_trt.py:201-206)")
-    if (isinstance(fn, DoNeRFTRT) and getattr(embed_fn, "multires", None) == 10
+    if (isinstance(fn, (DoNeRFTRT, NeRF)) and getattr(embed_fn, "multires", None) == 10
             and getattr(embeddirs_fn, "multires", None) == 4 and inputs.dim() == 3):
         return fn._ctx().run_network(inputs, viewdirs, precision=fn.precision)
     inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
@@ -62,7 +62,10 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     input_dirs = viewdirs[:, None].expand(inputs.shape)
     input_dirs_flat = torch.reshape(input_dirs, [-1, input_dirs.shape[-1]])
     embedded_dirs = embeddirs_fn(input_dirs_flat)
-    outputs_flat = fn(embedded, embedded_dirs)
+    if isinstance(fn, NeRF):            # the classic NeRF takes one concatenated tensor (base.py's run_network)
+        outputs_flat = fn(torch.cat([embedded, embedded_dirs], -1))
+    else:
+        outputs_flat = fn(embedded, embedded_dirs)
     return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
 
 
@@ -152,7 +155,7 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
     S = N_samples
     precision = kwargs.get('precision') or getattr(network_fine, 'precision', 'fp32')
     ours = (isinstance(min_max_ray_net, MinMaxRaySamplerTRT_Net) and isinstance(refine_net, MinMaxRayEpiSamplerTRT_Net)
-            and isinstance(network_fine, DoNeRFTRT))
+            and isinstance(network_fine, (DoNeRFTRT, NeRF)))
     stock_query = getattr(network_query_fn, "pn_stock", False)
     ray_batch = ops.as_f32c(ray_batch)
     or_ray_batch = ops.as_f32c(or_ray_batch)
@@ -475,6 +478,17 @@ def create_nerf(args):
         ckpt_path = ckpts[-1]
         print('Reloading from', ckpt_path)
         ckpt = torch.load(ckpt_path, map_location=dev)
+        if any(k.startswith('pts_linears.') for k in ckpt['network_fine_state_dict']):
+            # a stage-2 checkpoint: 'network_fine' is the classic NeRF (refine2.py:360-362, 890), which the reference's own infer
+            # script cannot load into its DoNeRFTRT (defect Q7); here the matching module is built instead
+            if getattr(args, 'precision', 'fp32') != 'fp32':
+                raise NotImplementedError("this checkpoint holds the classic NeRF topology, which runs in the fp32 tier only: "
+                                          "pass --precision fp32")
+            print('network_fine: classic NeRF topology (stage-2 checkpoint)')
+            model_fine = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, input_ch_views=input_ch_views, output_ch=output_ch,
+                              skips=[4], use_viewdirs=args.use_viewdirs).to(dev)
+            model_fine.precision = 'fp32'
+            model_fine.eval()
         load_state_dicts(model_fine, model_mmray, model_refine, ckpt)
     else:
         # no network in the build environment: deterministic random init

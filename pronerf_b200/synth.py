@@ -209,6 +209,25 @@ def make_weights(seed: int = 0, N_samples: int = 8, N_point_ray_enc: int = 48, n
     return sd
 
 
+def make_nerf_classic_weights(seed: int = 0, W: int = 256, calibrated: bool = False) -> dict:
+    """Deterministic random-init ``state_dict`` of the classic NeRF (run_nerf_helpers.py:792-823; D=8, skips=[4], use_viewdirs)
+    with nn.Linear's default init -- what a stage-2 checkpoint stores under ``network_fine_state_dict``."""
+    rs = np.random.RandomState(7654321 + seed)
+    sd = {}
+    dims = [(63, W)] + [(W + 63, W) if i == 4 else (W, W) for i in range(7)]
+    for i, (fi, fo) in enumerate(dims):
+        sd[f"pts_linears.{i}.weight"], sd[f"pts_linears.{i}.bias"] = _linear_default(rs, fi, fo)
+    sd["views_linears.0.weight"], sd["views_linears.0.bias"] = _linear_default(rs, W + 27, W // 2)
+    sd["feature_linear.weight"], sd["feature_linear.bias"] = _linear_default(rs, W, W)
+    sd["alpha_linear.weight"], sd["alpha_linear.bias"] = _linear_default(rs, W, 1)
+    sd["rgb_linear.weight"], sd["rgb_linear.bias"] = _linear_default(rs, W // 2, 3)
+    if calibrated:                                              # opacities and colours that are not all ~0
+        sd["alpha_linear.weight"] *= 60.0
+        sd["alpha_linear.bias"] += 20.0
+        sd["rgb_linear.weight"] *= 8.0
+    return sd
+
+
 def weights_checksum(sd: dict) -> float:
     tot = 0.0
     for net in sorted(sd):

@@ -383,6 +383,87 @@ def test_infer_driver_on_llff_capture(ops, tmp_path):
     np.testing.assert_allclose(res_trt["rgbs"], res["rgbs"], atol=1e-5, rtol=0)
 
 
+def test_nerf_classic_topology(ops):
+    """the classic NeRF of stage-2 checkpoints (helpers.py:792-847) as the shading network, fp32 tier --
+    module forward and fused run_network against the reference's own outputs (<= 2e-4 abs + 1e-4 rel, as for the other fp32
+    MLPs), a full render against the oracle (<= 1e-3), the checkpoint round trip through create_nerf, and the loud refusal of
+    the tensor-core tier."""
+    from pronerf_b200.helpers import get_embedder
+    from pronerf_b200.models import NeRF
+    from pronerf_b200.render import prepare_view, render, run_network
+    from tests.conftest import load_golden
+    g = load_golden("nerf_classic.npz")
+    pts, vd = T(g["pts"], DEV), T(g["viewdirs"], DEV)
+    embed_fn, _ = get_embedder(10, 0)
+    embeddirs_fn, _ = get_embedder(4, 0)
+    for tag, cal in (("random", False), ("calibrated", True)):
+        sd = synth.make_nerf_classic_weights(seed=0, calibrated=cal)
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        net.to(DEV).eval()
+        want = g[f"{tag}_raw"]
+        tol = dict(atol=2e-4 * max(1.0, np.abs(want).max()), rtol=1e-4)
+        raw_fused = run_network(pts, vd, net, embed_fn, embeddirs_fn)                       # encodings inside the kernel
+        np.testing.assert_allclose(raw_fused.reshape(-1, 4).cpu().numpy(), want, **tol)
+        e = ops.embed(pts.reshape(-1, 3), 10)
+        d = ops.embed(vd[:, None].expand(pts.shape).reshape(-1, 3), 4)
+        raw_mod = net(torch.cat([e, d], -1))                                                # the reference's call form
+        np.testing.assert_allclose(raw_mod.cpu().numpy(), want, **tol)
+        for n in (0, 1, 31, 33):                                                            # ragged 32-row tiles
+            assert torch.equal(net(torch.cat([e, d], -1)[:n]), raw_mod[:n])
+        net.precision = "bf16"
+        with pytest.raises(RuntimeError, match="PN_PREC_FP32 only"):
+            net(torch.cat([e, d], -1))
+    # a whole view with the classic NeRF as network_fine, against the oracle
+    scene = synth.make_small_scene(H=16, W=24)
+    sd3 = synth.make_weights(seed=0, calibrated=True)
+    sd3["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    _, samp, refn = make_modules(synth.make_weights(seed=0, calibrated=True), DEV)
+    nerf = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)
+    nerf.load_state_dict({k: torch.from_numpy(v) for k, v in sd3["network_fine_state_dict"].items()})
+    nerf.to(DEV).eval()
+    kw = make_kwargs((nerf, samp, refn), scene, DEV)
+    c2w = scene.poses[int(scene.i_test[1])]
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(c2w, scene.hwf, scene.K, kw)
+        rgb, _, depth, _ = render(rays, or_rays, sh, **call_kwargs(kw))
+    pv = O.prep_view(scene.H, scene.W, scene.K, c2w, scene.poses_ref)
+    ref = O.render_rays(sd3, pv["rays"], pv["mm_input"], scene.images_ref[pv["ref_nos"].numpy()], pv["project_mat"], pv["ro_w"],
+                        pv["rd_w"], keep=False)
+    np.testing.assert_allclose(rgb.reshape(-1, 3).cpu().numpy(), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(depth.reshape(-1).cpu().numpy(), ref["depth_map"].numpy(), atol=1e-3, rtol=0)
+    # the engine object (Renderer) picks the topology from the checkpoint's keys
+    from pronerf_b200.engine import Renderer
+    R = Renderer(sd3, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="fp32", device=DEV)
+    rgb_r, depth_r = R.render_view(c2w)
+    assert torch.equal(rgb_r, rgb.reshape(-1, 3)) and torch.equal(depth_r, depth.reshape(-1))
+    with pytest.raises(NotImplementedError, match="fp32 tier only"):
+        Renderer(sd3, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+
+
+def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
+    """The infer driver on a stage-2 style checkpoint .tar whose 'network_fine_state_dict' is the classic NeRF (the case the
+    reference's own infer script cannot load, defect Q7): create_nerf builds the matching module and renders."""
+    from pronerf_b200.render import train
+    sd = synth.make_weights(seed=0, calibrated=True)
+    sd["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    ckpt = {k: {n: torch.from_numpy(v) for n, v in d.items()} for k, d in sd.items()}
+    ckpt["global_step"] = 1
+    path = str(tmp_path / "200000.tar")
+    torch.save(ckpt, path)
+    cfg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "llff", "fern", "fern_b200.txt")
+    common = ["--config", cfg, "--factor", "32", "--render_test", "--max_images", "1", "--timing_repeats", "1", "--ft_path", path,
+              "--basedir", str(tmp_path / "logs")]
+    res = train(common + ["--expname", "classic", "--precision", "fp32"])
+    scene = synth.make_scene(factor=32)
+    pv = O.prep_view(scene.H, scene.W, scene.K, scene.poses[int(scene.i_test[0])], scene.poses_ref)
+    ref = O.render_rays(sd, pv["rays"], pv["mm_input"], scene.images_ref[pv["ref_nos"].numpy()], pv["project_mat"], pv["ro_w"],
+                        pv["rd_w"], keep=False)
+    np.testing.assert_allclose(res["rgbs"][0].reshape(-1, 3), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
+    with pytest.raises(NotImplementedError, match="--precision fp32"):
+        train(common + ["--expname", "classic16", "--precision", "bf16"])
+
+
 # ================================================================================================
 # bf16 tensor-core tier (tcgen05): judged by error statistics and delta-PSNR, not max-abs 1e-3
 # ================================================================================================

@@ -222,3 +222,20 @@ def test_llff_loader_matches_the_reference(tmp_path):
     assert (scene.H, scene.W) == (H, W) and np.array_equal(scene.i_ref, g["i_ref"]) and scene.images_ref.shape == (4, H, W, 3)
     np.testing.assert_allclose(scene.poses, g["poses"][:, :3, :4], atol=1e-6)
     assert np.array_equal(scene.gt_image(int(scene.i_test[1])), images[int(g["i_test"][1])])
+
+
+def test_classic_nerf_state_dict_keys():
+    """a19: the classic NeRF module carries the checkpoint's key set (pts_linears.*, views_linears.0.*, feature_linear.*,
+    alpha_linear.*, rgb_linear.*: 24 tensors) and refuses shapes outside the release's."""
+    from pronerf_b200 import synth
+    from pronerf_b200.models import NeRF
+    net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    sd = synth.make_nerf_classic_weights(seed=0)
+    assert set(net.state_dict().keys()) == set(sd.keys()) and len(sd) == 24
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == sd[k].shape, k
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    with pytest.raises(NotImplementedError):
+        NeRF(D=8, W=128, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(4, 90))

@@ -123,3 +123,14 @@ def test_fern504_subset(golden_fern):
                       pv["ro_w"][idx], pv["rd_w"][idx], keep=False)
     np.testing.assert_allclose(r["rgb_map"].numpy(), g["rgb_subset"], atol=1e-5, rtol=0)
     np.testing.assert_allclose(r["depth_map"].numpy(), g["depth_subset"], atol=1e-5, rtol=0)
+
+
+def test_nerf_classic_against_reference():
+    """the classic-NeRF restatement vs the reference's own ``NeRF`` module (tests/golden/nerf_classic.npz)."""
+    from tests.conftest import load_golden
+    g = load_golden("nerf_classic.npz")
+    pts, vd = T(g["pts"]), T(g["viewdirs"])
+    for tag, cal in (("random", False), ("calibrated", True)):
+        sd = synth.make_nerf_classic_weights(seed=0, calibrated=cal)
+        raw = O.run_network(sd, pts, vd)
+        np.testing.assert_allclose(raw.reshape(-1, 4).numpy(), g[f"{tag}_raw"], atol=2e-6 if not cal else 2e-4, rtol=1e-6)
