@@ -197,15 +197,16 @@ int pn_ctx_load_nerf_classic(pn_ctx_t* c, const int* in_dims, const int* out_dim
   for (int l = 0; l < 12; ++l) PN_REQUIRE(W[l] && b[l], "pn_ctx_load_nerf_classic: tensor %d is NULL", l);
   PN_CUDA_OK(cudaSetDevice(c->device));
   free_net(c->f32[PN_NET_NERF]);                            // one shading network per context
-  tc_free_net(c->tc[PN_NET_NERF]);
-  return prog_load_nerf_classic(c->nerf_classic, in_dims, out_dims, W, b, as_stream(stream));
+  int rc = prog_load_nerf_classic(c->nerf_classic, in_dims, out_dims, W, b, as_stream(stream));
+  if (rc != PN_OK) return rc;
+  return tc_load_nerf_classic(c->tc[PN_NET_NERF], in_dims, out_dims, W, b, as_stream(stream));
 }
 
 // classic topology: fp32 only in this build, and said loudly
 static int classic_precision_ok(int precision, const char* who) {
   if (precision == PN_PREC_FP32) return PN_OK;
-  set_error("%s: the classic NeRF topology (stage-2 checkpoints) runs in PN_PREC_FP32 only in this build; "
-            "the tcgen05 tier covers DoNeRFTRT", who);
+  set_error("%s: this form of the classic NeRF topology runs in PN_PREC_FP32 only (the tensor-core tier covers it through "
+            "pn_run_network / pn_render_rays, where both encodings are generated in-kernel)", who);
   return PN_ESTATE;
 }
 
@@ -299,9 +300,11 @@ int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int vie
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(c && pts && viewdirs && raw && N >= 0 && S >= 1 && viewdir_stride >= 3, "pn_run_network: bad arguments");
   if (c->nerf_classic.loaded) {
+    PN_CUDA_OK(cudaSetDevice(c->device));
+    if (precision == PN_PREC_BF16)
+      return tc_launch_nerf_classic(c->tc[PN_NET_NERF], pts, viewdirs, viewdir_stride, S, N * S, raw, as_stream(stream));
     int rcp = classic_precision_ok(precision, "pn_run_network");
     if (rcp != PN_OK) return rcp;
-    PN_CUDA_OK(cudaSetDevice(c->device));
     return prog_launch(c->nerf_classic, IN_ENCODE, pts, viewdirs, viewdir_stride, S, N * S, raw, as_stream(stream));
   }
   int rc = check_nerf(c->f32[PN_NET_NERF]);
@@ -336,10 +339,7 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   const NetF32& ns = c->f32[PN_NET_SAMPLER];
   const NetF32& nr = c->f32[PN_NET_REFINE];
   PN_REQUIRE(ns.loaded && nr.loaded && (c->f32[PN_NET_NERF].loaded || c->nerf_classic.loaded), "pn_render_rays: load all three networks first");
-  if (c->nerf_classic.loaded) {
-    int rcp = classic_precision_ok(f->precision, "pn_render_rays");
-    if (rcp != PN_OK) return rcp;
-  }
+
   PN_REQUIRE(ns.in_dim[0] == 6 * P && ns.out_dim[ns.n_layers - 1] == 3 * S + 3, "pn_render_rays: sampler net shape does not match P=%d S=%d", P, S);
   PN_REQUIRE(nr.in_dim[0] == 6 * S + 3 * NN * S && nr.out_dim[nr.n_layers - 1] == 4 * S + 3, "pn_render_rays: refine net shape does not match S=%d NN=%d", S, NN);
   int rc = check_nerf(c->f32[PN_NET_NERF]);

@@ -56,6 +56,7 @@ enum InputMode : int {
   IN_LOAD2 = 1,       // DoNeRFTRT.forward: [M,63] embedded + [M,27] embedded_dirs (joins at the last layer)
   IN_ENCODE = 2,      // run_network: [M,3] points + per-ray [M/S,3] view dirs, encoded in-kernel
   IN_PLUECKER = 3,    // sampler: rays [N, stride] -> 6P Pluecker features generated in-kernel
+  IN_CLASSIC = 5,     // classic NeRF (helpers.py:792-847): [M,3] points + per-ray view dirs, both encoded in-kernel (tensor-core tier)
   IN_LOAD16 = 4,      // rows come from a dense fp16 [M, K0] tensor (K0 % 8 == 0, 16-byte aligned): refine_input from pn_refine_input_f16
 };
 

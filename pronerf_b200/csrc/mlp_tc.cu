@@ -47,7 +47,8 @@ constexpr int A_BLOCK_BYTES = TILE_M * 128;             // one 64-wide K block o
 constexpr int A_SLOT_BYTES = 4 * A_BLOCK_BYTES;         // 64 KB
 constexpr int RING_SLOT_BYTES = (kHidden / 2) * 128;    // this CTA's half of a 256-row weight K block: 16 KB
 constexpr int N_RING = 5;
-constexpr int BIAS_FLOATS = kMaxLayers * kHidden;       // 8 KB
+constexpr int BIAS_ROWS = 14;                           // 8 layer biases (+ classic NeRF: 3 more, the alpha weights, 2 rows of alpha partial sums)
+constexpr int BIAS_FLOATS = BIAS_ROWS * kHidden;        // 14 KB
 constexpr int OFF_A = 0;
 constexpr int OFF_RING = OFF_A + 2 * A_SLOT_BYTES;
 constexpr int OFF_BIAS = OFF_RING + N_RING * RING_SLOT_BYTES;
@@ -65,9 +66,10 @@ constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 320
 constexpr int W_PRODUCER = N_EPI_WARPS;                 // warp 8 (scheduler 0)
 constexpr int W_MMA = N_EPI_WARPS + 1;                  // warp 9 (scheduler 1)
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_PHASES = 10;
+constexpr int MAX_PHASES = 14;
 
 enum EpiKind : int { EPI_HIDDEN = 0, EPI_MORE = 1, EPI_OUT = 2 };
+enum MoreSrc : int { MORE_LOAD = 0, MORE_PTS = 1, MORE_DIRS = 2 };   // what an EPI_MORE phase writes into K block 0
 
 // One (layer, K range) step of a slot: MMAs over nkb K blocks, then an epilogue.
 struct Phase {
@@ -79,20 +81,28 @@ struct Phase {
   int epi;          // EpiKind
   int merged;       // 1: all nkb K blocks of this (narrow) layer travel as ONE ring chunk [rank][kb][n_pad/2 rows x 128 B]
   uint32_t w_off;   // byte offset of the first chunk in the weight image
+  int act_none;     // hidden epilogue without activation (classic NeRF: feature_linear)
+  int more_src;     // EPI_MORE: MoreSrc
+  int side;         // hidden epilogue also accumulates the alpha head's dot product (classic NeRF: pts_linears.7)
 };
 
 struct Params {
   int n_phases;
   Phase ph[MAX_PHASES];
   const uint8_t* wimg;
-  const float* bias;            // [n_layers][256]
+  const float* bias;            // [n_bias_rows][256]
   int n_layers;
+  int n_bias_rows;
   int n_out;
   int k0;                       // width of the loaded first-layer operand (IN_LOAD / IN_LOAD2)
   const float* in0;
   int in_stride;
   const float* dirterm;         // NeRF: [M / dir_div][4] fp32 view-direction term of the last layer (no bias)
   int dir_div;
+  const float* vdir;            // classic NeRF: per-ray view directions [M / dir_div][vdir_stride], encoded in-kernel
+  int vdir_stride;
+  int alpha_row;                // classic NeRF: bias-table row holding alpha_linear's 256 weights; rows +1, +2 = partial sums
+  float alpha_bias;
   long long M;
   float* out;
   int head_lo[4];
@@ -346,9 +356,12 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
 // (8 x 16 B of this thread's row).  row_base = block + row offset, xr = (r & 7) << 4 (the 128B swizzle).
 // ptxas cannot tell the bias reads from the operand stores apart (both shared memory), so it never hoists a bias load
 // above an earlier store: the loads are issued by hand two chunks ahead (volatile asm keeps the order).
-template <int ACT>
-__device__ __forceinline__ void epilogue_store64(const float* v, uint32_t bias_addr, uint32_t row_base, uint32_t xr, long long* tl = nullptr) {
+// ACT: 0 ReLU, 1 ELU, 2 none.  SIDE: also return sum_c relu(y_c) * wa[c] over the 64 columns (wa = shared-memory address of
+// 64 fp32 weights), evaluated on the fp32 activations before they are rounded to fp16 (classic NeRF's alpha head).
+template <int ACT, bool SIDE = false>
+__device__ __forceinline__ float epilogue_store64(const float* v, uint32_t bias_addr, uint32_t row_base, uint32_t xr, uint32_t wa_addr = 0u) {
   float4 b[20];
+  float side = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) b[i] = ld_shared_v4f(bias_addr + 16u * i);
 #pragma unroll
@@ -364,12 +377,20 @@ __device__ __forceinline__ void epilogue_store64(const float* v, uint32_t bias_a
     add2(x[2], x[3], ba.z, ba.w, y[2], y[3]);
     add2(x[4], x[5], bb.x, bb.y, y[4], y[5]);
     add2(x[6], x[7], bb.z, bb.w, y[6], y[7]);
+    if (SIDE) {
+      const float4 w0 = ld_shared_v4f(wa_addr + 32u * c), w1 = ld_shared_v4f(wa_addr + 32u * c + 16u);
+      side = fmaf(fmaxf(y[0], 0.f), w0.x, side); side = fmaf(fmaxf(y[1], 0.f), w0.y, side);
+      side = fmaf(fmaxf(y[2], 0.f), w0.z, side); side = fmaf(fmaxf(y[3], 0.f), w0.w, side);
+      side = fmaf(fmaxf(y[4], 0.f), w1.x, side); side = fmaf(fmaxf(y[5], 0.f), w1.y, side);
+      side = fmaf(fmaxf(y[6], 0.f), w1.z, side); side = fmaf(fmaxf(y[7], 0.f), w1.w, side);
+    }
     uint32_t w[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : pack_h2(elu_f32(y[2 * u]), elu_f32(y[2 * u + 1]));
+    for (int u = 0; u < 4; ++u)
+      w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : (ACT == 1) ? pack_h2(elu_f32(y[2 * u]), elu_f32(y[2 * u + 1])) : pack_h2(y[2 * u], y[2 * u + 1]);
     st_shared_v4(row_base + ((uint32_t)(c << 4) ^ xr), w[0], w[1], w[2], w[3]);
-    if (kTimeline && tl) tl[c] = clock64();
   }
+  return side;
 }
 
 // debug timeline slots (leader CTA of cluster 0, its second iteration): index = base + phase * 2 + slot
@@ -419,7 +440,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   }
   if (warp == W_PRODUCER) tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
   if (warp < N_EPI_WARPS) {
-    for (int i = threadIdx.x; i < p.n_layers * kHidden; i += N_EPI_WARPS * 32) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_bias_rows * kHidden; i += N_EPI_WARPS * 32) s_bias[i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -616,9 +637,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     const uint32_t a_base = base + OFF_A;
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), xr = (uint32_t)(r & 7) << 4;
     uint32_t acc_par = 0;
-    constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER);
+    constexpr bool kClassic = (MODE == IN_CLASSIC);          // classic NeRF: extra phase kinds, see DESIGN.md 4.3
+    constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER || kClassic);
     constexpr bool kNerf = (MODE == IN_ENCODE || MODE == IN_LOAD2);
-    constexpr int kXin = (MODE == IN_ENCODE) ? 3 : 6;
+    constexpr int kXin = (MODE == IN_ENCODE || kClassic) ? 3 : 6;
     const int kb_first = p.ph[0].nkb;                      // K blocks of the first phase (<= 4)
 
     // global row of this thread in pair tile `tile`
@@ -631,13 +653,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
 #pragma unroll
       for (int i = 0; i < kXin; ++i) xin[i] = 0.f;
       if (row < p.M) {
-        const float* src = p.in0 + row * (MODE == IN_ENCODE ? 3 : p.in_stride);
+        const float* src = p.in0 + row * ((MODE == IN_ENCODE || kClassic) ? 3 : p.in_stride);
 #pragma unroll
         for (int i = 0; i < kXin; ++i) xin[i] = __ldg(src + i);
       }
     };
     auto precompute_input = [&](const float* xin, bool row_live, uint32_t* pre) {
-      if (MODE == IN_ENCODE) {
+      if (MODE == IN_ENCODE || kClassic) {
         if (ch == 0) encode32<0>(xin, pre);
         else encode32<1>(xin, pre);
       } else if (MODE == IN_PLUECKER) {
@@ -813,6 +835,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       for (; ph < np - 1; ++ph) {
         const uint32_t bias_addr = bias_base + (uint32_t)p.ph[ph].layer * (uint32_t)(kHidden * 4);
         const bool last_hidden = ph == np - 2;
+        if (kClassic && p.ph[ph].epi == EPI_MORE) {
+          // A layer whose input is a concatenation (helpers.py:833-834, 839): the K = 256 part has just been multiplied;
+          // the other part -- the encoded points (skip layer) or the encoded view direction (view layer) -- is written
+          // into K block 0 and a short accumulating phase follows.  The raw values are fetched before the accumulator wait.
+          const int src = p.ph[ph].more_src;
+#pragma unroll 1
+          for (int t = 0; t < nslots; ++t) {
+            const long long row = row_of(T0 + t);
+            float x3[3] = {0.f, 0.f, 0.f};
+            if (row < p.M) {
+              const float* g = (src == MORE_PTS) ? p.in0 + row * 3
+                                                 : p.vdir + (long long)((uint32_t)row / (uint32_t)p.dir_div) * p.vdir_stride;
+              x3[0] = __ldg(g); x3[1] = __ldg(g + 1); x3[2] = __ldg(g + 2);
+            }
+            mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+            acc_par ^= 1u << t;
+            tc_fence_after();
+            uint32_t pre[16];
+            if (src == MORE_PTS) {
+              precompute_input(x3, row < p.M, pre);
+              store_pre(t, pre);
+            } else if (ch == 0) {
+              // gamma_4(viewdir): [v, sin(2^l v), cos(2^l v)]_{l<4}, 27 values + 5 zeros = K block 0, chunks 0..3
+              float e[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = 0.f;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                e[c] = x3[c];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                  float sn, cs;
+                  __sincosf(x3[c] * (float)(1 << l), &sn, &cs);
+                  e[3 + 6 * l + c] = sn;
+                  e[6 + 6 * l + c] = cs;
+                }
+              }
+              const uint32_t dst = a_base + t * A_SLOT_BYTES + row_off;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                st_shared_v4(dst + ((uint32_t)(c << 4) ^ xr), pack_h2(e[8 * c], e[8 * c + 1]), pack_h2(e[8 * c + 2], e[8 * c + 3]),
+                             pack_h2(e[8 * c + 4], e[8 * c + 5]), pack_h2(e[8 * c + 6], e[8 * c + 7]));
+            }
+            publish(t, 3);
+          }
+          continue;
+        }
+        const bool act_none = kClassic && p.ph[ph].act_none != 0;
+        const bool side = kClassic && p.ph[ph].side != 0;
+        const bool narrow = kClassic && p.ph[ph].n_pad <= 128;           // 128-wide layer: only the first column group exists
 #pragma unroll 1
         for (int t = 0; t < nslots; ++t) {
           const bool tl_e = tl_it && ew == 0 && ph == 2 && t == 0;      // fine-grained stamps of one hidden epilogue
@@ -858,6 +930,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           tmem_ld32(taddr + 32, v + 32);
           tmem_wait_ld();
           tl_mark(p.timeline, tl_e, TL_EPI + 2);
+          if (kClassic && (act_none || side || narrow)) {
+            // classic NeRF's special layers: linear feature layer, the layer feeding the alpha head, the 128-wide view layer
+            if (!narrow) {
+              tmem_ld32(taddr + 128, v + 64);
+              tmem_ld32(taddr + 128 + 32, v + 96);
+            }
+            const uint32_t wa = base + OFF_BIAS + (uint32_t)(p.alpha_row * kHidden + ch * 64) * 4u;
+            float dot = 0.f;
+            if (act_none) epilogue_store64<2>(v, bias_addr, row_base, xr);
+            else if (side) dot = epilogue_store64<0, true>(v, bias_addr, row_base, xr, wa);
+            else epilogue_store64<0>(v, bias_addr, row_base, xr);
+            tmem_wait_ld();
+            if (!narrow) {
+              if (act_none) epilogue_store64<2>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
+              else if (side) dot += epilogue_store64<0, true>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr, wa + 512u);
+              else epilogue_store64<0>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
+            }
+            if (side)      // this thread's half of alpha_linear(h) for its row; the output phase adds the two halves
+              s_bias[(p.alpha_row + 1 + t) * kHidden + ch * TILE_M + r] = dot;
+            publish(t, 3);
+          } else {
           tmem_ld32(taddr + 128, v + 64);
           tmem_ld32(taddr + 128 + 32, v + 96);
           epilogue_store64<ACT>(v, bias_addr, row_base, xr);
@@ -868,6 +961,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           epilogue_store64<ACT>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
           tl_mark(p.timeline, tl_e, TL_EPI + 5);
           publish(t, p.split ? 2 : 3);
+          }
           tl_mark(p.timeline, tl_e, TL_EPI + 6);
           tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
           tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
@@ -920,7 +1014,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
         if (c0 < n_pad_out && live) {
           const float* bo = s_bias + layer_out * kHidden + c0;
-          if (kNerf) {
+          if (kClassic) {
+            // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
+            const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
+            *reinterpret_cast<float4*>(p.out + row * 4) =
+                make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
+          } else if (kNerf) {
             // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
             const float4 d = t ? dterm1 : dterm0;
             *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
@@ -955,7 +1054,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
 // each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout (narrow output layers: one chunk per layer, see below).  fold > 1: input column k stands for the sum of
 // columns k, k + fold_stride, ... (the sampler's P replicated Pluecker blocks).
 __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int fold, int fold_stride, int n_pad,
-                               int kblocks, int merged, uint8_t* __restrict__ dst) {
+                               int kblocks, int merged, uint8_t* __restrict__ dst, int k_src0 = 0) {
   const int total = kblocks * n_pad * 64;
   const int half_rows = n_pad / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -965,7 +1064,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_
     const int ks = kb * 64 + k;
     float v = 0.f;
     if (n < out_dim && ks < k_used)
-      for (int f = 0; f < fold; ++f) v += W[(size_t)n * in_dim + ks + f * fold_stride];
+      for (int f = 0; f < fold; ++f) v += W[(size_t)n * in_dim + k_src0 + ks + f * fold_stride];
     const int h = n / half_rows, rr = n - h * half_rows;
     // plain: [kb][rank][rows];  merged (narrow layers, one chunk per layer): [rank][kb][rows]
     const size_t blk = merged ? ((size_t)h * kblocks + kb) : ((size_t)kb * 2 + h);
@@ -1107,6 +1206,123 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   return PN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ classic NeRF
+// helpers.py:792-847 on the phase machinery: 13 phases.  Tensors in checkpoint order: pts_linears.0..7 (0..7), alpha_linear (8),
+// feature_linear (9), views_linears.0 (10), rgb_linear (11).
+struct ClassicPhase { int tensor, k_src0, k_used, n_out, bias_row, epi, act_none, more_src, side; };
+static const ClassicPhase kClassicPhases[13] = {
+    {0, 0, 63, 256, 0, tc::EPI_HIDDEN, 0, 0, 0},
+    {1, 0, 256, 256, 1, tc::EPI_HIDDEN, 0, 0, 0},
+    {2, 0, 256, 256, 2, tc::EPI_HIDDEN, 0, 0, 0},
+    {3, 0, 256, 256, 3, tc::EPI_HIDDEN, 0, 0, 0},
+    {4, 0, 256, 256, 4, tc::EPI_HIDDEN, 0, 0, 0},
+    {5, 63, 256, 256, 5, tc::EPI_MORE, 0, tc::MORE_PTS, 0},       // W5[:, 63:319] . h   (h = cat([input_pts, h]), helpers.py:833-834)
+    {5, 0, 63, 256, 5, tc::EPI_HIDDEN, 0, 0, 0},                  // + W5[:, 0:63] . gamma(pts)
+    {6, 0, 256, 256, 6, tc::EPI_HIDDEN, 0, 0, 0},
+    {7, 0, 256, 256, 7, tc::EPI_HIDDEN, 0, 0, 1},                 // its epilogue also evaluates alpha_linear on the fp32 activations
+    {9, 0, 256, 256, 8, tc::EPI_HIDDEN, 1, 0, 0},                 // feature_linear: no activation
+    {10, 0, 256, 128, 9, tc::EPI_MORE, 0, tc::MORE_DIRS, 0},      // Wv[:, 0:256] . feature
+    {10, 256, 27, 128, 9, tc::EPI_HIDDEN, 0, 0, 0},               // + Wv[:, 256:283] . gamma(viewdir), ReLU
+    {11, 0, 128, 3, 10, tc::EPI_OUT, 0, 0, 0},                    // rgb_linear
+};
+constexpr int kClassicAlphaRow = 11;
+constexpr int kClassicBiasRows = 12;
+
+struct ClassicLayout { int kblocks[13], n_pad[13]; bool merged[13]; size_t w_off[13]; size_t img_bytes, bias_off, total; };
+static ClassicLayout classic_layout() {
+  ClassicLayout L{};
+  size_t off = 0;
+  for (int i = 0; i < 13; ++i) {
+    const ClassicPhase& c = kClassicPhases[i];
+    L.kblocks[i] = (c.k_used + 63) / 64;
+    L.n_pad[i] = c.epi == tc::EPI_OUT ? 16 : c.n_out;
+    L.merged[i] = c.epi == tc::EPI_OUT;
+    L.w_off[i] = off;
+    off += (size_t)L.kblocks[i] * L.n_pad[i] * 128;
+  }
+  L.img_bytes = off;
+  L.bias_off = (off + 255) & ~(size_t)255;
+  L.total = L.bias_off + (size_t)kClassicBiasRows * kHidden * 4;
+  return L;
+}
+
+__global__ void pack_classic_alpha_kernel(const float* __restrict__ w_alpha, float* __restrict__ dst) {
+  if (threadIdx.x < kHidden) dst[threadIdx.x] = w_alpha[threadIdx.x];
+}
+
+int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, const float* const* W, const float* const* b,
+                         cudaStream_t stream) {
+  tc_free_net(n);
+  n.net_id = PN_NET_NERF;
+  n.classic = true;
+  n.supported = true;
+  const ClassicLayout L = classic_layout();
+  PN_CUDA_OK(cudaMalloc(&n.blob, L.total));
+  PN_CUDA_OK(cudaMemsetAsync(n.blob, 0, L.total, stream));
+  PN_CUDA_OK(cudaMalloc((void**)&n.error_flag, sizeof(int)));
+  PN_CUDA_OK(cudaMemsetAsync(n.error_flag, 0, sizeof(int), stream));
+  n.blob_bytes = L.total;
+  uint8_t* blob = reinterpret_cast<uint8_t*>(n.blob);
+  float* bias = reinterpret_cast<float*>(blob + L.bias_off);
+  for (int i = 0; i < 13; ++i) {
+    const ClassicPhase& c = kClassicPhases[i];
+    const int total = L.kblocks[i] * L.n_pad[i] * 64;
+    tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[c.tensor], out_dims[c.tensor], in_dims[c.tensor], c.k_used, 1, 0, L.n_pad[i],
+                                                                 L.kblocks[i], L.merged[i] ? 1 : 0, blob + L.w_off[i], c.k_src0);
+    PN_LAUNCH_OK("pack_tc_kernel(classic)");
+    tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[c.tensor], out_dims[c.tensor], bias + (size_t)c.bias_row * kHidden);
+    PN_LAUNCH_OK("pack_tc_bias_kernel(classic)");
+  }
+  pack_classic_alpha_kernel<<<1, kHidden, 0, stream>>>(W[8], bias + (size_t)kClassicAlphaRow * kHidden);
+  PN_LAUNCH_OK("pack_classic_alpha_kernel");
+  PN_CUDA_OK(cudaMemcpyAsync(&n.alpha_bias, b[8], sizeof(float), cudaMemcpyDeviceToHost, stream));
+  PN_CUDA_OK(cudaStreamSynchronize(stream));
+  n.loaded = true;
+  return PN_OK;
+}
+
+static int tc_max_clusters(const void* func, int* out);
+
+// run_network with the classic NeRF: pts [M,3] (M = N*S rows), per-ray view directions, both encoded in-kernel -> raw [M,4]
+int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, int viewdir_stride, int S, int64_t M, float* raw,
+                           cudaStream_t stream) {
+  if (!n.loaded || !n.classic) { set_error("classic NeRF weights not loaded on the tensor-core tier"); return PN_ESTATE; }
+  if (M == 0) return PN_OK;
+  const ClassicLayout L = classic_layout();
+  tc::Params p{};
+  const uint8_t* blob = reinterpret_cast<const uint8_t*>(n.blob);
+  p.wimg = blob;
+  p.bias = reinterpret_cast<const float*>(blob + L.bias_off);
+  p.n_layers = 13; p.n_bias_rows = kClassicBiasRows; p.n_out = 4; p.k0 = 63;
+  p.in0 = pts; p.in_stride = 3; p.M = M; p.out = raw;
+  p.vdir = viewdirs; p.vdir_stride = viewdir_stride; p.dir_div = S > 0 ? S : 1;
+  p.alpha_row = kClassicAlphaRow; p.alpha_bias = n.alpha_bias;
+  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.shift = 0;
+  p.n_phases = 13;
+  for (int i = 0; i < 13; ++i) {
+    const ClassicPhase& c = kClassicPhases[i];
+    tc::Phase& P = p.ph[i];
+    const int rem = c.k_used - (L.kblocks[i] - 1) * 64;
+    P.layer = c.bias_row; P.nkb = L.kblocks[i]; P.k16_last = (rem + 15) / 16; P.n_pad = L.n_pad[i];
+    P.acc = (i > 0 && kClassicPhases[i - 1].epi == tc::EPI_MORE) ? 1 : 0;
+    P.epi = c.epi; P.merged = L.merged[i] ? 1 : 0; P.w_off = (uint32_t)L.w_off[i];
+    P.act_none = c.act_none; P.more_src = c.more_src; P.side = c.side;
+  }
+  auto kern = tc::mlp_tc_kernel<0, IN_CLASSIC>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
+    int rc = tc_max_clusters((const void*)kern, &max_clusters);
+    if (rc != PN_OK) return rc;
+    if (max_clusters <= 0) { set_error("tc: no co-resident CTA pair fits on this device"); return PN_ECUDA; }
+  }
+  const long long units = (M + tc::UNIT_M - 1) / tc::UNIT_M;
+  const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);
+  kern<<<2 * clusters, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);
+  PN_LAUNCH_OK("mlp_tc_kernel(classic)");
+  return PN_OK;
+}
+
 static int tc_max_clusters(const void* func, int* out) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * 148);
@@ -1135,6 +1351,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   p.wimg = blob;
   p.bias = reinterpret_cast<const float*>(blob + L.bias_off);
   p.n_layers = n.n_layers;
+  p.n_bias_rows = n.n_layers;
   p.n_out = n.out_dim[n.n_layers - 1];
   p.k0 = n.in_dim[0];
   p.in0 = Lc.in0; p.in_stride = Lc.in_stride;

@@ -14,6 +14,8 @@ struct NetTC {
   int* error_flag = nullptr;     // device: set by the kernel's barrier watchdog before it traps
   float* dirterm = nullptr;      // device scratch (NeRF): per-ray view-direction term of the last layer, grown on demand
   size_t dirterm_rows = 0;
+  bool classic = false;          // classic NeRF topology (tc_load_nerf_classic)
+  float alpha_bias = 0.f;        // classic NeRF: alpha_linear.bias
   bool supported = false;        // shape within the tensor-core kernel's limits
   bool loaded = false;
 };
@@ -24,5 +26,10 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
 bool tc_available();
 void tc_set_timeline(long long* dev_buf);   // debug: clock64 stamps of CTA 0's second tile (208 slots)
 int tc_launch_mlp(NetTC& n, const MlpLaunch& L, cudaStream_t stream);
+// classic NeRF (helpers.py:792-847) on the tensor-core tier: 12 tensors in checkpoint order; run_network form only
+int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, const float* const* W, const float* const* b,
+                         cudaStream_t stream);
+int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, int viewdir_stride, int S, int64_t M, float* raw,
+                           cudaStream_t stream);
 
 }  // namespace pn

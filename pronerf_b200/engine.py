@@ -62,10 +62,8 @@ class Renderer:
         self.ctx.load_net(_abi.PN_NET_SAMPLER, *lin(s, names))
         self.ctx.load_net(_abi.PN_NET_REFINE, *lin(weights["refine_net_state_dict"], names))
         n = weights["network_fine_state_dict"]
-        if any(k.startswith("pts_linears.") for k in n):          # stage-2 checkpoint: the classic NeRF topology (fp32 tier)
+        if any(k.startswith("pts_linears.") for k in n):          # stage-2 checkpoint: the classic NeRF topology
             from .models import NERF_CLASSIC_KEYS
-            if self.precision != "fp32":
-                raise NotImplementedError("classic NeRF checkpoints run in the fp32 tier only: Renderer(..., precision='fp32')")
             self.ctx.load_nerf_classic(*lin(n, NERF_CLASSIC_KEYS))
         else:
             nl = sum(1 for k in n if k.startswith("layers.") and k.endswith(".weight"))

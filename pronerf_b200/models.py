@@ -89,7 +89,8 @@ class NeRF(_PackedNet):
     """The classic NeRF MLP (run_nerf_helpers.py:792-847) -- what stage 2 trains and saves as ``network_fine``
     (run_S_eS_eN_alter_base_refine2.py:360-362, 890).  ``forward(x)`` takes ``cat([embedded_pts, embedded_views])`` like
     the reference and returns ``cat([rgb, alpha])``.  Built for the release's shape: D=8, W=256, skips=[4], use_viewdirs,
-    63 / 27 encoded inputs; runs in the fp32 tier (the tcgen05 tier covers DoNeRFTRT)."""
+    63 / 27 encoded inputs.  Both tiers through ``run_network`` / ``render_rays`` (encodings generated in-kernel); this explicit
+    ``forward`` on pre-encoded inputs runs in the fp32 tier only."""
     NET_ID = _abi.PN_NET_NERF
 
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):

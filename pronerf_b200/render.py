@@ -481,13 +481,10 @@ def create_nerf(args):
         if any(k.startswith('pts_linears.') for k in ckpt['network_fine_state_dict']):
             # a stage-2 checkpoint: 'network_fine' is the classic NeRF (refine2.py:360-362, 890), which the reference's own infer
             # script cannot load into its DoNeRFTRT (defect Q7); here the matching module is built instead
-            if getattr(args, 'precision', 'fp32') != 'fp32':
-                raise NotImplementedError("this checkpoint holds the classic NeRF topology, which runs in the fp32 tier only: "
-                                          "pass --precision fp32")
             print('network_fine: classic NeRF topology (stage-2 checkpoint)')
             model_fine = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, input_ch_views=input_ch_views, output_ch=output_ch,
                               skips=[4], use_viewdirs=args.use_viewdirs).to(dev)
-            model_fine.precision = 'fp32'
+            model_fine.precision = getattr(args, 'precision', 'fp32')
             model_fine.eval()
         load_state_dicts(model_fine, model_mmray, model_refine, ckpt)
     else:

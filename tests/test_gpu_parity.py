@@ -386,8 +386,7 @@ def test_infer_driver_on_llff_capture(ops, tmp_path):
 def test_nerf_classic_topology(ops):
     """the classic NeRF of stage-2 checkpoints (helpers.py:792-847) as the shading network, fp32 tier --
     module forward and fused run_network against the reference's own outputs (<= 2e-4 abs + 1e-4 rel, as for the other fp32
-    MLPs), a full render against the oracle (<= 1e-3), the checkpoint round trip through create_nerf, and the loud refusal of
-    the tensor-core tier."""
+    MLPs), a full render against the oracle (<= 1e-3), and the tensor-core tier against both."""
     from pronerf_b200.helpers import get_embedder
     from pronerf_b200.models import NeRF
     from pronerf_b200.render import prepare_view, render, run_network
@@ -437,8 +436,31 @@ def test_nerf_classic_topology(ops):
     R = Renderer(sd3, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="fp32", device=DEV)
     rgb_r, depth_r = R.render_view(c2w)
     assert torch.equal(rgb_r, rgb.reshape(-1, 3)) and torch.equal(depth_r, depth.reshape(-1))
-    with pytest.raises(NotImplementedError, match="fp32 tier only"):
-        Renderer(sd3, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    # tensor-core tier: the same network on tcgen05 (13 phases: skip and view layers as "more operand" phases, alpha from the
+    # fp32 epilogue of pts_linears.7, linear feature layer, 128-wide view layer) -- raw vs the reference's own outputs, and the
+    # rendered view vs the fp32 tier
+    _bf16_ready(ops)
+    for tag, cal in (("random", False), ("calibrated", True)):
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_nerf_classic_weights(seed=0, calibrated=cal).items()})
+        net.to(DEV).eval()
+        net.precision = "bf16"
+        raw16 = run_network(pts, vd, net, embed_fn, embeddirs_fn).reshape(-1, 4).cpu().numpy().astype(np.float64)
+        want = g[f"{tag}_raw"].astype(np.float64)
+        mx = np.abs(raw16 - want).max() / max(np.abs(want).max(), 1e-6)
+        rms = np.sqrt(np.mean((raw16 - want) ** 2)) / max(np.sqrt(np.mean(want ** 2)), 1e-9)
+        print(f"classic NeRF, tensor-core tier [{tag}]: max {mx:.2e} rms {rms:.2e} of the output scale")
+        assert mx < 5e-2 and rms < 1.5e-2, (mx, rms)
+        big = torch.cat([pts] * 9, 0)[:800]                                                 # > one 512-row unit, ragged tail
+        bigv = torch.cat([vd] * 9, 0)[:800]
+        raw_big = run_network(big, bigv, net, embed_fn, embeddirs_fn)
+        assert torch.equal(raw_big[:96], run_network(pts, vd, net, embed_fn, embeddirs_fn))
+    R16 = Renderer(sd3, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    rgb16, depth16 = R16.render_view(c2w)
+    from tests.util import psnr
+    p16 = psnr(rgb16.cpu().numpy(), rgb_r.cpu().numpy())
+    print(f"classic NeRF view, tensor-core tier vs fp32 tier: {p16:.1f} dB")
+    assert torch.isfinite(rgb16).all() and p16 >= 38.0
 
 
 def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
@@ -460,8 +482,9 @@ def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
     ref = O.render_rays(sd, pv["rays"], pv["mm_input"], scene.images_ref[pv["ref_nos"].numpy()], pv["project_mat"], pv["ro_w"],
                         pv["rd_w"], keep=False)
     np.testing.assert_allclose(res["rgbs"][0].reshape(-1, 3), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
-    with pytest.raises(NotImplementedError, match="--precision fp32"):
-        train(common + ["--expname", "classic16", "--precision", "bf16"])
+    res16 = train(common + ["--expname", "classic16", "--precision", "bf16"])
+    from tests.util import psnr
+    assert psnr(res16["rgbs"][0], res["rgbs"][0]) >= 38.0
 
 
 # ================================================================================================
