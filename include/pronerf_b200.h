@@ -91,6 +91,11 @@ int pn_ctx_profile_read(pn_ctx_t* ctx, float* ms, int max_frames);
  * [0,S) sigmoid = depth_values, [S,2S) mm_density_add, [2S,3S) mm_density_mul, [3S,3S+3) sigmoid = mm_rgb. */
 int pn_sampler_forward(pn_ctx_t* ctx, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream);
 
+/* The same with the sampler input generated inside the kernel from the NDC ray batch (trt.py:274-278 fused: the 6P-wide
+ * mm_input never exists): rays [N, ray_stride] (o_ndc, d_ndc, ...), P points per ray. */
+int pn_sampler_forward_rays(pn_ctx_t* ctx, const float* rays, int ray_stride, int64_t N, int S, int P, float* out, int precision,
+                            pn_stream_t stream);
+
 /* MinMaxRayEpiSamplerTRT_Net.forward (helpers.py:1526-1540) / RefineEngine.run (engines:303-311).
  * x [N, 6S+3*NN*S] -> out [N, 4S+3]: [0,S) sigmoid = refine_depth, [S,4S) tanh = points_offset,
  * [4S,4S+3) sigmoid = refine_rgb. */
@@ -177,6 +182,18 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
 int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col,
                  const float* add, const float* mul, int64_t N, int S, float* rgb, float* depth, float* disp,
                  float* acc, float* weights, pn_stream_t stream);
+
+/* Stage-1 flavour of raw2outputs (run_S_eS_eN_alter_base.py:501-548): raw is clamped to +-raw_clamp first (the reference uses
+ * 10; <= 0 = no clamp) and add / mul may both be NULL (the NeRF-only step composites without the sampler's density heads). */
+int pn_composite_stage1(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                        const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp,
+                        float* acc, float* weights, pn_stream_t stream);
+
+/* Stage-1 exploration sampling (base.py:689-707, 730), deterministic forward variant: depth [N,S] (sorted) ->
+ * z [N, S*n_mult] = d_s + (m/n_mult) * |d_s - d_{s+1}| (d_S := far = rays[:,7]) and query [N, S*n_mult, 3] = o + dir * z.
+ * (The reference draws n_mult in [1, 64/S], the direction and an extra |N(0, 0.2)| jitter at random per step.) */
+int pn_explore_samples(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, float* z,
+                       float* query, pn_stream_t stream);
 
 /* ---- per-view prep (trt.py:245-278; helpers.py:2705-2714, 2776-2793) ---------------------------- */
 /* get_rays + viewdir normalise + ndc_rays for one H x W view.  c2w [3,4] row-major HOST floats,

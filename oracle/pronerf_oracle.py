@@ -365,3 +365,42 @@ def render_view(weights, scene, c2w, S=8, keep=False):
     r["rgb_map"] = r["rgb_map"].reshape(scene.H, scene.W, 3)
     r["depth_map"] = r["depth_map"].reshape(scene.H, scene.W)
     return r, pv
+
+
+# ----------------------------------------------------------------------------- stage 1 (BASELINE config 3)
+def explore_samples(rays_o, rays_d, depth, far, n_mult):
+    """run_S_eS_eN_alter_base.py:689-707, 730, the deterministic forward variant: n_mult samples per predicted sample,
+    spread over the gap to the next one (the last gap ends at ``far``); sorted; query points ``o + d * z``.
+    (The reference draws n_mult, the direction and an extra jitter at random: :690, :697, :713-728.)"""
+    N, S = depth.shape
+    if n_mult > 1:
+        mults = torch.linspace(0, 1 - 1 / n_mult, n_mult).to(depth)[None]
+        diff = torch.abs(depth - torch.cat((depth[:, 1:], far * torch.ones(N, 1).type_as(depth)), 1))
+        z = (depth[:, :, None] + mults[:, None, :] * diff[:, :, None]).view(N, S * n_mult)
+        z, _ = torch.sort(z, dim=-1)
+    else:
+        z = depth
+    return z, rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+
+
+def raw2outputs_stage1(raw, z_vals, rays_d):
+    """base.py:501-548 without the sampler's density heads (the NeRF-only step): raw clamped to +-10."""
+    dists = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], torch.full_like(z_vals[..., :1], 1e10)], -1)
+    dists = dists * torch.norm(rays_d[..., None, :], dim=-1)
+    raw = torch.clamp(raw, -1e1, 1e1)
+    rgb = torch.sigmoid(raw[..., :3])
+    alpha = 1. - torch.exp(-F.relu(raw[..., 3]) * dists)
+    weights = alpha * torch.cumprod(torch.cat([torch.ones((alpha.shape[0], 1)), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    return torch.sum(weights[..., None] * rgb, -2), torch.sum(weights * z_vals, -1), torch.sum(weights, -1)
+
+
+def stage1_forward(weights, rays, mm_input, n_mult, S=8):
+    """BASELINE config 3 as SURVEY 8(d) reads it: sampler MLP -> sort (base.py:596-606) -> exploration sampling -> classic NeRF
+    -> plain compositing; projection and refine net bypassed."""
+    rays_o, rays_d, near, far, viewdirs = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8], rays[:, 8:11]
+    _, add, mul, d = sampler_forward(weights["mmr_network_fn_state_dict"], mm_input, S)
+    depth, _, _, _, _ = sort_lift(d, add, mul, near, far)
+    z, q = explore_samples(rays_o, rays_d, depth, far, n_mult)
+    raw = run_network(weights["network_fine_state_dict"], q, viewdirs)
+    rgb, dmap, acc = raw2outputs_stage1(raw, z, rays_d)
+    return dict(depth=depth, z=z, query=q, raw=raw, rgb_map=rgb, depth_map=dmap, acc_map=acc)

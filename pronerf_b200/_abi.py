@@ -42,6 +42,7 @@ SIGNATURES = {
     "pn_ctx_load_net": (_i, [_p, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), _p]),
     "pn_ctx_load_nerf_classic": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), _p]),
     "pn_sampler_forward": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
+    "pn_sampler_forward_rays": (_i, [_p, _p, _i, _i64, _i, _i, _p, _i, _p]),
     "pn_refine_forward": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "pn_nerf_forward": (_i, [_p, _p, _p, _i64, _p, _i, _p]),
     "pn_run_network": (_i, [_p, _p, _p, _i, _i64, _i, _p, _i, _p]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "pn_refine_pluecker": (_i, [_p, _i, _p, _i64, _i, _p, _i, _p]),
     "pn_interval_refine": (_i, [_p, _i, _p, _p, _i, _i64, _i, _p, _p, _p]),
     "pn_composite": (_i, [_p, _p, _p, _i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "pn_composite_stage1": (_i, [_p, _p, _p, _i, _i, _p, _p, _f, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "pn_explore_samples": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _p]),
     "pn_raygen": (_i, [_i, _i, _d, _d, _d, _d, C.POINTER(_f), _f, _f, _f, _f, _i, _i, _p, _p, _p]),
     "pn_render_rays": (_i, [_p, C.POINTER(Frame), _p]),
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,

@@ -245,6 +245,19 @@ int pn_sampler_forward(pn_ctx_t* c, const float* x, int64_t N, int S, float* out
   return run_mlp(c, PN_NET_SAMPLER, L, precision, as_stream(stream));
 }
 
+int pn_sampler_forward_rays(pn_ctx_t* c, const float* rays, int ray_stride, int64_t N, int S, int P, float* out, int precision,
+                            pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(c && rays && out && N >= 0 && S >= 1 && P >= 1 && ray_stride >= 6, "pn_sampler_forward_rays: bad arguments");
+  const NetF32& n = c->f32[PN_NET_SAMPLER];
+  PN_REQUIRE(!n.loaded || (n.out_dim[n.n_layers - 1] == 3 * S + 3 && n.in_dim[0] == 6 * P),
+             "pn_sampler_forward_rays: net shape does not match S=%d P=%d", S, P);
+  MlpLaunch L{};
+  L.act = 1; L.input_mode = IN_PLUECKER; L.in0 = rays; L.in1 = nullptr; L.in_stride = ray_stride; L.S = S; L.P = P; L.M = N; L.out = out;
+  heads_sampler(L, S);
+  return run_mlp(c, PN_NET_SAMPLER, L, precision, as_stream(stream));
+}
+
 int pn_refine_forward(pn_ctx_t* c, const float* x, int64_t N, int S, float* out, int precision, pn_stream_t stream) {
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(c && x && out && N >= 0 && S >= 1, "pn_refine_forward: bad arguments");

@@ -61,6 +61,13 @@ __device__ __forceinline__ float linspace01(int i, int P) {
   return (i < P / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(P - 1 - i), 1.f);
 }
 
+// torch.linspace(0, end, n)[i] as the CPU kernel computes it: step = end/(n-1); first half fl(step * i), second half end - step*(n-1-i)
+__device__ __forceinline__ float linspace_step(int i, int n, float end) {
+  if (n <= 1) return 0.f;
+  float step = __fdiv_rn(end, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
 // One thread per (ray, point): 6 outputs.  (All P blocks are equal up to rounding, but the reference feeds
 // the rounded ones to the sampler, so they are reproduced op for op.)
 __global__ void sampler_input_kernel(const float* __restrict__ rays, int ray_stride, int64_t N, int P,
@@ -193,6 +200,30 @@ __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_s
     q[t * 3 + c] = __fadd_rn(__fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz)), __fmul_rn(1e-2f, off[c]));
 }
 
+// ------------------------------------------------------------------------------------------------ stage-1 exploration sampling
+// base.py:689-707, 730 (the NeRF-only training step of stage 1), deterministic "forward" variant: every predicted sample s
+// spawns n_mult samples z = d_s + (m / n_mult) * |d_s - d_{s+1}| (d_S := far), m = 0..n_mult-1 -- already ascending, so the
+// reference's torch.sort (":not really needed?") is the identity -- and the query points o + dir * z.  The reference draws
+// n_mult, the direction and an extra |N(0, 0.2)| jitter at random; a benchmark fixes n_mult and drops the jitter.
+__global__ void explore_samples_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth, int64_t N,
+                                       int S, int n_mult, float mult_end, float* __restrict__ z, float* __restrict__ q) {
+  const int So = S * n_mult;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * So) return;
+  int64_t r = t / So;
+  int j = (int)(t - r * So);
+  int s = j / n_mult, m = j - s * n_mult;
+  const float* ray = rays + r * ray_stride;
+  const float* d = depth + r * S;
+  float dc = d[s];
+  float dn = (s + 1 < S) ? d[s + 1] : ray[7];                                   // far * ones   (base.py:698)
+  float mult = (n_mult > 1) ? linspace_step(m, n_mult, mult_end) : 0.f;         // torch.linspace(0, 1 - 1/n_mult, n_mult)[m]
+  float zz = __fadd_rn(dc, __fmul_rn(mult, fabsf(__fsub_rn(dc, dn))));
+  z[t] = zz;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) q[t * 3 + c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+}
+
 // ------------------------------------------------------------------------------------------------ compositing
 // S lanes per ray (S a power of two <= 32): lane = (ray-in-warp, sample).  Every global access is
 // coalesced (consecutive lanes read consecutive float4 / float); the transmittance T_s = prod_{j<s}(1-a_j+1e-10)
@@ -204,27 +235,33 @@ __device__ __forceinline__ float disp_of(float wz, float ws) {
   return 1.f / ((q != q) ? q : fmaxf(1e-10f, q));
 }
 
+// stage 1 clamps the network output before compositing (torch.clamp(raw, -10, 10), base.py:523); the infer path does not (Q4)
+__device__ __forceinline__ float4 clamp_raw(float4 r, float c) {
+  if (c > 0.f) { r.x = fminf(fmaxf(r.x, -c), c); r.y = fminf(fmaxf(r.y, -c), c); r.z = fminf(fmaxf(r.z, -c), c); r.w = fminf(fmaxf(r.w, -c), c); }
+  return r;
+}
+
 template <int S>
 __global__ void composite_scan_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                       const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                       const float* __restrict__ add, const float* __restrict__ mul, int64_t N,
                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                      float* __restrict__ acc, float* __restrict__ weights) {
+                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one (ray, sample) per thread
   int64_t r = t / S;
   int s = (int)(t % S);
   bool live = r < N;
   int64_t rr = live ? r : (N - 1);
   int64_t tt = rr * S + s;
-  float4 rw = reinterpret_cast<const float4*>(raw)[tt];
+  float4 rw = clamp_raw(reinterpret_cast<const float4*>(raw)[tt], raw_clamp);
   float zc = z[tt];
   float zn = __shfl_down_sync(0xffffffffu, zc, 1);                  // z_{s+1} (same segment when s < S-1)
   const float* rd = rays + rr * ray_stride + ray_d_col;
   float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
   float dist = (s == S - 1) ? 1e10f : (zn - zc);
   dist *= dn;
-  float sig = fmaxf(rw.w + add[tt], 0.f);
-  float alpha = (1.f - expf(-sig * dist)) * fmaxf(mul[tt], 0.f);
+  float sig = fmaxf(rw.w + (add ? add[tt] : 0.f), 0.f);
+  float alpha = (1.f - expf(-sig * dist)) * (mul ? fmaxf(mul[tt], 0.f) : 1.f);
   // exclusive product scan of (1 - alpha + 1e-10) over the segment
   float f = 1.f - alpha + 1e-10f;
   float incl = f;
@@ -261,7 +298,7 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
                                      const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                      const float* __restrict__ add, const float* __restrict__ mul, int64_t N, int S,
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                     float* __restrict__ acc, float* __restrict__ weights) {
+                                     float* __restrict__ acc, float* __restrict__ weights, float raw_clamp) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   const float* rd = rays + r * ray_stride + ray_d_col;
@@ -269,11 +306,11 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wz = 0.f, ws = 0.f;
   for (int s = 0; s < S; ++s) {
     int64_t tt = r * S + s;
-    float4 rw = reinterpret_cast<const float4*>(raw)[tt];
+    float4 rw = clamp_raw(reinterpret_cast<const float4*>(raw)[tt], raw_clamp);
     float zc = z[tt];
     float dist = (s == S - 1) ? 1e10f : (z[tt + 1] - zc);
     dist *= dn;
-    float alpha = (1.f - expf(-fmaxf(rw.w + add[tt], 0.f) * dist)) * fmaxf(mul[tt], 0.f);
+    float alpha = (1.f - expf(-fmaxf(rw.w + (add ? add[tt] : 0.f), 0.f) * dist)) * (mul ? fmaxf(mul[tt], 0.f) : 1.f);
     float w = alpha * T;
     T *= (1.f - alpha + 1e-10f);
     cr += w * sigmoidf_(rw.x); cg += w * sigmoidf_(rw.y); cb += w * sigmoidf_(rw.z);
@@ -410,16 +447,28 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
   return PN_OK;
 }
 
-int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
-                 const float* mul, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc, float* weights,
-                 pn_stream_t stream) {
+int pn_explore_samples(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, float* z, float* query,
+                       pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(rays && depth && z && query && N >= 0 && S >= 1 && n_mult >= 1 && S * n_mult <= 1024 && ray_stride >= 8,
+             "pn_explore_samples: bad arguments (S=%d n_mult=%d)", S, n_mult);
+  const float mult_end = (float)(1.0 - 1.0 / (double)n_mult);   // the Python double `1 - 1/n_mult`, rounded once like torch does
+  explore_samples_kernel<<<blocks_for(N * S * n_mult), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, N, S, n_mult, mult_end,
+                                                                                       z, query);
+  PN_LAUNCH_OK("pn_explore_samples");
+  return PN_OK;
+}
+
+int pn_composite_stage1(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                        const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
+                        float* weights, pn_stream_t stream) {
   if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
-  PN_REQUIRE(raw && z && rays && add && mul && rgb && depth && N >= 0 && S >= 1 && ray_stride >= ray_d_col + 3,
+  PN_REQUIRE(raw && z && rays && rgb && depth && N >= 0 && S >= 1 && ray_stride >= ray_d_col + 3 && ((add == nullptr) == (mul == nullptr)),
              "pn_composite: bad arguments");
   cudaStream_t st = as_stream(stream);
 #define PN_COMP(SS)                                                                                                  \
   composite_scan_kernel<SS><<<blocks_for(N * SS), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, \
-                                                                     rgb, depth, disp, acc, weights)
+                                                                     rgb, depth, disp, acc, weights, raw_clamp)
   switch (S) {
     case 2: PN_COMP(2); break;
     case 4: PN_COMP(4); break;
@@ -428,11 +477,18 @@ int pn_composite(const float* raw, const float* z, const float* rays, int ray_st
     case 32: PN_COMP(32); break;
     default:
       composite_seq_kernel<<<blocks_for(N), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, S, rgb,
-                                                              depth, disp, acc, weights);
+                                                              depth, disp, acc, weights, raw_clamp);
   }
 #undef PN_COMP
   PN_LAUNCH_OK("pn_composite");
   return PN_OK;
+}
+
+int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                 const float* mul, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc, float* weights,
+                 pn_stream_t stream) {
+  PN_REQUIRE(N == 0 || (add && mul), "pn_composite: bad arguments");
+  return pn_composite_stage1(raw, z, rays, ray_stride, ray_d_col, add, mul, 0.f, N, S, rgb, depth, disp, acc, weights, stream);
 }
 
 int pn_raygen(int H, int W, double fx, double fy, double cx, double cy, const float* c2w_host, float near_, float far_,

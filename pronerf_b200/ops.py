@@ -126,6 +126,15 @@ class Context:
                                            stream_ptr(x.device)), "pn_sampler_forward")
         return out
 
+    def sampler_forward_rays(self, rays, S, P, precision="fp32", out=None):
+        """Sampler MLP with its Pluecker input generated in-kernel from the NDC ray batch [N, >=6] -> heads [N, 3S+3]."""
+        rays = as_f32c(rays)
+        out = self._out(out, (rays.shape[0], 3 * S + 3), rays)
+        with _cuda_guard(rays):
+            check(lib().pn_sampler_forward_rays(self.handle, dptr(rays, "rays"), rays.shape[1], rays.shape[0], S, P, dptr(out),
+                                                PRECISIONS[precision], stream_ptr(rays.device)), "pn_sampler_forward_rays")
+        return out
+
     def refine_forward(self, x, S, precision="fp32", out=None):
         x = as_f32c(x)
         out = self._out(out, (x.shape[0], 4 * S + 3), x)
@@ -419,6 +428,32 @@ def composite(raw, z_vals, rays_d, add, mul, extras: bool = True):
                                  disp.data_ptr() if extras else None, acc.data_ptr() if extras else None,
                                  w.data_ptr() if extras else None, stream_ptr(raw.device)), "pn_composite")
     return rgb, disp, acc, w, depth
+
+
+def composite_stage1(raw, z_vals, rays_d, add=None, mul=None, raw_clamp: float = 10.0):
+    """Stage-1 raw2outputs (base.py:501-548): raw clamped to +-raw_clamp, optional density heads -> (rgb_map, depth_map, acc_map)."""
+    raw, z_vals, rays_d = (as_f32c(t) for t in (raw, z_vals, rays_d))
+    N, S = z_vals.shape
+    rgb, depth, acc = _empty((N, 3), raw), _empty((N,), raw), _empty((N,), raw)
+    a = dptr(as_f32c(add), "add") if add is not None else None
+    m = dptr(as_f32c(mul), "mul") if mul is not None else None
+    with _cuda_guard(raw):
+        check(lib().pn_composite_stage1(dptr(raw, "raw"), dptr(z_vals, "z_vals"), dptr(rays_d, "rays_d"), rays_d.shape[1], 0, a, m,
+                                        float(raw_clamp), N, S, dptr(rgb), dptr(depth), None, dptr(acc), None,
+                                        stream_ptr(raw.device)), "pn_composite_stage1")
+    return rgb, depth, acc
+
+
+def explore_samples(rays, depth, n_mult: int):
+    """Stage-1 exploration sampling, deterministic forward variant (base.py:689-707, 730) -> z [N, S*n_mult], query [N, S*n_mult, 3]."""
+    rays, depth = as_f32c(rays), as_f32c(depth)
+    N, S = depth.shape
+    z = _empty((N, S * n_mult), depth)
+    q = _empty((N, S * n_mult, 3), depth)
+    with _cuda_guard(depth):
+        check(lib().pn_explore_samples(dptr(rays, "rays"), rays.shape[1], dptr(depth, "depth"), N, S, int(n_mult), dptr(z), dptr(q),
+                                       stream_ptr(depth.device)), "pn_explore_samples")
+    return z, q
 
 
 def raygen(H, W, K, c2w, device, near=0., far=1., or_near=1., or_far=10., row0=0, nrows=None):

@@ -487,6 +487,34 @@ def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
     assert psnr(res16["rgbs"][0], res["rgbs"][0]) >= 38.0
 
 
+@pytest.mark.parametrize("n_mult", [1, 3, 8])
+def test_stage1_style_forward(ops, n_mult):
+    """BASELINE config 3 / SURVEY 8(f4): sampler MLP -> sort -> exploration sampling (base.py:689-707, deterministic variant) ->
+    classic NeRF -> stage-1 compositing (raw clamped to +-10, base.py:523), against the oracle's restatement of the same chain:
+    exploration depths and query points BIT-EXACT on identical sorted depths, fp32 tier rgb / depth <= 1e-3, tensor-core tier by
+    PSNR."""
+    from pronerf_b200.engine import Renderer
+    from pronerf_b200.stage1 import stage1_forward
+    from tests.util import psnr
+    scene = synth.make_small_scene(H=20, W=28)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    sd["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    pv = O.prep_view(scene.H, scene.W, scene.K, scene.poses[8], scene.poses_ref)
+    ref = O.stage1_forward(sd, pv["rays"], pv["mm_input"], n_mult)
+    rays = pv["rays"].to(DEV)
+    z, q = ops.explore_samples(rays, ref["depth"].to(DEV), n_mult)
+    assert torch.equal(z.cpu(), ref["z"]) and torch.equal(q.cpu(), ref["query"])
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="fp32", device=DEV)
+    rgb, depth, acc = stage1_forward(R.ctx, rays, 8, 48, n_mult, "fp32")
+    np.testing.assert_allclose(rgb.cpu().numpy(), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(depth.cpu().numpy(), ref["depth_map"].numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(acc.cpu().numpy(), ref["acc_map"].numpy(), atol=1e-3, rtol=0)
+    if ops.bf16_tier_available():
+        R16 = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+        rgb16, _, _ = stage1_forward(R16.ctx, rays, 8, 48, n_mult, "bf16")
+        assert torch.isfinite(rgb16).all() and psnr(rgb16.cpu().numpy(), ref["rgb_map"].numpy()) >= 38.0
+
+
 # ================================================================================================
 # bf16 tensor-core tier (tcgen05): judged by error statistics and delta-PSNR, not max-abs 1e-3
 # ================================================================================================
