@@ -13,6 +13,14 @@ restatement against those vectors (bit-exact for the sort permutation, the proje
 coordinates and the bilinear tap indices; <=1e-6 for floating-point stages).  The reference has no
 tests or golden vectors of its own.
 
+Later additions: ``nerf_classic_forward`` is pinned to the reference's own ``NeRF`` module
+(``oracle/make_golden_nerf_classic.py`` -> ``tests/golden/nerf_classic.npz``); the LLFF loader restatement lives in the
+package (host-side I/O, ``pronerf_b200/llff_io.py``) and is pinned to the reference's loader by
+``oracle/make_golden_llff.py``.  **Parity unpinned** for ``explore_samples`` / ``stage1_forward``: the reference's
+exploration sampling draws ``n_mult``, the direction and a jitter at random inside ``render_rays`` (base.py:690-728), so
+there is no deterministic reference output to store; the restatement follows the cited lines for the forward variant
+with the jitter removed, and everything it composes (sampler, sort, classic NeRF, compositing formula) is pinned.
+
 Every function cites the reference lines it follows.  Paths are relative to ``/root/reference``;
 ``trt.py`` = ``run_S_eS_eN_alter_trt.py``, ``helpers.py`` = ``run_nerf_helpers.py``, ``iw.py`` =
 ``inverse_warp.py``.

@@ -687,6 +687,33 @@ def test_multi_view_batch(ops, precision):
     assert not torch.equal(rgb_o, rgb_h)
 
 
+def test_cuda_graph_replay(ops):
+    """One pn_render_rays pass (7 kernels on the tensor-core tier) is capturable in a CUDA graph once the context's scratch has
+    reached its high-water mark (no allocation, no synchronisation inside): replays are bit-identical to the eager pass."""
+    _bf16_ready(ops)
+    from pronerf_b200.engine import Renderer
+    scene = synth.make_small_scene(H=20, W=28)
+    sd = synth.make_weights(seed=3, calibrated=True)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    batch = R.prepare_views([scene.poses[i] for i in (0, 8)])
+    rgb_e, depth_e = R.render_prepared(batch)                      # warm-up: scratch, occupancy queries, weight packing
+    rgb_e, depth_e = rgb_e.clone(), depth_e.clone()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        R.render_prepared(batch)
+        s.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            R.render_prepared(batch)
+    for _ in range(3):
+        batch["rgb"].zero_(); batch["depth"].zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(batch["rgb"], rgb_e) and torch.equal(batch["depth"], depth_e)
+
+
 def test_bf16_edge_cases(ops):
     _bf16_ready(ops)
     scene = synth.make_small_scene(H=16, W=20)
