@@ -326,7 +326,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        # the tensor-core tier multiplies IEEE fp16 operands and accumulates in fp32 (the "bf16" tier name is historical)
+        "dtype": "fp16" if precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "ProNeRF stage-2 infer, fern-shaped 504x378, 3 test views (571536 rays/step), S=8, P=48, NN=4, "
                                "random-init sampler+refine+DoNeRFTRT", "precision": precision,
                    "l2": "flushed before every timed step (256 MiB memset outside the step events)",

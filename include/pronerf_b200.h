@@ -41,7 +41,7 @@ typedef struct pn_ctx pn_ctx_t;   /* owns packed weights + scratch, like the ref
 
 /* arithmetic tier of the three MLPs */
 #define PN_PREC_FP32    0         /* fp32 SIMT FMA: the <=1e-3 max-abs parity tier            */
-#define PN_PREC_BF16    1         /* bf16 operands, fp32 accumulate in TMEM on tcgen05 tensor cores */
+#define PN_PREC_BF16    1         /* 16-bit operands (IEEE fp16 since v3 of the kernel; the name is historical), fp32 accumulate in TMEM on tcgen05 */
 
 int         pn_version(void);
 const char* pn_last_error(void);
@@ -60,7 +60,7 @@ void pn_ctx_destroy(pn_ctx_t* ctx);
 /* Load one network from nn.Linear-layout device tensors: W[l] is [out_dims[l], in_dims[l]] row-major,
  * b[l] is [out_dims[l]].  Layer order = fc_backbone.0..5, fc_output (sampler / refine) or
  * layers.0..7 (DoNeRFTRT); state_dict keys per trt.py:478-481.  Hidden width must be 256.
- * Packs both the fp32 (k-major) and the bf16 (UMMA canonical, 128B-swizzled) images of the weights. */
+ * Packs both the fp32 (k-major) and the 16-bit (fp16, UMMA canonical, 128B-swizzled) images of the weights. */
 int pn_ctx_load_net(pn_ctx_t* ctx, int net, int n_layers, const int* in_dims, const int* out_dims,
                     const float* const* W_device, const float* const* b_device, pn_stream_t stream);
 
