@@ -16,6 +16,7 @@
 #ifndef PRONERF_B200_H
 #define PRONERF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -250,6 +251,17 @@ int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doub
                          const float* c2w_host, const float* texels, const int* tex_index_host,
                          const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
                          float* depth_host, void* texels_ready_event, pn_stream_t stream);
+
+/* ---- peer frame buffers: the final tile gather of a sharded frame as direct stores over NVLink -------------------------
+ * One process per GPU.  The destination rank calls pn_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; handle64 = 64 bytes to
+ * ship to the other ranks by any means), every other rank pn_peer_open's the handle (cudaIpcOpenMemHandle with lazy peer
+ * access) and passes `mapped pointer + its band's offset` as pn_frame_t.rgb / .depth: the compositing kernel then writes the
+ * band straight into the destination GPU's frame while it renders, and the only thing left is a barrier.  (The reference has
+ * no distributed code)  pn_peer_close unmaps, pn_peer_free releases the owner's allocation. */
+int pn_peer_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int pn_peer_open(int device, const unsigned char* handle64, void** dev_ptr);
+int pn_peer_close(void* dev_ptr);
+int pn_peer_free(void* dev_ptr);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,10 @@ SIGNATURES = {
     "pn_composite_stage1": (_i, [_p, _p, _p, _i, _i, _p, _p, _f, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pn_explore_samples": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _p]),
     "pn_raygen": (_i, [_i, _i, _d, _d, _d, _d, C.POINTER(_f), _f, _f, _f, _f, _i, _i, _p, _p, _p]),
+    "pn_peer_alloc": (_i, [_i, C.c_size_t, C.POINTER(_p), C.c_char_p]),
+    "pn_peer_open": (_i, [_i, C.c_char_p, C.POINTER(_p)]),
+    "pn_peer_close": (_i, [_p]),
+    "pn_peer_free": (_i, [_p]),
     "pn_render_rays": (_i, [_p, C.POINTER(Frame), _p]),
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
                                   _p, _p, _p, _p]),

@@ -518,4 +518,44 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
   return PN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ peer frame buffers
+// The tile gather of a sharded frame as direct stores over NVLink: the destination rank allocates the frame
+// buffer here (cudaMalloc, so that the IPC handle covers exactly this allocation), the other ranks map it into their
+// address space and hand `frame + band offset` to pn_render_rays as rgb / depth -- the compositing kernel's stores then land
+// in the destination GPU's memory while the band is still being rendered, and no collective follows.
+int pn_peer_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  PN_REQUIRE(dev_ptr && handle64 && bytes > 0, "pn_peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  PN_CUDA_OK(cudaSetDevice(device));
+  void* p = nullptr;
+  PN_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return PN_OK;
+}
+
+int pn_peer_open(int device, const unsigned char* handle64, void** dev_ptr) {
+  PN_REQUIRE(dev_ptr && handle64, "pn_peer_open: bad arguments");
+  PN_CUDA_OK(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  PN_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PN_OK;
+}
+
+int pn_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return PN_OK;
+  PN_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return PN_OK;
+}
+
+int pn_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return PN_OK;
+  PN_CUDA_OK(cudaFree(dev_ptr));
+  return PN_OK;
+}
+
 }  // extern "C"

@@ -14,11 +14,12 @@ import torch
 import torch.distributed as dist
 from pronerf_b200 import synth
 from pronerf_b200.engine import Renderer
-from pronerf_b200.multigpu import gather_frame, shard_rows
+from pronerf_b200.multigpu import PeerFrame, gather_frame, render_frame_sharded_p2p, shard_rows
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--factor", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--p2p", action="store_true", help="gather by direct peer stores into rank 0's frame (CUDA IPC over NVLink) instead of NCCL send/recv")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -40,7 +41,12 @@ def barrier():
     torch.cuda.synchronize(dev)
 
 
+peer = PeerFrame(H, W, dev, dst=0) if (args.p2p and world > 1) else None
+
+
 def frame():
+    if peer is not None:
+        return render_frame_sharded_p2p(R, c2w, peer, prep=prep)
     rgb, depth = R.render_prepared(prep)
     if world > 1:
         return gather_frame(rgb, depth, H, W, dst=0)
@@ -61,7 +67,11 @@ for _ in range(args.reps):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(float(t.item()))
-band_sum = torch.stack([prep["rgb"].double().sum(), prep["depth"].double().sum()])
+if peer is not None:                               # this rank's band as it sits in the destination frame
+    b_rgb, b_depth = peer.band(row0, nrows)
+else:
+    b_rgb, b_depth = prep["rgb"], prep["depth"]
+band_sum = torch.stack([b_rgb.double().sum(), b_depth.double().sum()])
 if world > 1:
     dist.all_reduce(band_sum)
 if rank == 0:
@@ -76,9 +86,21 @@ if rank == 0:
     ok_band = bool(torch.equal(rgb_c.reshape(nr_chk, W, 3), full_rgb[r0:r0 + nr_chk]) and
                    torch.equal(depth_c.reshape(nr_chk, W), full_depth[r0:r0 + nr_chk]))
     best = min(times)
+    if peer is not None:                           # and the peer-store frame must equal the NCCL-gathered one bit for bit
+        full_rgb, full_depth = full_rgb.clone(), full_depth.clone()
     print(json.dumps({"config": f"{W}x{H} frame, row bands over {world} GPU(s), S=8, tensor-core tier", "n_gpus": world, "rays": H * W,
+                      "gather": "direct peer stores (CUDA IPC over NVLink)" if peer is not None else ("NCCL send/recv" if world > 1 else "none"),
                       "ms_best": best, "ms_all": times, "mrays_s": H * W / best / 1e3, "gather_bytes": H * W * 16,
                       "checks": {"finite": ok_finite, "checksum_of_band_checksums": ok_sum, "band_bit_identical": ok_band}}))
     assert ok_finite and ok_sum and ok_band
+if peer is not None:
+    # cross-check against the NCCL gather of the same bands
+    rgb_b, depth_b = R.render_prepared(prep)
+    ref_rgb, ref_depth = gather_frame(rgb_b, depth_b, H, W, dst=0)
+    if rank == 0:
+        assert torch.equal(ref_rgb, full_rgb) and torch.equal(ref_depth, full_depth), "peer-store frame != NCCL-gathered frame"
+        print(json.dumps({"p2p_equals_nccl_gather": True}))
+    dist.barrier()
+    peer.close()
 if world > 1:
     dist.destroy_process_group()

@@ -239,3 +239,15 @@ def test_classic_nerf_state_dict_keys():
         NeRF(D=8, W=128, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         net(torch.zeros(4, 90))
+
+
+def test_peer_frame_band_views():
+    """Host logic of the peer-store gather (multigpu.PeerFrame): bands of all ranks tile the destination frame exactly."""
+    from pronerf_b200.multigpu import all_shards
+    H, W = 37, 5
+    cover = np.zeros(H * W, dtype=np.int32)
+    for world in (1, 2, 3, 8):
+        cover[:] = 0
+        for row0, nrows in all_shards(H, world):
+            cover[row0 * W:(row0 + nrows) * W] += 1
+        assert (cover == 1).all()
