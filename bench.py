@@ -1,21 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the ProNeRF per-ray render hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the ProNeRF per-ray render hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py --gpus N --steps K --warmup W [--precision bf16|fp32] [--impl reference]
 
 Workload (BASELINE.json configs[1]): the full synthetic fern-shaped test set -- 3 views of 504x378, 8 samples/ray,
-48-point ray encoding, 4 neighbour views, random-init networks.  One STEP = one pass of the hot path over that
-batch: 3 x (sampler MLP -> sort/lift -> project+gather -> refine MLP -> interval refinement -> encode+NeRF MLP ->
-composite) = 571 536 rays.  At N GPUs every rank renders the whole batch (view-parallel serving; no data-path
-collective) -> weak scaling; value = rays of all ranks / max-over-ranks device time.
+48-point ray encoding, 4 neighbour views, random-init networks.  One STEP = one pass of the hot path over that batch:
+the rays of the 3 views stacked into one multi-view pass (sampler MLP -> fused sort/lift + Pluecker + project/gather ->
+refine MLP -> interval refinement -> encode + NeRF MLP -> composite; 7 kernels on the tensor-core tier) = 571 536 rays.
+At N GPUs every rank renders the whole batch (view-parallel serving; no data-path collective) -> weak scaling;
+value = rays of all ranks / max-over-ranks device time.
 
 * ``value``  kernel-only throughput: rays, reference views and weights resident in HBM, per-step CUDA events,
   L2 flushed (256 MiB memset) before every timed step.
-* ``e2e``    same metric through the host-buffer plug-in call (``Renderer.render_view_host`` ->
-  ``pn_render_view_host``): every step uploads the reference views from pinned host memory, every view uploads
-  its pose + projection matrices and reads rgb + depth back into pinned host memory.
-* ``roofline``  the dominant kernel (encode+NeRF MLP) timed live with CUDA events around that kernel inside the
-  timed region (``pn_ctx_profile``), against MEASURED_PEAKS.json.
+* ``e2e``    same metric through the host-buffer plug-in call (``Renderer.render_views_host`` ->
+  ``pn_render_views_host``): every step uploads + packs the reference views from pinned host memory (on a copy stream,
+  under the sampler MLP), uploads the poses + projection matrices and reads rgb + depth of all views back into pinned
+  host memory.
+* ``roofline``  the dominant kernel (encode + NeRF MLP) timed live with CUDA events around that stage inside the
+  timed region (``pn_ctx_profile``), against MEASURED_PEAKS.json; ``traffic`` from the committed ncu capture.
 * ``cpu_baseline``  the CPU oracle port (PyTorch fp32 ops in the reference's order) on the box's host cores.
 * ``--impl reference``  times that CPU port alone on a bounded sample of the same workload.
 """
