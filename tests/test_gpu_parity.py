@@ -687,6 +687,55 @@ def test_multi_view_batch(ops, precision):
     assert not torch.equal(rgb_o, rgb_h)
 
 
+def test_full_size_properties(ops):
+    """BASELINE size (one 504x378 view, 190 512 rays), size-independent properties of every stage and of the tensor-core tier:
+    sortedness / permutation of the sampler depths, linearity and zero-padding bound of the bilinear gather, bounds of the
+    compositing, and ray independence of the whole tensor-core pass (halves and a permuted batch render bit-identical pixels)."""
+    _bf16_ready(ops)
+    from pronerf_b200.engine import Renderer
+    scene = synth.make_scene(factor=8)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    prep = R.prepare_view(scene.poses[int(scene.i_test[1])])
+    rays, or_rays = prep["rays"], prep["or_rays"]
+    n, S = rays.shape[0], 8
+    heads = R.ctx.sampler_forward_rays(rays, S, 48, precision="bf16")
+    # (1) fused refine-input kernel: depths ascending, (depth, add, mul) a permutation of the heads, fp16 rows finite
+    depth, add, mul, rin = ops.refine_input_f16(heads, rays, or_rays, R.texels, prep["project_mat"], S, tex_index=prep["tex_index"])
+    assert bool((depth[:, 1:] >= depth[:, :-1]).all())
+    scaled = heads[:, :S] * (rays[:, 7:8] - rays[:, 6:7]) + rays[:, 6:7]
+    assert torch.equal(torch.sort(scaled, -1)[0], depth)
+    assert torch.equal(torch.sort(heads[:, S:2 * S], -1)[0], torch.sort(add, -1)[0])
+    assert torch.equal(torch.sort(heads[:, 2 * S:3 * S], -1)[0], torch.sort(mul, -1)[0])
+    assert bool(torch.isfinite(rin.float()).all())
+    # (2) bilinear gather: linear in the images; with an all-ones image every feature is the sum of its valid tap weights in [0, 1]
+    d3 = 1.0 / (1.0 - depth - 1e-5)
+    g = torch.Generator().manual_seed(5)
+    A = torch.rand(scene.images_ref.shape, generator=g).to(DEV)
+    B = torch.rand(scene.images_ref.shape, generator=g).to(DEV)
+    ga, gb, gab, g1 = (ops.project_gather(ops.pack_images(x), prep["project_mat"], or_rays, or_rays[:, 3:], d3, ray_stride=11)
+                       for x in (A, B, 0.25 * A + 0.5 * B, torch.ones_like(A)))
+    assert float((gab - (0.25 * ga + 0.5 * gb)).abs().max()) <= 2e-6
+    assert float(g1.min()) >= 0.0 and float(g1.max()) <= 1.0 + 1e-6
+    # (3) the whole tensor-core pass: ray independence at full size, and compositing bounds on its outputs
+    rgb, dmap = R.render_prepared(prep)
+    rgb, dmap = rgb.clone(), dmap.clone()
+    assert bool(torch.isfinite(rgb).all()) and float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5
+    assert float(dmap.min()) >= -1e-5 and float(dmap.max()) <= 1.0 + 1e-5          # sum w z with z in [near, far] = [0, 1], sum w <= 1
+    half = n // 2 + 77
+    outs = []
+    for sl in (slice(0, half), slice(half, n)):
+        sub = dict(prep, rays=rays[sl].contiguous(), or_rays=or_rays[sl].contiguous(), rgb=torch.empty((sl.stop - sl.start, 3), device=DEV),
+                   depth=torch.empty((sl.stop - sl.start,), device=DEV))
+        outs.append(tuple(t.clone() for t in R.render_prepared(sub)))
+    assert torch.equal(torch.cat([outs[0][0], outs[1][0]]), rgb) and torch.equal(torch.cat([outs[0][1], outs[1][1]]), dmap)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).to(DEV)
+    sub = dict(prep, rays=rays[perm].contiguous(), or_rays=or_rays[perm].contiguous(), rgb=torch.empty((n, 3), device=DEV),
+               depth=torch.empty((n,), device=DEV))
+    rp, dp = R.render_prepared(sub)
+    assert torch.equal(rp, rgb[perm]) and torch.equal(dp, dmap[perm])
+
+
 def test_cuda_graph_replay(ops):
     """One pn_render_rays pass (7 kernels on the tensor-core tier) is capturable in a CUDA graph once the context's scratch has
     reached its high-water mark (no allocation, no synchronisation inside): replays are bit-identical to the eager pass."""
