@@ -79,7 +79,9 @@ int pn_ctx_load_nerf_classic(pn_ctx_t* ctx, const int* in_dims, const int* out_d
  * pn_ctx_profile_read synchronises on the last recorded event, writes up to max_frames rows of
  * PN_N_STAGES per-kernel durations in ms (oldest first), returns the number of rows and clears the ring.
  * Stage order: sampler MLP, sort+lift, refine-Pluecker, project+gather, refine MLP, interval refine,
- * encode+NeRF MLP, composite.  (The reference times whole render() calls only, trt.py:327-332.) */
+ * encode+NeRF MLP (incl. its view-direction pre-pass), composite.  On the PN_PREC_BF16 tier stages 2-4 are ONE kernel
+ * (pn_refine_input_f16): its time is reported under project+gather and the other two read ~0.
+ * (The reference times whole render() calls only, trt.py:327-332.) */
 #define PN_N_STAGES      8
 #define PN_PROFILE_RING  256
 int pn_ctx_profile(pn_ctx_t* ctx, int enable);
