@@ -140,6 +140,19 @@ int pn_sort_lift(const float* heads, int head_stride, const float* rays, int ray
 int pn_warp(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,
             int64_t ro_bstride, const float* w2c, int64_t N, float* out, int32_t* x0y0, pn_stream_t stream);
 
+/* Stage-2 TRAINING warp inverse_warp_rod1_rt2_coords(img, depth, ro1, rd1, c2w2, intrinsics, intrinsics_inv, scale=1,
+ * padding_mode='zeros') (iw.py:515-581): like pn_warp but the source camera pose c2w2 [B,3,4] is inverted in the kernel, the
+ * projection divides by |z| + 1e-8 and out-of-range normalised coordinates are pushed out of the image.  ro1, rd1 [*,3,N]
+ * (batch stride ro_bstride, 0 for repeated views); intrinsics [B,3,3] (intrinsics_inv is unused by the reference too). */
+int pn_warp_train(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,
+                  int64_t ro_bstride, const float* c2w2, const float* intrinsics, int64_t N, float* out, int32_t* x0y0,
+                  pn_stream_t stream);
+
+/* refine2.py:616-626: per-ray choice of NN source views (ref_nos [N,NN] int32) out of k_ref warped ones (warps [k_ref*S,3,N]),
+ * warps that fell outside their source image replaced by the mean over the ray's valid views -> epi_features [N, 3*S*NN]. */
+int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, float* epi,
+                          pn_stream_t stream);
+
 /* Pack NN reference views [NN,H,W,3] (render_kwargs['images'][ref_nos], trt.py:286) into 16-byte RGBA fp32
  * texels [NN,H,W,4] so that one bilinear tap is one 128-bit load. */
 int pn_pack_images(const float* images_hwc, int NN, int H, int W, float* texels, pn_stream_t stream);

@@ -412,3 +412,54 @@ def stage1_forward(weights, rays, mm_input, n_mult, S=8):
     raw = run_network(weights["network_fine_state_dict"], q, viewdirs)
     rgb, dmap, acc = raw2outputs_stage1(raw, z, rays_d)
     return dict(depth=depth, z=z, query=q, raw=raw, rgb_map=rgb, depth_map=dmap, acc_map=acc)
+
+
+# ----------------------------------------------------------------------------- stage-2 training warp
+def warp_train(img, depth, ro1, rd1, c2w2, intrinsics):
+    """inverse_warp.py:515-581 ``inverse_warp_rod1_rt2_coords`` (scale = 1, padding_mode = 'zeros'), restated op for op.
+
+    img [B,C,H,W]; depth [B,N] (the reference's [B,H,W] flattened); ro1, rd1 [B,3,N]; c2w2 [B,3,4]; intrinsics [B,3,3].
+    Unlike the infer variant (iw.py:584-619) this one inverts the camera pose itself and divides by |z| + 1e-8.
+    torch.bmm on CPU: [B,3,3]x[B,3,N] is a sequential FMA chain over k (0 mismatches on 480 k elements), the [B,3,3]x[B,3,1]
+    product of the translation is plain multiply-adds.  Returns (projected [B,C,N], X_norm, Y_norm, x0, y0)."""
+    B, C, H, W = img.shape
+    R2 = c2w2[:, :, 0:3]
+    t2 = c2w2[:, :, 3, None]
+    R2_ = torch.transpose(R2, 2, 1)
+    t2_ = -((R2_[:, :, 0:1] * t2[:, 0:1] + R2_[:, :, 1:2] * t2[:, 1:2]) + R2_[:, :, 2:3] * t2[:, 2:3])      # -bmm(R2_, t2), :536
+
+    def bmm_k3(M, w):
+        acc = M[:, :, 0:1] * w[:, 0:1, :]
+        for k in (1, 2):
+            acc = (M[:, :, k:k + 1].double() * w[:, k:k + 1, :].double() + acc.double()).float()
+        return acc
+    w = ro1 + rd1 * depth.view(B, 1, -1)                       # :539
+    c2 = bmm_k3(R2_, w) + t2_                                  # :542
+    z = torch.abs(c2[:, 2, None, :])                           # :546
+    c2_ = c2 / (z + 1e-8)
+    c2_[:, 2, :] = 1
+    c2_[:, 1, :] *= -1
+    p2 = bmm_k3(intrinsics, c2_)                               # :550
+    X, Y = p2[:, 0], p2[:, 1]
+    X_norm = 2 * X / (W - 1) - 1                               # :555-556
+    Y_norm = 2 * Y / (H - 1) - 1
+    X_norm = torch.where((X_norm > 1) | (X_norm < -1), torch.full_like(X_norm, 2.0), X_norm)      # :561-565
+    Y_norm = torch.where((Y_norm > 1) | (Y_norm < -1), torch.full_like(Y_norm, 2.0), Y_norm)
+    out, ix, iy, x0, y0 = grid_sample_bilinear_zeros(img, X_norm, Y_norm)                           # :578-579
+    return out, X_norm, Y_norm, x0, y0
+
+
+def epi_features_train(warps, ref_nos, S):
+    """run_S_eS_eN_alter_base_refine2.py:616-626: per ray pick its num_neighbor source views out of the k_ref warped ones,
+    replace warps that fell outside their source image (all three channels zero) by the mean over the ray's valid views,
+    and lay the features out as [N, 3*S*NN] (feature index (k*S+s)*3+ch).  warps [k_ref*S, 3, N], ref_nos [N, NN] int64."""
+    N = warps.shape[-1]
+    k_ref = warps.shape[0] // S
+    NN = ref_nos.shape[1]
+    warps_flat = warps.clone().view(1, k_ref, S, 3, 1, N)
+    rays_valid_id = ref_nos.transpose(0, 1)[None, :, None, None, None].repeat(1, 1, S, 3, 1, 1)
+    valid_warps_flat = torch.gather(warps_flat, dim=1, index=rays_valid_id.long())
+    valid_warp = (torch.sum(valid_warps_flat, 3, True) > 0).type_as(warps).repeat(1, 1, 1, 3, 1, 1)
+    mean_sample_warp = torch.sum(valid_warp * valid_warps_flat, 1, True) / (torch.sum(valid_warp, 1, True) + 1e-6)
+    valid_warps_flat = valid_warps_flat * valid_warp + mean_sample_warp * (1 - valid_warp)
+    return (valid_warps_flat.view(S * NN, 3, N).permute(2, 0, 1)).reshape(-1, 3 * S * NN)

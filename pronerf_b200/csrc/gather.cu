@@ -272,6 +272,91 @@ warp_kernel(const float* __restrict__ img, int B, int C, int H, int W, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage-2 TRAINING warp (inverse_warp.py:515-581, inverse_warp_rod1_rt2_coords; scale = 1, zeros padding): the source pose is
+// inverted here (R' w - R' t), the projection divides by |z| + 1e-8 and flips y, pixels whose normalised coordinate leaves
+// [-1, 1] are pushed out of the image before grid_sample.  Op order as PyTorch executes it on CPU (oracle.warp_train):
+//   t_r = -((R[0][r] t0 + R[1][r] t1) + R[2][r] t2)              (plain multiply-adds: a [3,3]x[3,1] product)
+//   c_r = fma(R[2][r], w2, fma(R[1][r], w1, R[0][r] w0)) + t_r   (FMA chain over k)
+//   c_  = c / (|c_z| + 1e-8), c__z = 1, c__y = -c__y;  p = K c_  (FMA chain);  X = p_0, Y = p_1
+__global__ void __launch_bounds__(256)
+warp_train_kernel(const float* __restrict__ img, int B, int C, int H, int W, const float* __restrict__ depth,
+                  const float* __restrict__ ro1, const float* __restrict__ rd1, int64_t ro_bstride, const float* __restrict__ c2w,
+                  const float* __restrict__ Kmat, int64_t N, float* __restrict__ out, int32_t* __restrict__ x0y0) {
+  int b = blockIdx.y;
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* ro = ro1 + b * ro_bstride;
+  const float* rd = rd1 + b * ro_bstride;
+  const float* P = c2w + b * 12;      // [3][4]: R = P[r][0..2], t = P[r][3]
+  const float* Kb = Kmat + b * 9;
+  float d = depth[(int64_t)b * N + n];
+  float w[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) w[i] = __fadd_rn(ro[i * N + n], __fmul_rn(rd[i * N + n], d));
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float t = -__fadd_rn(__fadd_rn(__fmul_rn(P[0 * 4 + r], P[0 * 4 + 3]), __fmul_rn(P[1 * 4 + r], P[1 * 4 + 3])), __fmul_rn(P[2 * 4 + r], P[2 * 4 + 3]));
+    float acc = __fmaf_rn(P[2 * 4 + r], w[2], __fmaf_rn(P[1 * 4 + r], w[1], __fmul_rn(P[0 * 4 + r], w[0])));
+    c[r] = __fadd_rn(acc, t);
+  }
+  float z = __fadd_rn(fabsf(c[2]), 1e-8f);
+  float cx = __fdiv_rn(c[0], z), cy = -__fdiv_rn(c[1], z), cz = 1.f;
+  float X = __fmaf_rn(Kb[2], cz, __fmaf_rn(Kb[1], cy, __fmul_rn(Kb[0], cx)));
+  float Y = __fmaf_rn(Kb[5], cz, __fmaf_rn(Kb[4], cy, __fmul_rn(Kb[3], cx)));
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  float Xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, X), wm1), 1.f);
+  float Yn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, Y), hm1), 1.f);
+  if (Xn > 1.f || Xn < -1.f) Xn = 2.f;            // iw.py:561-565 (NaN compares false and stays NaN, like the reference)
+  if (Yn > 1.f || Yn < -1.f) Yn = 2.f;
+  Tap tp;
+  tp.ix = __fmul_rn(__fadd_rn(Xn, 1.f), wm1 / 2.f);
+  tp.iy = __fmul_rn(__fadd_rn(Yn, 1.f), hm1 / 2.f);
+  tp.x0f = floorf(tp.ix);
+  tp.y0f = floorf(tp.iy);
+  Bilin bl = bilinear_setup(tp, W, H);
+  bool v00 = bl.vx0 && bl.vy0, v01 = bl.vx1 && bl.vy0, v10 = bl.vx0 && bl.vy1, v11 = bl.vx1 && bl.vy1;
+  for (int ch = 0; ch < C; ++ch) {
+    const float* pl = img + ((int64_t)b * C + ch) * H * W + (int64_t)bl.y0 * W + bl.x0;
+    float a = 0.f;
+    a += v00 ? __ldg(pl) * bl.nw : 0.f;
+    a += v01 ? __ldg(pl + 1) * bl.ne : 0.f;
+    a += v10 ? __ldg(pl + W) * bl.sw : 0.f;
+    a += v11 ? __ldg(pl + W + 1) * bl.se : 0.f;
+    out[((int64_t)b * C + ch) * N + n] = a;
+  }
+  if (x0y0) {
+    x0y0[((int64_t)b * N + n) * 2] = clamp_index(tp.x0f);
+    x0y0[((int64_t)b * N + n) * 2 + 1] = clamp_index(tp.y0f);
+  }
+}
+
+// refine2.py:616-626: per ray gather its NN source views out of the k_ref warped ones, replace warps that fell outside their
+// source image (channel sum <= 0) by the mean over the ray's valid views, write epi_features [N, 3*S*NN].
+// One thread per (ray, sample).  warps [k_ref*S][3][N]; ref_nos [N][NN] int32.
+__global__ void epi_features_train_kernel(const float* __restrict__ warps, const int32_t* __restrict__ ref_nos, int k_ref, int NN,
+                                          int S, int64_t N, float* __restrict__ epi) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * S) return;
+  int64_t n = t / S;
+  int s = (int)(t - n * S);
+  float sum[3] = {0.f, 0.f, 0.f}, cnt = 0.f;
+  float v[8][3];
+  bool ok[8];
+  for (int k = 0; k < NN; ++k) {
+    int id = ref_nos[n * NN + k];
+    id = id < 0 ? 0 : (id >= k_ref ? k_ref - 1 : id);
+    const float* src = warps + ((int64_t)(id * S + s) * 3) * N + n;
+    v[k][0] = src[0]; v[k][1] = src[N]; v[k][2] = src[2 * N];
+    ok[k] = (v[k][0] + v[k][1]) + v[k][2] > 0.f;                     // torch.sum over the channel dim
+    if (ok[k]) { sum[0] += v[k][0]; sum[1] += v[k][1]; sum[2] += v[k][2]; cnt += 1.f; }
+  }
+  const float den = cnt + 1e-6f;
+  float* o = epi + n * (3 * S * NN);
+  for (int k = 0; k < NN; ++k)
+    for (int c = 0; c < 3; ++c) o[(k * S + s) * 3 + c] = ok[k] ? v[k][c] : sum[c] / den;
+}
+
 // tex_index_host: [n_views][NN] ints (NULL = identity for every view); project_mat: device [n_views][NN][12]
 int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
                             const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,
@@ -343,6 +428,28 @@ int pn_refine_input_f16(const float* heads, int head_stride, const float* rays, 
                         pn_stream_t stream) {
   return launch_refine_input_f16(heads, head_stride, rays, or_rays, ray_stride, texels, tex_index_host, 1, N, NN, H, W,
                                  project_mat, N, S, depth, add, mul, refine_in_f16, x0y0, as_stream(stream));
+}
+
+int pn_warp_train(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,
+                  int64_t ro_bstride, const float* c2w2, const float* intrinsics, int64_t N, float* out, int32_t* x0y0,
+                  pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(img && depth && ro1 && rd1 && c2w2 && intrinsics && out, "pn_warp_train: null pointer");
+  PN_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && H >= 2 && W >= 2 && N >= 0 && ro_bstride >= 0,
+             "pn_warp_train: bad shape (B=%d C=%d H=%d W=%d)", B, C, H, W);
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
+  warp_train_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, B, C, H, W, depth, ro1, rd1, ro_bstride, c2w2, intrinsics, N, out, x0y0);
+  PN_LAUNCH_OK("pn_warp_train");
+  return PN_OK;
+}
+
+int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, float* epi,
+                          pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(warps && ref_nos && epi && k_ref >= 1 && NN >= 1 && NN <= 8 && S >= 1 && N >= 0, "pn_epi_features_train: bad arguments");
+  epi_features_train_kernel<<<(unsigned)((N * S + 255) / 256), 256, 0, as_stream(stream)>>>(warps, ref_nos, k_ref, NN, S, N, epi);
+  PN_LAUNCH_OK("pn_epi_features_train");
+  return PN_OK;
 }
 
 int pn_warp(const float* img, int B, int C, int H, int W, const float* depth, const float* ro1, const float* rd1,

@@ -331,6 +331,47 @@ def warp(img, depth, ro1, rd1, w2c, want_index: bool = False):
     return (out, idx) if want_index else out
 
 
+def warp_train(img, depth, ro1, rd1, c2w2, intrinsics, want_index: bool = False):
+    """inverse_warp_rod1_rt2_coords core (iw.py:515-581, scale 1, zeros padding) -> projected [B,C,N] (+ int32 [B,N,2])."""
+    img, c2w2, intrinsics = as_f32c(img), as_f32c(c2w2), as_f32c(intrinsics)
+    B, Cc, H, W = img.shape
+    depth = as_f32c(depth).reshape(B, -1)
+    N = depth.shape[1]
+
+    def base(t):
+        if t.dim() == 3 and t.shape[0] == B and t.stride(0) == 0:
+            return as_f32c(t[0]), 0
+        if t.dim() == 3 and t.shape[0] == 1:
+            return as_f32c(t[0]), 0
+        return as_f32c(t), 3 * N
+    ro, so = base(ro1)
+    rd, sd = base(rd1)
+    if so != sd:
+        ro, so = (ro.expand(B, 3, N).contiguous(), 3 * N) if so == 0 else (ro, so)
+        rd, sd = (rd.expand(B, 3, N).contiguous(), 3 * N) if sd == 0 else (rd, sd)
+    out = _empty((B, Cc, N), img)
+    idx = _empty((B, N, 2), img, torch.int32) if want_index else None
+    with _cuda_guard(img):
+        check(lib().pn_warp_train(dptr(img, "img"), B, Cc, H, W, dptr(depth, "depth"), dptr(ro, "ro1"), dptr(rd, "rd1"), so,
+                                  dptr(c2w2, "c2w2"), dptr(intrinsics, "intrinsics"), N, dptr(out),
+                                  idx.data_ptr() if want_index else None, stream_ptr(img.device)), "pn_warp_train")
+    return (out, idx) if want_index else out
+
+
+def epi_features_train(warps, ref_nos, S: int):
+    """refine2.py:616-626: warps [k_ref*S,3,N], ref_nos [N,NN] -> epi_features [N, 3*S*NN] with the masked mean fill."""
+    warps = as_f32c(warps).reshape(warps.shape[0], 3, -1)
+    N = warps.shape[-1]
+    k_ref = warps.shape[0] // S
+    rn = ref_nos.to(torch.int32).contiguous()
+    NN = rn.shape[1]
+    epi = _empty((N, 3 * S * NN), warps)
+    with _cuda_guard(warps):
+        check(lib().pn_epi_features_train(dptr(warps, "warps"), dptr(rn, "ref_nos", torch.int32), k_ref, NN, S, N, dptr(epi),
+                                          stream_ptr(warps.device)), "pn_epi_features_train")
+    return epi
+
+
 def pack_images(images_hwc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[NN,H,W,3] fp32 -> RGBA fp32 texels [NN,H,W,4] (one 128-bit load per bilinear tap)."""
     im = as_f32c(images_hwc)

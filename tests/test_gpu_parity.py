@@ -515,6 +515,34 @@ def test_stage1_style_forward(ops, n_mult):
         assert torch.isfinite(rgb16).all() and psnr(rgb16.cpu().numpy(), ref["rgb_map"].numpy()) >= 38.0
 
 
+def test_training_warp_and_mean_fill(ops):
+    """the stage-2 training warp (iw.py:515-581) and the masked mean fill of its features (refine2.py:616-626):
+    output vs the reference's own function (<= 2e-6), floor indices bit-exact vs the oracle, features vs the oracle."""
+    from pronerf_b200.inverse_warp import inverse_warp_rod1_rt2_coords
+    from tests.conftest import load_golden
+    g = load_golden("warp_train.npz")
+    img, depth, ro1, rd1, c2w2, K = (T(g[k]) for k in ("img", "depth", "ro1", "rd1", "c2w2", "K"))
+    B, N = depth.shape[0], depth.shape[-1]
+    out, none = inverse_warp_rod1_rt2_coords(img.to(DEV), depth.to(DEV), ro1.to(DEV), rd1.to(DEV), c2w2.to(DEV), K.to(DEV),
+                                             torch.inverse(K).to(DEV), padding_mode='zeros')
+    assert none is None and tuple(out.shape) == tuple(g["out"].shape)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], atol=2e-6, rtol=0)                      # the reference's own output
+    ref_out, _, _, x0, y0 = O.warp_train(img, depth.reshape(B, -1), ro1, rd1, c2w2, K)
+    warped, idx = ops.warp_train(img.to(DEV), depth.reshape(B, -1).to(DEV), ro1.to(DEV), rd1.to(DEV), c2w2.to(DEV), K.to(DEV), want_index=True)
+    idx = idx.cpu().long()
+    big = 2 ** 30
+    assert torch.equal(idx[..., 0], x0.clamp(-big, big)) and torch.equal(idx[..., 1], y0.clamp(-big, big))
+    # stride-0 expanded rays (what refine2.py:606-607 builds with .repeat) == materialised ones
+    out_e = ops.warp_train(img.to(DEV), depth.reshape(B, -1).to(DEV), ro1[:1].to(DEV).expand(B, -1, -1), rd1[:1].to(DEV).expand(B, -1, -1),
+                           c2w2.to(DEV), K.to(DEV))
+    assert torch.equal(out_e, warped)
+    S, k_ref = 4, 6
+    gen = torch.Generator().manual_seed(3)
+    ref_nos = torch.stack([torch.randperm(k_ref, generator=gen)[:4].sort()[0] for _ in range(N)], 0)
+    epi = ops.epi_features_train(warped, ref_nos.to(DEV), S)
+    np.testing.assert_allclose(epi.cpu().numpy(), O.epi_features_train(ref_out, ref_nos, S).numpy(), atol=2e-6, rtol=0)
+
+
 # ================================================================================================
 # bf16 tensor-core tier (tcgen05): judged by error statistics and delta-PSNR, not max-abs 1e-3
 # ================================================================================================

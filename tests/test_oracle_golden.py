@@ -134,3 +134,26 @@ def test_nerf_classic_against_reference():
         sd = synth.make_nerf_classic_weights(seed=0, calibrated=cal)
         raw = O.run_network(sd, pts, vd)
         np.testing.assert_allclose(raw.reshape(-1, 4).numpy(), g[f"{tag}_raw"], atol=2e-6 if not cal else 2e-4, rtol=1e-6)
+
+
+def test_training_warp_against_reference():
+    """SURVEY 8 (f4): oracle.warp_train vs the reference's own inverse_warp_rod1_rt2_coords (tests/golden/warp_train.npz);
+    the masked mean fill of refine2.py:616-624 keeps valid warps and fills the others with the mean over the ray's valid views."""
+    from tests.conftest import load_golden
+    g = load_golden("warp_train.npz")
+    img, depth, ro1, rd1, c2w2, K = (T(g[k]) for k in ("img", "depth", "ro1", "rd1", "c2w2", "K"))
+    out, Xn, Yn, x0, y0 = O.warp_train(img, depth.reshape(depth.shape[0], -1), ro1, rd1, c2w2, K)
+    want = g["out"].reshape(out.shape)
+    np.testing.assert_allclose(out.numpy(), want, atol=1e-6, rtol=0)        # (the bilinear blend may differ by an fp32 rounding)
+    assert float(((Xn == 2) | (Xn.abs() <= 1)).float().mean()) == 1.0
+    S, k_ref, N = 4, 6, out.shape[-1]
+    gen = torch.Generator().manual_seed(3)
+    ref_nos = torch.stack([torch.randperm(k_ref, generator=gen)[:4].sort()[0] for _ in range(N)], 0)
+    epi = O.epi_features_train(out, ref_nos, S)
+    assert epi.shape == (N, 3 * S * 4)
+    picked = torch.gather(out.view(k_ref, S, 3, N), 0, ref_nos.t()[:, None, None, :].expand(-1, S, 3, -1))      # [NN,S,3,N]
+    valid = picked.sum(2, keepdim=True) > 0
+    got = epi.view(N, 4, S, 3).permute(1, 2, 3, 0)
+    assert torch.equal(got[valid.expand_as(got)], picked[valid.expand_as(picked)])                            # valid warps untouched
+    mean = (picked * valid).sum(0, keepdim=True) / (valid.float().sum(0, keepdim=True) + 1e-6)
+    assert torch.allclose(got[~valid.expand_as(got)], mean.expand_as(got)[~valid.expand_as(got)], atol=1e-6)
