@@ -463,3 +463,38 @@ def epi_features_train(warps, ref_nos, S):
     mean_sample_warp = torch.sum(valid_warp * valid_warps_flat, 1, True) / (torch.sum(valid_warp, 1, True) + 1e-6)
     valid_warps_flat = valid_warps_flat * valid_warp + mean_sample_warp * (1 - valid_warp)
     return (valid_warps_flat.view(S * NN, 3, N).permute(2, 0, 1)).reshape(-1, 3 * S * NN)
+
+
+def stage2_eval_forward(weights, rays, or_rays, images_train, poses_train, K, target_pose, S=8, P=48, NN=4):
+    """run_S_eS_eN_alter_base_refine2.py:525-680 ``render_rays`` in evaluation mode (randomize=False, train_nerf=False):
+    sampler -> sort/lift (eps 1e-5, :570) -> TRAINING warp into all k_ref training views (:603-614) -> per-ray nearest NN views
+    by translation distance to the target pose (:587-600) + masked mean fill (:616-624) -> refine net -> interval refinement +
+    offsets (:640-668) -> classic NeRF (run_network with concatenated encodings) -> raw2outputs with the density heads, no
+    clamp (:475-522).  images_train [k_ref,H,W,3]; poses_train [k_ref,3,4]; K [3,3]; target_pose [3,4]."""
+    rays_o, rays_d, near, far, viewdirs = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8], rays[:, 8:11]
+    N = rays.shape[0]
+    pts, _ = query_points_linear(rays_o, rays_d, 0., 1., P)
+    mm_input = pluecker(pts, rays_d[:, None, :].expand(-1, P, -1)).reshape(N, 6 * P)
+    mm_rgb, add, mul, d = sampler_forward(weights["mmr_network_fn_state_dict"], mm_input, S)
+    depth, add, mul, _, depth3d = sort_lift(d, add, mul, near, far)
+    images_train, poses_train = _t(images_train), _t(poses_train)
+    k_ref = images_train.shape[0]
+    target = _t(target_pose)[None].repeat(N, 1, 1)
+    rel = torch.sum((target[:, None, :, 3] - poses_train[:, :, 3]) ** 2, 2) ** (1 / 2)
+    _, rel_idx = torch.sort(rel, dim=1)
+    ref_nos = rel_idx[:, 0:NN]
+    ref_rgb = torch.repeat_interleave(images_train.permute(0, 3, 1, 2), repeats=S, dim=0)
+    ref_pose = torch.repeat_interleave(poses_train, repeats=S, dim=0)
+    ro1 = or_rays[:, 0:3].t()[None].repeat(S * k_ref, 1, 1)
+    rd1 = or_rays[:, 3:6].t()[None].repeat(S * k_ref, 1, 1)
+    Kb = _t(np.asarray(K, dtype=np.float32))[None].repeat(S * k_ref, 1, 1)
+    depths = depth3d[None, None].repeat(k_ref, 1, 1, 1).permute(0, 3, 1, 2).reshape(-1, N)
+    warps, _, _, x0, y0 = warp_train(ref_rgb, depths, ro1, rd1, ref_pose, Kb)
+    epi = epi_features_train(warps, ref_nos, S)
+    rin = refine_input(rays_o, rays_d, depth, epi)
+    rdepth, rrgb, off = refine_forward(weights["refine_net_state_dict"], rin, S)
+    z, q = interval_refine(rays_o, rays_d, depth, near, far, rdepth, off)
+    raw = run_network(weights["network_fine_state_dict"], q, viewdirs)
+    rgb_map, _, _, _, depth_map = raw2outputs(raw, z, rays_d, add, mul)
+    return dict(rgb_map0=rrgb, rgb_map1=rgb_map, depth_map=depth_map, mm_rgb=mm_rgb, z_vals=z.mean(-1), z_vals0=depth.mean(-1),
+                ref_nos=ref_nos, depth=depth, depth3d=depth3d, warps=warps, epi=epi, x0=x0, y0=y0, z=z, query=q, raw=raw)

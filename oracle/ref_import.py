@@ -46,3 +46,16 @@ def load():
     import inverse_warp as IW         # noqa: E402
     _cache["mods"] = (ref, H, IW)
     return _cache["mods"]
+
+
+def load_refine2():
+    """The stage-2 training script (run_S_eS_eN_alter_base_refine2.py), unmodified, with the same stub modules."""
+    if "refine2" in _cache:
+        return _cache["refine2"]
+    load()                                                    # stubs + sys.path
+    sys.modules["load_llff"].load_llff_data = None
+    spec = importlib.util.spec_from_file_location("pronerf_ref_refine2", os.path.join(REF_ROOT, "run_S_eS_eN_alter_base_refine2.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _cache["refine2"] = mod
+    return mod

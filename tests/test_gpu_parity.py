@@ -543,6 +543,35 @@ def test_training_warp_and_mean_fill(ops):
     np.testing.assert_allclose(epi.cpu().numpy(), O.epi_features_train(ref_out, ref_nos, S).numpy(), atol=2e-6, rtol=0)
 
 
+def test_stage2_eval_forward(ops):
+    """the stage-2 evaluation forward (refine2.py:525-680, randomize=False: training warp into all training views,
+    per-ray nearest views + masked mean fill, classic NeRF) on the CUDA kernels against the REFERENCE'S OWN render_rays output
+    (tests/golden/stage2_eval.npz): fp32 tier <= 1e-3 on every returned map; tensor-core tier by PSNR."""
+    from pronerf_b200.engine import Renderer
+    from pronerf_b200.stage2 import stage2_eval_forward
+    from tests.conftest import load_golden
+    from tests.util import psnr
+    g = load_golden("stage2_eval.npz")
+    scene = synth.make_small_scene(H=12, W=16)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    sd["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    images_train = synth.make_images(len(scene.poses), scene.H, scene.W, scene.seed, views=[int(i) for i in scene.i_train])
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    rays, or_rays = pv["rays"].to(DEV), pv["or_rays"].to(DEV)
+    for prec in ("fp32", "bf16"):
+        if prec == "bf16" and not ops.bf16_tier_available():
+            continue
+        R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision=prec, device=DEV)
+        r = stage2_eval_forward(R.ctx, rays, or_rays, images_train, scene.poses[scene.i_train], scene.K, g["c2w"], precision=prec)
+        if prec == "fp32":
+            for k in ("z_vals0", "mm_rgb", "rgb_map0", "z_vals", "rgb_map1", "depth_map"):
+                np.testing.assert_allclose(r[k].cpu().numpy(), g[k], atol=1e-3, rtol=0, err_msg=k)
+        else:
+            p = psnr(r["rgb_map1"].cpu().numpy(), g["rgb_map1"])
+            print(f"stage-2 eval forward, tensor-core tier vs the reference: {p:.1f} dB")
+            assert torch.isfinite(r["rgb_map1"]).all() and p >= 38.0
+
+
 # ================================================================================================
 # bf16 tensor-core tier (tcgen05): judged by error statistics and delta-PSNR, not max-abs 1e-3
 # ================================================================================================

@@ -157,3 +157,23 @@ def test_training_warp_against_reference():
     assert torch.equal(got[valid.expand_as(got)], picked[valid.expand_as(picked)])                            # valid warps untouched
     mean = (picked * valid).sum(0, keepdim=True) / (valid.float().sum(0, keepdim=True) + 1e-6)
     assert torch.allclose(got[~valid.expand_as(got)], mean.expand_as(got)[~valid.expand_as(got)], atol=1e-6)
+
+
+def _stage2_inputs():
+    scene = synth.make_small_scene(H=12, W=16)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    sd["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    images_train = synth.make_images(len(scene.poses), scene.H, scene.W, scene.seed, views=[int(i) for i in scene.i_train])
+    return scene, sd, images_train
+
+
+def test_stage2_eval_forward_against_reference():
+    """the whole stage-2 evaluation forward (refine2.py:525-680, randomize=False) restated from the oracle's
+    stages vs the reference's own render_rays on the same scene and weights (tests/golden/stage2_eval.npz)."""
+    from tests.conftest import load_golden
+    g = load_golden("stage2_eval.npz")
+    scene, sd, images_train = _stage2_inputs()
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    r = O.stage2_eval_forward(sd, pv["rays"], pv["or_rays"], images_train, scene.poses[scene.i_train], scene.K, g["c2w"])
+    for k, tol in (("z_vals0", 1e-6), ("mm_rgb", 1e-6), ("rgb_map0", 1e-5), ("z_vals", 1e-5), ("rgb_map1", 2e-5), ("depth_map", 2e-5)):
+        np.testing.assert_allclose(r[k].numpy(), g[k], atol=tol, rtol=0, err_msg=k)
