@@ -149,9 +149,11 @@ int pn_warp_train(const float* img, int B, int C, int H, int W, const float* dep
                   pn_stream_t stream);
 
 /* refine2.py:616-626: per-ray choice of NN source views (ref_nos [N,NN] int32) out of k_ref warped ones (warps [k_ref*S,3,N]),
- * warps that fell outside their source image replaced by the mean over the ray's valid views -> epi_features [N, 3*S*NN]. */
-int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, float* epi,
-                          pn_stream_t stream);
+ * warps that fell outside their source image replaced by the mean over the ray's valid views -> epi_features [N, 3*S*NN].
+ * sample_major = 0: feature index (k*S+s)*3+ch (stage 2, refine2.py:626, and the infer path); 1: s*(NN*3)+k*3+ch (stage 1,
+ * base.py:664-665). */
+int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, int sample_major,
+                          float* epi, pn_stream_t stream);
 
 /* Pack NN reference views [NN,H,W,3] (render_kwargs['images'][ref_nos], trt.py:286) into 16-byte RGBA fp32
  * texels [NN,H,W,4] so that one bilinear tap is one 128-bit load. */

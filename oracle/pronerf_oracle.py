@@ -449,7 +449,7 @@ def warp_train(img, depth, ro1, rd1, c2w2, intrinsics):
     return out, X_norm, Y_norm, x0, y0
 
 
-def epi_features_train(warps, ref_nos, S):
+def epi_features_train(warps, ref_nos, S, stage1_layout=False):
     """run_S_eS_eN_alter_base_refine2.py:616-626: per ray pick its num_neighbor source views out of the k_ref warped ones,
     replace warps that fell outside their source image (all three channels zero) by the mean over the ray's valid views,
     and lay the features out as [N, 3*S*NN] (feature index (k*S+s)*3+ch).  warps [k_ref*S, 3, N], ref_nos [N, NN] int64."""
@@ -462,6 +462,8 @@ def epi_features_train(warps, ref_nos, S):
     valid_warp = (torch.sum(valid_warps_flat, 3, True) > 0).type_as(warps).repeat(1, 1, 1, 3, 1, 1)
     mean_sample_warp = torch.sum(valid_warp * valid_warps_flat, 1, True) / (torch.sum(valid_warp, 1, True) + 1e-6)
     valid_warps_flat = valid_warps_flat * valid_warp + mean_sample_warp * (1 - valid_warp)
+    if stage1_layout:        # base.py:664-665: sample-major features, index s*(NN*3) + k*3 + ch
+        return (valid_warps_flat.view(NN, S, 3, N).permute(3, 1, 0, 2)).reshape(-1, S * NN * 3)
     return (valid_warps_flat.view(S * NN, 3, N).permute(2, 0, 1)).reshape(-1, 3 * S * NN)
 
 
@@ -498,3 +500,38 @@ def stage2_eval_forward(weights, rays, or_rays, images_train, poses_train, K, ta
     rgb_map, _, _, _, depth_map = raw2outputs(raw, z, rays_d, add, mul)
     return dict(rgb_map0=rrgb, rgb_map1=rgb_map, depth_map=depth_map, mm_rgb=mm_rgb, z_vals=z.mean(-1), z_vals0=depth.mean(-1),
                 ref_nos=ref_nos, depth=depth, depth3d=depth3d, warps=warps, epi=epi, x0=x0, y0=y0, z=z, query=q, raw=raw)
+
+
+def stage1_eval_forward(weights, rays, or_rays, images_train, poses_train, K, target_pose, S=8, P=48, NN=4):
+    """run_S_eS_eN_alter_base.py:554-761 ``render_rays`` in evaluation mode (randomize=False, train_sampler=False): like the
+    stage-2 forward but the depth lift uses eps 1e-6 (:607), the epipolar features are laid out sample-major (:664-665), the
+    learned offsets are NOT applied (:733-734), ``network_fn`` is the classic NeRF, and the compositing clamps raw to +-10 and
+    ignores the sampler's density heads (:751-753).  ``weights['network_fn_state_dict']`` = the classic NeRF."""
+    rays_o, rays_d, near, far, viewdirs = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8], rays[:, 8:11]
+    N = rays.shape[0]
+    pts, _ = query_points_linear(rays_o, rays_d, 0., 1., P)
+    mm_input = pluecker(pts, rays_d[:, None, :].expand(-1, P, -1)).reshape(N, 6 * P)
+    mm_rgb, add, mul, d = sampler_forward(weights["mmr_network_fn_state_dict"], mm_input, S)
+    depth, add, mul, _, _ = sort_lift(d, add, mul, near, far)
+    depth3d = 1 / (1 - depth - 1e-6)                                                            # :607
+    images_train, poses_train = _t(images_train), _t(poses_train)
+    k_ref = images_train.shape[0]
+    target = _t(target_pose)[None].repeat(N, 1, 1)
+    rel = torch.sum((target[:, None, :, 3] - poses_train[:, :, 3]) ** 2, 2) ** (1 / 2)
+    _, rel_idx = torch.sort(rel, dim=1)
+    ref_nos = rel_idx[:, 0:NN]
+    ref_rgb = torch.repeat_interleave(images_train.permute(0, 3, 1, 2), repeats=S, dim=0)
+    ref_pose = torch.repeat_interleave(poses_train, repeats=S, dim=0)
+    ro1 = or_rays[:, 0:3].t()[None].repeat(S * k_ref, 1, 1)
+    rd1 = or_rays[:, 3:6].t()[None].repeat(S * k_ref, 1, 1)
+    Kb = _t(np.asarray(K, dtype=np.float32))[None].repeat(S * k_ref, 1, 1)
+    depths = depth3d[None, None].repeat(k_ref, 1, 1, 1).permute(0, 3, 1, 2).reshape(-1, N)
+    warps, _, _, _, _ = warp_train(ref_rgb, depths, ro1, rd1, ref_pose, Kb)
+    epi = epi_features_train(warps, ref_nos, S, stage1_layout=True)
+    rin = refine_input(rays_o, rays_d, depth, epi)
+    rdepth, rrgb, off = refine_forward(weights["refine_net_state_dict"], rin, S)
+    z, _ = interval_refine(rays_o, rays_d, depth, near, far, rdepth, off)
+    q = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]                           # no offsets (:733)
+    raw = run_network(weights["network_fn_state_dict"], q, viewdirs)
+    rgb_map, depth_map, _ = raw2outputs_stage1(raw, z, rays_d)
+    return dict(rgb_map0=rrgb, rgb_map1=rgb_map, depth_map=depth_map, mm_rgb=mm_rgb, depth_map0=z.mean(-1), z=z, epi=epi, depth=depth)

@@ -59,3 +59,16 @@ def load_refine2():
     spec.loader.exec_module(mod)
     _cache["refine2"] = mod
     return mod
+
+
+def load_base():
+    """The stage-1 training script (run_S_eS_eN_alter_base.py), unmodified, with the same stub modules."""
+    if "base" in _cache:
+        return _cache["base"]
+    load()
+    sys.modules["load_llff"].load_llff_data = None
+    spec = importlib.util.spec_from_file_location("pronerf_ref_base", os.path.join(REF_ROOT, "run_S_eS_eN_alter_base.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _cache["base"] = mod
+    return mod

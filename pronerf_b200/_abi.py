@@ -52,7 +52,7 @@ SIGNATURES = {
     "pn_sort_lift": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pn_warp": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i64, _p, _i64, _p, _p, _p]),
     "pn_warp_train": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p]),
-    "pn_epi_features_train": (_i, [_p, _p, _i, _i, _i, _i64, _p, _p]),
+    "pn_epi_features_train": (_i, [_p, _p, _i, _i, _i, _i64, _i, _p, _p]),
     "pn_pack_images": (_i, [_p, _i, _i, _i, _p, _p]),
     "pn_project_gather": (_i, [_p, C.POINTER(_i), _i, _i, _i, _p, _p, _p, _i, _p, _i64, _i, _p, _i, _i, _p, _p]),
     "pn_refine_input_f16": (_i, [_p, _i, _p, _p, _i, _p, C.POINTER(_i), _i, _i, _i, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),

@@ -335,7 +335,7 @@ warp_train_kernel(const float* __restrict__ img, int B, int C, int H, int W, con
 // source image (channel sum <= 0) by the mean over the ray's valid views, write epi_features [N, 3*S*NN].
 // One thread per (ray, sample).  warps [k_ref*S][3][N]; ref_nos [N][NN] int32.
 __global__ void epi_features_train_kernel(const float* __restrict__ warps, const int32_t* __restrict__ ref_nos, int k_ref, int NN,
-                                          int S, int64_t N, float* __restrict__ epi) {
+                                          int S, int64_t N, int sample_major, float* __restrict__ epi) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * S) return;
   int64_t n = t / S;
@@ -354,7 +354,8 @@ __global__ void epi_features_train_kernel(const float* __restrict__ warps, const
   const float den = cnt + 1e-6f;
   float* o = epi + n * (3 * S * NN);
   for (int k = 0; k < NN; ++k)
-    for (int c = 0; c < 3; ++c) o[(k * S + s) * 3 + c] = ok[k] ? v[k][c] : sum[c] / den;
+    for (int c = 0; c < 3; ++c)      // stage 2 / infer: (k*S + s)*3 + c (refine2.py:626);  stage 1: s*(NN*3) + k*3 + c (base.py:664-665)
+      o[sample_major ? (s * NN + k) * 3 + c : (k * S + s) * 3 + c] = ok[k] ? v[k][c] : sum[c] / den;
 }
 
 // tex_index_host: [n_views][NN] ints (NULL = identity for every view); project_mat: device [n_views][NN][12]
@@ -443,11 +444,11 @@ int pn_warp_train(const float* img, int B, int C, int H, int W, const float* dep
   return PN_OK;
 }
 
-int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, float* epi,
-                          pn_stream_t stream) {
+int pn_epi_features_train(const float* warps, const int32_t* ref_nos, int k_ref, int NN, int S, int64_t N, int sample_major,
+                          float* epi, pn_stream_t stream) {
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(warps && ref_nos && epi && k_ref >= 1 && NN >= 1 && NN <= 8 && S >= 1 && N >= 0, "pn_epi_features_train: bad arguments");
-  epi_features_train_kernel<<<(unsigned)((N * S + 255) / 256), 256, 0, as_stream(stream)>>>(warps, ref_nos, k_ref, NN, S, N, epi);
+  epi_features_train_kernel<<<(unsigned)((N * S + 255) / 256), 256, 0, as_stream(stream)>>>(warps, ref_nos, k_ref, NN, S, N, sample_major, epi);
   PN_LAUNCH_OK("pn_epi_features_train");
   return PN_OK;
 }

@@ -358,8 +358,9 @@ def warp_train(img, depth, ro1, rd1, c2w2, intrinsics, want_index: bool = False)
     return (out, idx) if want_index else out
 
 
-def epi_features_train(warps, ref_nos, S: int):
-    """refine2.py:616-626: warps [k_ref*S,3,N], ref_nos [N,NN] -> epi_features [N, 3*S*NN] with the masked mean fill."""
+def epi_features_train(warps, ref_nos, S: int, sample_major: bool = False):
+    """refine2.py:616-626 / base.py:655-665: warps [k_ref*S,3,N], ref_nos [N,NN] -> epi_features [N, 3*S*NN] with the masked mean
+    fill; ``sample_major`` selects stage 1's feature order."""
     warps = as_f32c(warps).reshape(warps.shape[0], 3, -1)
     N = warps.shape[-1]
     k_ref = warps.shape[0] // S
@@ -367,7 +368,7 @@ def epi_features_train(warps, ref_nos, S: int):
     NN = rn.shape[1]
     epi = _empty((N, 3 * S * NN), warps)
     with _cuda_guard(warps):
-        check(lib().pn_epi_features_train(dptr(warps, "warps"), dptr(rn, "ref_nos", torch.int32), k_ref, NN, S, N, dptr(epi),
+        check(lib().pn_epi_features_train(dptr(warps, "warps"), dptr(rn, "ref_nos", torch.int32), k_ref, NN, S, N, int(sample_major), dptr(epi),
                                           stream_ptr(warps.device)), "pn_epi_features_train")
     return epi
 

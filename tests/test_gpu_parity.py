@@ -545,8 +545,9 @@ def test_training_warp_and_mean_fill(ops):
 
 def test_stage2_eval_forward(ops):
     """the stage-2 evaluation forward (refine2.py:525-680, randomize=False: training warp into all training views,
-    per-ray nearest views + masked mean fill, classic NeRF) on the CUDA kernels against the REFERENCE'S OWN render_rays output
-    (tests/golden/stage2_eval.npz): fp32 tier <= 1e-3 on every returned map; tensor-core tier by PSNR."""
+    per-ray nearest views + masked mean fill, classic NeRF) and the stage-1 one (base.py:554-761: eps 1e-6 lift, sample-major
+    features, no offsets, clamped compositing) on the CUDA kernels against the REFERENCE'S OWN render_rays outputs
+    (tests/golden/stage2_eval.npz, stage1_eval.npz): fp32 tier <= 1e-3 on every returned map; tensor-core tier by PSNR."""
     from pronerf_b200.engine import Renderer
     from pronerf_b200.stage2 import stage2_eval_forward
     from tests.conftest import load_golden
@@ -569,6 +570,21 @@ def test_stage2_eval_forward(ops):
         else:
             p = psnr(r["rgb_map1"].cpu().numpy(), g["rgb_map1"])
             print(f"stage-2 eval forward, tensor-core tier vs the reference: {p:.1f} dB")
+            assert torch.isfinite(r["rgb_map1"]).all() and p >= 38.0
+    # stage 1 (base.py:554-761, randomize=False, train_sampler=False) against ITS reference output
+    from pronerf_b200.stage2 import stage1_eval_forward
+    g1 = load_golden("stage1_eval.npz")
+    for prec in ("fp32", "bf16"):
+        if prec == "bf16" and not ops.bf16_tier_available():
+            continue
+        R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision=prec, device=DEV)
+        r = stage1_eval_forward(R.ctx, rays, or_rays, images_train, scene.poses[scene.i_train], scene.K, g1["c2w"], precision=prec)
+        if prec == "fp32":
+            for k in ("mm_rgb", "rgb_map0", "depth_map0", "rgb_map1", "depth_map"):
+                np.testing.assert_allclose(r[k].cpu().numpy(), g1[k], atol=1e-3, rtol=0, err_msg="stage1 " + k)
+        else:
+            p = psnr(r["rgb_map1"].cpu().numpy(), g1["rgb_map1"])
+            print(f"stage-1 eval forward, tensor-core tier vs the reference: {p:.1f} dB")
             assert torch.isfinite(r["rgb_map1"]).all() and p >= 38.0
 
 

@@ -177,3 +177,16 @@ def test_stage2_eval_forward_against_reference():
     r = O.stage2_eval_forward(sd, pv["rays"], pv["or_rays"], images_train, scene.poses[scene.i_train], scene.K, g["c2w"])
     for k, tol in (("z_vals0", 1e-6), ("mm_rgb", 1e-6), ("rgb_map0", 1e-5), ("z_vals", 1e-5), ("rgb_map1", 2e-5), ("depth_map", 2e-5)):
         np.testing.assert_allclose(r[k].numpy(), g[k], atol=tol, rtol=0, err_msg=k)
+
+
+def test_stage1_eval_forward_against_reference():
+    """the stage-1 evaluation forward (base.py:554-761, randomize=False, train_sampler=False: eps 1e-6 lift,
+    sample-major epipolar features, no offsets, clamped compositing without density heads) vs the reference's own render_rays."""
+    from tests.conftest import load_golden
+    g = load_golden("stage1_eval.npz")
+    scene, sd, images_train = _stage2_inputs()
+    sd = dict(sd, network_fn_state_dict=sd["network_fine_state_dict"])
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    r = O.stage1_eval_forward(sd, pv["rays"], pv["or_rays"], images_train, scene.poses[scene.i_train], scene.K, g["c2w"])
+    for k, tol in (("mm_rgb", 1e-6), ("rgb_map0", 1e-5), ("depth_map0", 1e-5), ("rgb_map1", 2e-5), ("depth_map", 2e-5)):
+        np.testing.assert_allclose(r[k].numpy(), g[k], atol=tol, rtol=0, err_msg=k)
