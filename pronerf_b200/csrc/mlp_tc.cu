@@ -49,15 +49,25 @@ constexpr int RING_SLOT_BYTES = (kHidden / 2) * 128;    // this CTA's half of a 
 constexpr int N_RING = 5;
 constexpr int BIAS_ROWS = 14;                           // 8 layer biases (+ classic NeRF: 3 more, the alpha weights, 2 rows of alpha partial sums)
 constexpr int BIAS_FLOATS = BIAS_ROWS * kHidden;        // 14 KB
+// Output staging (sampler / refine heads): a warp's 32 rows x n_out floats are one contiguous global range, but thread = row,
+// so direct stores scatter 4 bytes over 32 sectors per instruction.  Each ch = 0 warp transposes through a private 2304-byte
+// window (rows_per_pass x n_out floats) and writes 16 bytes per lane.  The window overlays bias rows 8.. (classic NeRF only,
+// whose float4 output needs no staging) and extends past the bias table.
+constexpr int STAGE_BIAS_ROW0 = 8;
+constexpr int STAGE_FLOATS = 576;                       // per warp: 16 rows x 36 floats
+constexpr int STAGE_BYTES = 4 * STAGE_FLOATS * 4;       // 9216
+constexpr int BIAS_REGION = (STAGE_BIAS_ROW0 * kHidden * 4 + STAGE_BYTES > BIAS_FLOATS * 4) ? STAGE_BIAS_ROW0 * kHidden * 4 + STAGE_BYTES : BIAS_FLOATS * 4;
 constexpr int OFF_A = 0;
 constexpr int OFF_RING = OFF_A + 2 * A_SLOT_BYTES;
 constexpr int OFF_BIAS = OFF_RING + N_RING * RING_SLOT_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;
+constexpr int OFF_STAGE = OFF_BIAS + STAGE_BIAS_ROW0 * kHidden * 4;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_REGION;
 // barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2 slots][2 halves], acc_full[2]
 constexpr int N_BARS = 2 * N_RING + 6;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B (swizzle atom)
+static_assert(SMEM_ALLOC <= 232448, "over the 227 KB per-CTA shared-memory limit of sm_100");
 constexpr int N_EPI_WARPS = 8;                          // lane quadrant x column half.  Register budget: the register file is per SM
                                                         // sub-partition (16 K), and with 10 warps one sub-partition holds 3 -> 168 per thread
 constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 320
@@ -105,10 +115,10 @@ struct Params {
   float alpha_bias;
   long long M;
   float* out;
-  int head_lo[4];
-  int head_act[3];
+  float4 head_tab[96];          // output column c: y = x * .w + (.y / (1 + 2^(x * .x)) + .z), x = accumulator + bias (head_coeffs)
   int shift;                    // phases slot 1 runs behind slot 0 (0 = in step)
   int split;                    // 1: hidden epilogues publish their first K block early (two-step operand hand-over)
+  int out_rpp;                  // rows per staging pass of the head output (multiple of 4)
   int* error_flag;
   long long* timeline;          // debug: leader CTA of cluster 0 stamps clock64() of its second iteration
 };
@@ -300,10 +310,23 @@ __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, flo
       : "f"(x0), "f"(x1), "f"(b0), "f"(b1));
 }
 
-__device__ __forceinline__ float head_apply_fast(float v, int kind) {
-  if (kind == HEAD_SIGMOID) return 1.f / (1.f + __expf(-v));
-  if (kind == HEAD_TANH) return tanhf(v);
-  return v;
+// Head activations of the tensor-core tier as one branch-free form: y = c x + (a / (1 + 2^(s x)) + b), per-column
+// coefficients in the kernel parameters (constant-bank operands, no loads):
+//   none: (0, 0, 0, 1)    sigmoid x = 1 / (1 + 2^(-x log2 e)): (-log2 e, 1, 0, 0)    tanh x = 2 sigmoid(2x) - 1: (-2 log2 e, 2, -1, 0)
+// on the SFU (ex2 + rcp, ~1e-6 relative; 2^inf = inf gives 0).  With a run-time `kind` test per column every column was
+// its own basic block (constant loads, compares, branches) and the lone output warp of a scheduler walked ~30 dependent
+// chains one after the other: 8 K cycles per 128-row tile for 27 columns (timeline stamps TL_OUT).
+__device__ __forceinline__ float head_apply_tab(float x, const float4& h) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * h.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(h.w, x, fmaf(h.y, r, h.z));
+}
+static float4 head_coeffs(int kind) {
+  const float l2e = 1.4426950408889634f;
+  if (kind == HEAD_SIGMOID) return make_float4(-l2e, 1.f, 0.f, 0.f);
+  if (kind == HEAD_TANH) return make_float4(-2.f * l2e, 2.f, -1.f, 0.f);
+  return make_float4(0.f, 0.f, 0.f, 1.f);
 }
 
 // The padded frequency encoding gamma_10(x) = [x, sin(2^l x), cos(2^l x)]_{l<10}, 0 (helpers.py:666-671), 64 elements per
@@ -403,6 +426,7 @@ constexpr int TL_EPI = 100;      // epilogue warp 0, phase 2 slot 0: [0] first 6
 constexpr int TL_FACC = 150;     // follower CTA, epilogue warp 0: accumulator-full observed
 constexpr int TL_FARR = 170;     // follower CTA, epilogue warp 0: arrived on operand-ready
 constexpr int TL_SYNC = 140;    // clock64() right after the setup cluster barrier: [0] leader, [1] follower (per-SM clock offset)
+constexpr int TL_OUT = 110;     // epilogue warp 0, output phase, slot t: [6t + 0] body entry, [1] before the accumulator wait, [2] accumulator in registers, [3] next operand stored, [4] outputs stored
 constexpr int TL_N = 208;
 __device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
   if (kTimeline && tl && on) tl[slot] = clock64();
@@ -714,7 +738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     //     stored once the slot's operand buffer is free. ---
     constexpr int kPf = 9;                                 // 128 rows x 144 halves = 2304 chunks = 9 per thread
     const int cpr = p.k0 >> 3;                             // real chunks per row
-    struct Range16 { int c_lo, w, total; };
+    struct Range16 { int c_lo, w, total; uint32_t magic; };   // g / w == (g * magic) >> 20 for g < 128 * w, 2 <= w <= 32
     auto range16 = [&](int kb_lo, int nblk) {
       Range16 R;
       R.c_lo = kb_lo * 8;
@@ -722,31 +746,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       if (c_hi >= cpr) c_hi = (cpr + 1) & ~1;              // last block: pad to a whole K = 16 step with zero chunks
       R.w = c_hi - R.c_lo;
       R.total = TILE_M * R.w;
+      R.magic = ((1u << 20) + (uint32_t)R.w - 1u) / (uint32_t)R.w;
       return R;
     };
-    auto fetch16 = [&](long long tile, const Range16& R, int g, uint4& v) {
+    // a tile's rows: first chunk in global memory and how many of its 128 rows exist (32-bit math per chunk from here on)
+    struct Tile16 { const uint4* src; int rows; };
+    auto tile16 = [&](long long tile) {
+      Tile16 T;
+      const long long row0 = tile * PAIR_M + (long long)rank * TILE_M;
+      const long long left = p.M - row0;
+      T.rows = left >= TILE_M ? TILE_M : (left > 0 ? (int)left : 0);
+      T.src = reinterpret_cast<const uint4*>(p.in0) + row0 * cpr;
+      return T;
+    };
+    auto fetch16 = [&](const Tile16& T, const Range16& R, int g, uint4& v) {
       v = make_uint4(0u, 0u, 0u, 0u);
       if (g < R.total) {
-        const int row = g / R.w, c = R.c_lo + (g - row * R.w);
-        const long long grow = tile * PAIR_M + (long long)rank * TILE_M + row;
-        if (grow < p.M && c < cpr) v = __ldg(reinterpret_cast<const uint4*>(p.in0) + grow * cpr + c);
+        const int row = (int)(((uint32_t)g * R.magic) >> 20), c = R.c_lo + (g - row * R.w);
+        if (row < T.rows && c < cpr) v = __ldg(T.src + (row * cpr + c));
       }
     };
     auto store16 = [&](int t, const Range16& R, int g, const uint4& v) {
       if (g < R.total) {
-        const int row = g / R.w, cc = g - row * R.w;       // chunk within the range: block cc >> 3, chunk cc & 7
+        const int row = (int)(((uint32_t)g * R.magic) >> 20), cc = g - row * R.w;       // chunk within the range: block cc >> 3, chunk cc & 7
         st_shared_v4(a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7), v.x, v.y, v.z, v.w);
       }
     };
     auto prefetch16 = [&](long long tile, int kb_lo, int nblk, uint4* pf) {
       const Range16 R = range16(kb_lo, nblk);
+      const Tile16 T = tile16(tile);
 #pragma unroll
-      for (int u = 0; u < kPf; ++u) fetch16(tile, R, (int)threadIdx.x + u * (N_EPI_WARPS * 32), pf[u]);
+      for (int u = 0; u < kPf; ++u) fetch16(T, R, (int)threadIdx.x + u * (N_EPI_WARPS * 32), pf[u]);
     };
     // store the prefetched chunks, then load + store whatever the range holds beyond them
     auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk, const uint4* pf, bool have_pf) {
       const Range16 R = range16(kb_lo, nblk);
       constexpr int NT = N_EPI_WARPS * 32;
+      const Tile16 T = tile16(tile);
       if (have_pf) {
 #pragma unroll
         for (int u = 0; u < kPf; ++u) store16(t, R, (int)threadIdx.x + u * NT, pf[u]);
@@ -754,7 +790,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       for (int g0 = have_pf ? kPf * NT : 0; g0 < R.total; g0 += 4 * NT) {
         uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) fetch16(tile, R, g0 + (int)threadIdx.x + u * NT, v[u]);
+        for (int u = 0; u < 4; ++u) fetch16(T, R, g0 + (int)threadIdx.x + u * NT, v[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) store16(t, R, g0 + (int)threadIdx.x + u * NT, v[u]);
       }
@@ -977,6 +1013,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       for (int t = 0; t < nslots; ++t) {
         const long long tile = T0 + t;
         const bool has_next = tile + stride < n_pairs;
+        const bool tl_o = tl_it && ew == 0;
+        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 0);
         uint32_t pre[16];
         if (kCompute && has_next) {                            // overlaps the wait below
           float xin[kXin];
@@ -986,6 +1024,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         }
         uint4 pf[kPf];
         if (MODE == IN_LOAD16 && has_next) prefetch16(tile + stride, 0, kb_first, pf);   // in flight across the wait below
+        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 1);
         mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
         acc_par ^= 1u << t;
         tc_fence_after();
@@ -1003,40 +1042,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           if (n_pad_out > c0 + 32) tmem_ld16(taddr + c0 + 32, v + 32);
           tmem_wait_ld();
         }
+        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 2);
         if (has_next) {
           if (kCompute) store_pre(t, pre);
           else if (MODE == IN_LOAD16) load_input16(tile + stride, t, 0, kb_first, pf, true);
           else load_input(tile + stride, t, 0, kb_first);
         }
+        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 3);
         publish(t, 3);
         tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
         tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
         tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
-        if (c0 < n_pad_out && live) {
-          const float* bo = s_bias + layer_out * kHidden + c0;
-          if (kClassic) {
+        if (kClassic) {
+          if (ch == 0 && live) {
             // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
+            const float* bo = s_bias + layer_out * kHidden;
             const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
             *reinterpret_cast<float4*>(p.out + row * 4) =
                 make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
-          } else if (kNerf) {
+          }
+        } else if (kNerf) {
+          if (ch == 0 && live) {
             // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
+            const float* bo = s_bias + layer_out * kHidden;
             const float4 d = t ? dterm1 : dterm0;
             *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
-          } else {
-            float* orow = p.out + row * p.n_out + c0;
+          }
+        } else if (c0 < n_pad_out) {
+          // Head outputs (sampler / refine).  A warp's 32 rows x n_out floats are ONE contiguous global range, but thread = row:
+          // direct stores would scatter 4 bytes over 32 sectors per instruction.  Activation in registers, then rows_per_pass
+          // rows at a time through the lane quadrant's staging window and out as 16-byte stores.  n_out > 48: the quadrant's
+          // two warps (columns [0,48) and [48,96)) share the window and meet at a 64-thread named barrier.
+          const int n_out = p.n_out, rpp = p.out_rpp;
+          const bool two = n_pad_out > 48;
+          const float* bo = s_bias + layer_out * kHidden + c0;
+          auto activate = [&](auto c0_tag) {
+            constexpr int C0 = decltype(c0_tag)::value;
 #pragma unroll
-            for (int o = 0; o < 48; ++o) {
-              if (c0 + o < p.n_out) {
-                int kind = HEAD_NONE;
+            for (int g = 0; g < 3; ++g) {
+              if (n_pad_out > C0 + 16 * g) {
 #pragma unroll
-                for (int gq = 0; gq < 3; ++gq)
-                  if (c0 + o >= p.head_lo[gq] && c0 + o < p.head_lo[gq + 1]) kind = p.head_act[gq];
-                orow[o] = head_apply_fast(v[o] + bo[o], kind);
+                for (int i = 0; i < 16; ++i) v[16 * g + i] = head_apply_tab(v[16 * g + i] + bo[16 * g + i], p.head_tab[C0 + 16 * g + i]);
               }
             }
+          };
+          if (ch == 0) activate(std::integral_constant<int, 0>());
+          else activate(std::integral_constant<int, 48>());
+          auto sync_out = [&]() {
+            if (two) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            else __syncwarp();
+          };
+          float* stg = reinterpret_cast<float*>(sm + OFF_STAGE) + q * STAGE_FLOATS;
+          const long long grow_w = row - lane;                   // global row of the quadrant's first thread (a multiple of 32)
+          const int i0 = (two ? ch * 32 + lane : lane) * 4, istep = two ? 256 : 128;
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += rpp) {
+            const int l = lane - r0;
+            if (l >= 0 && l < rpp) {
+              float* d = stg + l * n_out + c0;
+#pragma unroll
+              for (int o = 0; o < 48; ++o)
+                if (c0 + o < n_out) d[o] = v[o];
+            }
+            sync_out();
+            const long long nl = p.M - (grow_w + r0);
+            int nrows = 32 - r0 < rpp ? 32 - r0 : rpp;
+            if (nl < nrows) nrows = nl > 0 ? (int)nl : 0;
+            const int nfl = nrows * n_out;
+            float* dst = p.out + (grow_w + r0) * n_out;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              for (int i = i0; i < nfl; i += istep) {
+                if (i + 4 <= nfl) {
+                  *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stg + i);
+                } else {
+                  for (int k = i; k < nfl; ++k) dst[k] = stg[k];
+                }
+              }
+            } else {
+              for (int i = i0 >> 2; i < nfl; i += istep >> 2) dst[i] = stg[i];
+            }
+            sync_out();
           }
         }
+        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 4);
       }
     }
   }
@@ -1356,8 +1444,12 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   p.k0 = n.in_dim[0];
   p.in0 = Lc.in0; p.in_stride = Lc.in_stride;
   p.M = Lc.M; p.out = Lc.out;
-  for (int i = 0; i < 4; ++i) p.head_lo[i] = Lc.head_lo[i];
-  for (int i = 0; i < 3; ++i) p.head_act[i] = Lc.head_act[i];
+  for (int c = 0; c < 96; ++c) {
+    int kind = HEAD_NONE;
+    for (int g = 0; g < 3; ++g)
+      if (c >= Lc.head_lo[g] && c < Lc.head_lo[g + 1]) kind = Lc.head_act[g];
+    p.head_tab[c] = tc::head_coeffs(kind);
+  }
   p.error_flag = n.error_flag;
   p.timeline = g_tc_timeline;
   {
@@ -1365,6 +1457,11 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     static const int env_shift = getenv("PN_TC_SHIFT") ? atoi(getenv("PN_TC_SHIFT")) : -1;
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
     p.split = env_split >= 0 ? (env_split != 0) : 0;
+    // head output staging: as many rows per pass as fit the quadrant's window, a multiple of 4 (16-byte aligned passes)
+    {
+      int rpp = (tc::STAGE_FLOATS / (p.n_out > 0 ? p.n_out : 1)) & ~3;
+      p.out_rpp = rpp > 32 ? 32 : rpp;
+    }
     p.shift = 0;           // the two slots run in step (the epilogue warps' loops assume it)
     (void)env_shift;
   }

@@ -17,8 +17,13 @@ elif which == "refine":
     x = torch.randn(M, 144, device=dev) * 0.5
     ctx = refn._ctx(); run = lambda: ctx.refine_forward(x, 8, "bf16"); nph = 7
 elif which == "refine16":
+    M = 571536
     x = (torch.randn(M, 144, device=dev) * 0.5).to(torch.float16)
     ctx = refn._ctx(); run = lambda: ctx.refine_forward_f16(x, 8); nph = 7
+elif which == "sampler_rays":      # the bench path: Pluecker input generated in-kernel (6-wide folded first layer)
+    M = 571536
+    rays = torch.randn(M, 11, device=dev)
+    ctx = samp._ctx(); run = lambda: ctx.sampler_forward_rays(rays, 8, 48, "bf16"); nph = 7
 else:
     x = torch.randn(M, 288, device=dev) * 0.5
     ctx = samp._ctx(); run = lambda: ctx.sampler_forward(x, 8, "bf16"); nph = 8
@@ -39,3 +44,6 @@ for ph in range(nph):
 names = ["body entry", "before acc wait", "first 64 cols loaded", "first store64 done", "second wait_ld done", "second store64 done", "published", "body exit"]
 print("epilogue warp 0, phase 2 slot 0 (acc seen %s):" % rel(40 + 4), ", ".join(f"{n} {rel(100 + k)}" for k, n in enumerate(names)))
 print("  prev arrive (ph1 s1)", rel(60 + 3), " next acc seen (ph2 s1)", rel(40 + 5))
+onames = ["body entry", "before acc wait", "acc in registers", "next operand stored", "outputs stored"]
+for s_ in range(2):
+    print(f"epilogue warp 0, output phase slot {s_}:", ", ".join(f"{n} {rel(110 + 6 * s_ + k)}" for k, n in enumerate(onames)))
