@@ -39,6 +39,10 @@ struct pn_ctx {
   float* view_buf = nullptr;
   size_t view_floats = 0;
   float* pm_dev = nullptr;         // projection matrices of the host-buffer entry points: [kMaxViews][8][12]
+  // pn_render_views_host: the first chunk's results go home on this stream while the second chunk renders
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t chunk_done = nullptr, d2h_done = nullptr;
+  int sm_count = 0;
   // stage timing ring (pn_ctx_profile)
   bool profile = false;
   std::vector<cudaEvent_t> ev;      // PN_PROFILE_RING * (PN_N_STAGES + 1), created lazily
@@ -105,6 +109,9 @@ void pn_ctx_destroy(pn_ctx_t* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->view_buf) cudaFree(c->view_buf);
   if (c->pm_dev) cudaFree(c->pm_dev);
+  if (c->chunk_done) cudaEventDestroy(c->chunk_done);
+  if (c->d2h_done) cudaEventDestroy(c->d2h_done);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
 }
@@ -331,7 +338,11 @@ int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int vie
 // ------------------------------------------------------------------------------------------------ the whole path
 // Scratch layout per ray (floats): heads 3S+3 | depth S | add S | mul S | depth3d S | refine_in 6S+3NN*S |
 // refine_out 4S+3 | z S | query 3S | raw 4S
-int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
+}  // extern "C"
+
+// rows [ray_base, ray_base + f->N) of a multi-view batch whose views hold f->rays_per_view rays each: every pointer of `f`
+// already points at the chunk's first row; ray_base only selects the view (matrices, neighbour ordering) of a row.
+static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base, pn_stream_t stream) {
   if (f && f->N == 0) return PN_OK;    // empty batch: nothing to validate or launch
   PN_REQUIRE(c && f, "pn_render_rays: null pointer");
   PN_REQUIRE(f->rays && f->or_rays && f->texels && f->project_mat && f->rgb && f->depth, "pn_render_rays: frame has a NULL buffer");
@@ -341,8 +352,9 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   const int S = f->S, NN = f->NN, P = f->P;
   const int nv = f->n_views > 1 ? f->n_views : 1;
   PN_REQUIRE(nv <= kMaxViews, "pn_render_rays: n_views=%d exceeds PN_MAX_VIEWS=%d", nv, kMaxViews);
-  PN_REQUIRE(nv == 1 || (f->rays_per_view >= 1 && f->rays_per_view * nv == N),
-             "pn_render_rays: N=%lld is not n_views=%d x rays_per_view=%lld", (long long)N, nv, (long long)f->rays_per_view);
+  PN_REQUIRE(nv == 1 || (f->rays_per_view >= 1 && ray_base >= 0 && ray_base + N <= f->rays_per_view * nv),
+             "pn_render_rays: rows [%lld, +%lld) are outside n_views=%d x rays_per_view=%lld", (long long)ray_base, (long long)N, nv,
+             (long long)f->rays_per_view);
   const int64_t rpv = nv > 1 ? f->rays_per_view : N;
   int tix[kMaxViews * 8];
   for (int v = 0; v < nv; ++v)
@@ -404,9 +416,10 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
     PN_STAGE_MARK(2);
     PN_STAGE_MARK(3);
     rc = launch_refine_input_f16(heads, hs, f->rays, f->or_rays, 11, f->texels, tix, nv, rpv, NN, f->H, f->W, f->project_mat, N, S,
-                                 depth, add, mul, rin, nullptr, st);
+                                 depth, add, mul, rin, nullptr, st, ray_base);
     if (rc != PN_OK) return rc;
   } else {
+  PN_REQUIRE(ray_base == 0, "pn_render_rays: chunked passes need the fused refine-input kernel (tensor-core tier, S in 4/8/16)");
   // (2) sort + lift  trt.py:631-637
   rc = pn_sort_lift(heads, hs, f->rays, 11, N, S, depth, add, mul, nullptr, depth3d, stream);
   if (rc != PN_OK) return rc;
@@ -446,6 +459,17 @@ int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
   PN_STAGE_MARK(8);
 #undef PN_STAGE_MARK
   return PN_OK;
+}
+
+extern "C" {
+
+int pn_render_rays(pn_ctx_t* c, const pn_frame_t* f, pn_stream_t stream) {
+  if (f && f->N == 0) return PN_OK;
+  PN_REQUIRE(c && f, "pn_render_rays: null pointer");
+  const int nv = f->n_views > 1 ? f->n_views : 1;
+  PN_REQUIRE(nv == 1 || (f->rays_per_view >= 1 && f->rays_per_view * nv == f->N),
+             "pn_render_rays: N=%lld is not n_views=%d x rays_per_view=%lld", (long long)f->N, nv, (long long)f->rays_per_view);
+  return render_rays_chunk(c, f, 0, stream);
 }
 
 
@@ -510,6 +534,41 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
   for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
   f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
   f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host; f.texels_ready = texels_ready_event;
+  // Two chunks on the tensor-core tier: the first is a whole number of waves of every persistent MLP kernel (one wave =
+  // a 512-ray unit per CTA pair), so splitting adds no tail; its rgb / depth travel to the host on a second stream while
+  // the second chunk renders.  Every ray is independent: the chunks' results are bit-identical to the single pass.
+  int64_t n_a = 0;
+  if (precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported) {
+    if (c->sm_count == 0) PN_CUDA_OK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    const int64_t wave = (int64_t)(c->sm_count / 2) * 512;
+    n_a = wave > 0 ? (n * 3 / 4) / wave * wave : 0;
+    if (n_a >= n) n_a = 0;
+  }
+  if (n_a > 0) {
+    if (!c->d2h_stream) {
+      PN_CUDA_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+      PN_CUDA_OK(cudaEventCreateWithFlags(&c->chunk_done, cudaEventDisableTiming));
+      PN_CUDA_OK(cudaEventCreateWithFlags(&c->d2h_done, cudaEventDisableTiming));
+    }
+    pn_frame_t fa = f, fb = f;
+    fa.N = n_a;
+    fb.N = n - n_a;
+    fb.rays = rays + n_a * 11; fb.or_rays = or_rays + n_a * 11; fb.rgb = rgb + n_a * 3; fb.depth = depth + n_a;
+    rc = render_rays_chunk(c, &fa, 0, stream);
+    if (rc != PN_OK) return rc;
+    PN_CUDA_OK(cudaEventRecord(c->chunk_done, st));
+    PN_CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, c->chunk_done, 0));
+    PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n_a * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+    PN_CUDA_OK(cudaMemcpyAsync(depth_host, depth, (size_t)n_a * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+    PN_CUDA_OK(cudaEventRecord(c->d2h_done, c->d2h_stream));
+    rc = render_rays_chunk(c, &fb, n_a, stream);
+    if (rc != PN_OK) return rc;
+    PN_CUDA_OK(cudaMemcpyAsync(rgb_host + n_a * 3, rgb + n_a * 3, (size_t)(n - n_a) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PN_CUDA_OK(cudaMemcpyAsync(depth_host + n_a, depth + n_a, (size_t)(n - n_a) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PN_CUDA_OK(cudaStreamWaitEvent(st, c->d2h_done, 0));       // the caller's stream order covers both chunks
+    PN_CUDA_OK(cudaStreamSynchronize(st));
+    return PN_OK;
+  }
   rc = pn_render_rays(c, &f, stream);
   if (rc != PN_OK) return rc;
   PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -109,7 +109,7 @@ int prog_launch(const NetProg& net, int input_mode, const float* in0, const floa
 int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
                             const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,
                             int W, const float* project_mat, int64_t N, int S, float* depth, float* add, float* mul,
-                            void* refine_in_f16, int32_t* x0y0, cudaStream_t stream);
+                            void* refine_in_f16, int32_t* x0y0, cudaStream_t stream, int64_t ray_base = 0);
 
 // ---------------------------------------------------------------------------------------------
 // Accurate fp32 helpers shared by kernels.  Nothing here may be compiled with --use_fast_math.

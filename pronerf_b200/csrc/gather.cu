@@ -148,7 +148,7 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
                     const float* __restrict__ or_rays, int rs, const float4* __restrict__ texels, TexIndexViews tex, int NNr,
                     int H, int W, const float* __restrict__ pm, int n_views, int64_t rays_per_view, int64_t N,
                     float* __restrict__ depth, float* __restrict__ add, float* __restrict__ mul, __half* __restrict__ rin,
-                    int32_t* __restrict__ x0y0) {
+                    int32_t* __restrict__ x0y0, int64_t ray_base) {
   constexpr int RPB = 256 / S;                              // rays per block
   constexpr int KMAX = 6 * S + 3 * 8 * S;
   __shared__ float sM[kMaxViews * 8 * 12];
@@ -167,7 +167,8 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
   // multi-view batches: rays of view `view` occupy rows [view * rays_per_view, +rays_per_view); each view has its own
   // neighbour ordering (texel indices) and projection matrices (trt.py:281-294)
   int view = 0;
-  if (n_views > 1) { view = (int)(r / rays_per_view); view = view < n_views ? view : n_views - 1; }
+  // (ray_base: this launch covers rows [ray_base, ray_base + N) of the batch -- chunked passes of pn_render_views_host)
+  if (n_views > 1) { view = (int)((r + ray_base) / rays_per_view); view = view < n_views ? view : n_views - 1; }
   const float* vM = sM + view * NN * 12;
   const float near_ = ray[6], far_ = ray[7];
   const float v = __fadd_rn(__fmul_rn(h[i], __fsub_rn(far_, near_)), near_);   // depth * (far - near) + near   trt.py:631
@@ -362,7 +363,7 @@ __global__ void epi_features_train_kernel(const float* __restrict__ warps, const
 int launch_refine_input_f16(const float* heads, int head_stride, const float* rays, const float* or_rays, int ray_stride,
                             const float* texels, const int* tex_index_host, int n_views, int64_t rays_per_view, int NN, int H,
                             int W, const float* project_mat, int64_t N, int S, float* depth, float* add, float* mul,
-                            void* refine_in_f16, int32_t* x0y0, cudaStream_t st) {
+                            void* refine_in_f16, int32_t* x0y0, cudaStream_t st, int64_t ray_base) {
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(heads && rays && or_rays && texels && project_mat && depth && add && mul && refine_in_f16,
              "pn_refine_input_f16: null pointer");
@@ -381,7 +382,7 @@ int launch_refine_input_f16(const float* heads, int head_stride, const float* ra
   __half* rin = reinterpret_cast<__half*>(refine_in_f16);
 #define PN_RI(SS, NT)                                                                                                    \
   refine_input_kernel<SS, NT><<<(unsigned)((N + (256 / SS) - 1) / (256 / SS)), 256, 0, st>>>(                            \
-      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, n_views, rays_per_view, N, depth, add, mul, rin, x0y0)
+      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, n_views, rays_per_view, N, depth, add, mul, rin, x0y0, ray_base)
   if (NN == 4) {
     if (S == 4) PN_RI(4, 4); else if (S == 8) PN_RI(8, 4); else PN_RI(16, 4);
   } else {

@@ -736,7 +736,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     //     chunk g of the range -> (row, chunk-in-row) -> the swizzled operand position.  Up to kPf chunks per thread are
     //     fetched into registers BEFORE the accumulator wait of the output phase (the loads do not depend on it) and
     //     stored once the slot's operand buffer is free. ---
-    constexpr int kPf = 9;                                 // 128 rows x 144 halves = 2304 chunks = 9 per thread
     const int cpr = p.k0 >> 3;                             // real chunks per row
     struct Range16 { int c_lo, w, total; uint32_t magic; };   // g / w == (g * magic) >> 20 for g < 128 * w, 2 <= w <= 32
     auto range16 = [&](int kb_lo, int nblk) {
@@ -772,22 +771,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         st_shared_v4(a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7), v.x, v.y, v.z, v.w);
       }
     };
-    auto prefetch16 = [&](long long tile, int kb_lo, int nblk, uint4* pf) {
+    // The same range as asynchronous copies (cp.async, 16 bytes each, zero-filled outside the tile): no staging registers
+    // -- nine 16-byte register prefetches per thread spilled at the 168-register ceiling, and a spilled load is a
+    // synchronous one (two exposed L2 round trips per tile).  Issued once the slot's operand buffer is free; the caller
+    // overlaps the latency with the head activations and calls cp_async_wait() before publishing.
+    auto cp_input16 = [&](long long tile, int t, int kb_lo, int nblk) {
       const Range16 R = range16(kb_lo, nblk);
       const Tile16 T = tile16(tile);
-#pragma unroll
-      for (int u = 0; u < kPf; ++u) fetch16(T, R, (int)threadIdx.x + u * (N_EPI_WARPS * 32), pf[u]);
+#pragma unroll 3
+      for (int g = (int)threadIdx.x; g < R.total; g += N_EPI_WARPS * 32) {
+        const int row = (int)(((uint32_t)g * R.magic) >> 20), cc = g - row * R.w, c = R.c_lo + cc;
+        const bool ok = row < T.rows && c < cpr;
+        const uint4* src = ok ? T.src + (row * cpr + c) : reinterpret_cast<const uint4*>(p.in0);
+        const uint32_t dst = a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // store the prefetched chunks, then load + store whatever the range holds beyond them
-    auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk, const uint4* pf, bool have_pf) {
+    auto cp_async_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+    // synchronous form (prologue, and the second part of a first layer wider than 256): load 4 chunks, store 4 chunks
+    auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk) {
       const Range16 R = range16(kb_lo, nblk);
       constexpr int NT = N_EPI_WARPS * 32;
       const Tile16 T = tile16(tile);
-      if (have_pf) {
-#pragma unroll
-        for (int u = 0; u < kPf; ++u) store16(t, R, (int)threadIdx.x + u * NT, pf[u]);
-      }
-      for (int g0 = have_pf ? kPf * NT : 0; g0 < R.total; g0 += 4 * NT) {
+      for (int g0 = 0; g0 < R.total; g0 += 4 * NT) {
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) fetch16(T, R, g0 + (int)threadIdx.x + u * NT, v[u]);
@@ -827,7 +834,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         precompute_input(xin, row < p.M, pre);
         store_pre(t, pre);
       } else if (MODE == IN_LOAD16) {
-        load_input16(cur.tile(t), t, 0, kb_first, nullptr, false);
+        load_input16(cur.tile(t), t, 0, kb_first);
       } else {
         load_input(cur.tile(t), t, 0, kb_first);
       }
@@ -860,7 +867,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
           acc_par ^= 1u << t;
           tc_fence_after();
-          if (MODE == IN_LOAD16) load_input16(T0 + t, t, kb_first, p.ph[1].nkb, nullptr, false);
+          if (MODE == IN_LOAD16) load_input16(T0 + t, t, kb_first, p.ph[1].nkb);
           else load_input(T0 + t, t, kb_first, p.ph[1].nkb);
           publish(t, 3);
         }
@@ -1022,8 +1029,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
           precompute_input(xin, row_of(tile + stride) < p.M, pre);
         }
-        uint4 pf[kPf];
-        if (MODE == IN_LOAD16 && has_next) prefetch16(tile + stride, 0, kb_first, pf);   // in flight across the wait below
         tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 1);
         mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
         acc_par ^= 1u << t;
@@ -1045,14 +1050,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 2);
         if (has_next) {
           if (kCompute) store_pre(t, pre);
-          else if (MODE == IN_LOAD16) load_input16(tile + stride, t, 0, kb_first, pf, true);
+          else if (MODE == IN_LOAD16) cp_input16(tile + stride, t, 0, kb_first);      // lands under the head activations
           else load_input(tile + stride, t, 0, kb_first);
         }
         tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 3);
-        publish(t, 3);
-        tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
-        tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
-        tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
+        if (MODE != IN_LOAD16) {
+          publish(t, 3);
+          tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
+          tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+          tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
+        }
         if (kClassic) {
           if (ch == 0 && live) {
             // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
@@ -1068,13 +1075,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
             const float4 d = t ? dterm1 : dterm0;
             *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
           }
-        } else if (c0 < n_pad_out) {
+        } else if (MODE == IN_LOAD16 || c0 < n_pad_out) {
           // Head outputs (sampler / refine).  A warp's 32 rows x n_out floats are ONE contiguous global range, but thread = row:
           // direct stores would scatter 4 bytes over 32 sectors per instruction.  Activation in registers, then rows_per_pass
           // rows at a time through the lane quadrant's staging window and out as 16-byte stores.  n_out > 48: the quadrant's
           // two warps (columns [0,48) and [48,96)) share the window and meet at a 64-thread named barrier.
           const int n_out = p.n_out, rpp = p.out_rpp;
-          const bool two = n_pad_out > 48;
+          const bool two = n_pad_out > 48, mine = MODE != IN_LOAD16 || c0 < n_pad_out;
           const float* bo = s_bias + layer_out * kHidden + c0;
           auto activate = [&](auto c0_tag) {
             constexpr int C0 = decltype(c0_tag)::value;
@@ -1087,7 +1094,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
             }
           };
           if (ch == 0) activate(std::integral_constant<int, 0>());
-          else activate(std::integral_constant<int, 48>());
+          else if (mine) activate(std::integral_constant<int, 48>());
+          if (MODE == IN_LOAD16) {                               // the asynchronous operand copies have landed by now
+            cp_async_wait();
+            publish(t, 3);
+            tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
+            tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+            tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
+          }
           auto sync_out = [&]() {
             if (two) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             else __syncwarp();
@@ -1096,7 +1110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           const long long grow_w = row - lane;                   // global row of the quadrant's first thread (a multiple of 32)
           const int i0 = (two ? ch * 32 + lane : lane) * 4, istep = two ? 256 : 128;
 #pragma unroll 1
-          for (int r0 = 0; r0 < 32; r0 += rpp) {
+          for (int r0 = 0; mine && r0 < 32; r0 += rpp) {
             const int l = lane - r0;
             if (l >= 0 && l < rpp) {
               float* d = stg + l * n_out + c0;

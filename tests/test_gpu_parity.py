@@ -760,6 +760,25 @@ def test_multi_view_batch(ops, precision):
     assert not torch.equal(rgb_o, rgb_h)
 
 
+def test_views_host_chunked(ops):
+    """pn_render_views_host splits a tensor-core batch into a whole number of MLP waves + the rest and sends the first
+    chunk's frames home while the second renders (the chunk boundary falls inside view 1 here): bit-identical to the
+    single device-resident pass, view-dependent matrices and neighbour orderings included."""
+    _bf16_ready(ops)
+    from pronerf_b200.engine import Renderer
+    scene = synth.make_small_scene(H=126, W=168)
+    sd = synth.make_weights(seed=3, calibrated=True)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    views = [scene.poses[i] for i in (0, 8, 16)]
+    n = 3 * scene.H * scene.W
+    wave = (torch.cuda.get_device_properties(0).multi_processor_count // 2) * 512
+    assert 0 < (n * 3 // 4) // wave * wave < n, "the batch must be large enough to be split"
+    rgb, depth = R.render_prepared(R.prepare_views(views))
+    for _ in range(2):
+        rgb_h, depth_h = R.render_views_host(views)
+        assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(depth_h, depth.cpu())
+
+
 def test_full_size_properties(ops):
     """BASELINE size (one 504x378 view, 190 512 rays), size-independent properties of every stage and of the tensor-core tier:
     sortedness / permutation of the sampler depths, linearity and zero-padding bound of the bilinear gather, bounds of the
