@@ -339,7 +339,7 @@ def main():
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R.image_bytes + len(views) * (12 + 12 * NN) * 4),
                 "d2h_bytes_per_step": int(len(views) * n_view * 16), "ms_per_step": e2e_step_ms,
-                "api": "Renderer.set_images (pinned H2D + pack, on a copy stream) + Renderer.render_views_host -> pn_render_views_host (all views of the step in one pass)"},
+                "api": "Renderer.set_images (pinned H2D + pack, on a copy stream) + Renderer.render_views_host -> pn_render_views_host (all views of the step as two wave-aligned chunks; the first chunk's frames go D2H on a second stream under the second chunk)"},
         "gpu_launches": int(args.steps * LAUNCHES_PER_STEP[precision]),
         "roofline": roof, "roofline_gather": gather,
         "stage_ms_per_view": {k: v / len(views) for k, v in stage_avg.items()},

@@ -261,8 +261,10 @@ int pn_render_view_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doubl
 
 /* render_path (trt.py:223-363) for n_views poses in one pass, HOST buffers: c2w_host [n_views,3,4], tex_index_host
  * [n_views,NN] (NULL = identity), project_mat_host [n_views,NN,3,4]; full frames; rgb_host [n_views*H*W,3] and
- * depth_host [n_views*H*W] (ideally pinned).  Uploads poses + matrices, generates all rays on the device, runs ONE
- * pn_render_rays over the n_views*H*W rays, downloads the frames and synchronises the stream.
+ * depth_host [n_views*H*W] (ideally pinned).  Uploads poses + matrices, generates all rays on the device, runs the
+ * pn_render_rays pass over the n_views*H*W rays, downloads the frames and synchronises the stream.  With PN_PREC_BF16
+ * the pass runs as two chunks (the first a whole number of waves of the persistent MLP kernels) and the first chunk's
+ * frames are downloaded on a second stream while the second chunk renders; results are bit-identical to one pass.
  * texels_ready_event: optional cudaEvent_t as in pn_frame_t.texels_ready (NULL = texels are ready on `stream`). */
 int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy, int n_views,
                          const float* c2w_host, const float* texels, const int* tex_index_host,

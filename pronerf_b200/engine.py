@@ -131,7 +131,8 @@ class Renderer:
                     rgb=torch.empty((n, 3), device=self.device), depth=torch.empty((n,), device=self.device))
 
     def render_views_host(self, c2ws, rgb_host=None, depth_host=None):
-        """End to end with HOST buffers for a batch of poses: one upload of poses + matrices, ONE pass, one download."""
+        """End to end with HOST buffers for a batch of poses: one upload of poses + matrices, one pass
+        (two wave-aligned chunks on the tensor-core tier, the first chunk's download overlapping the second's compute)."""
         params = [self.view_params(c) for c in c2ws]
         return self.ctx.render_views_host(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
                                           np.stack([p[2] for p in params], 0), self.S, self.P,
