@@ -541,7 +541,7 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
   if (precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported) {
     if (c->sm_count == 0) PN_CUDA_OK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     const int64_t wave = (int64_t)(c->sm_count / 2) * 512;
-    n_a = wave > 0 ? (n * 3 / 4) / wave * wave : 0;
+    n_a = wave > 0 ? (n * 7 / 8) / wave * wave : 0;      // the rest still renders longer than the first chunk's frames travel
     if (n_a >= n) n_a = 0;
   }
   if (n_a > 0) {

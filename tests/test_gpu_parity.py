@@ -772,7 +772,7 @@ def test_views_host_chunked(ops):
     views = [scene.poses[i] for i in (0, 8, 16)]
     n = 3 * scene.H * scene.W
     wave = (torch.cuda.get_device_properties(0).multi_processor_count // 2) * 512
-    assert 0 < (n * 3 // 4) // wave * wave < n, "the batch must be large enough to be split"
+    assert 0 < (n * 7 // 8) // wave * wave < n, "the batch must be large enough to be split"
     rgb, depth = R.render_prepared(R.prepare_views(views))
     for _ in range(2):
         rgb_h, depth_h = R.render_views_host(views)
