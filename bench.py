@@ -48,8 +48,8 @@ S, P, NN = 8, 48, 4
 # dirterm pre-pass, NeRF MLP, composite; fp32 tier = 8 stage kernels + one extra gather per additional view
 LAUNCHES_PER_STEP = {"bf16": 7, "fp32": 10}
 # dram__bytes_read.sum + dram__bytes_write.sum of the NeRF kernel from the committed ncu --set full capture, per ray
-NERF_DRAM_BYTES_PER_RAY = (65.40e6 + 31.92e6) / 571536
-NERF_TRAFFIC_SOURCE = "profiles/r01_c4_summary.md (ncu --set full, one 3-view launch: 65.4 MB read + 31.9 MB written)"
+NERF_DRAM_BYTES_PER_RAY = (64.97e6 + 30.77e6) / 571536
+NERF_TRAFFIC_SOURCE = "profiles/r01_c9_summary.md (ncu --set full, one 3-view launch: 65.0 MB read + 30.8 MB written)"
 
 
 def load_peaks():
