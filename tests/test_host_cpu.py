@@ -251,3 +251,55 @@ def test_peer_frame_band_views():
         for row0, nrows in all_shards(H, world):
             cover[row0 * W:(row0 + nrows) * W] += 1
         assert (cover == 1).all()
+
+
+def test_projection_matrices_hoisted_per_scene_equal_the_per_view_form():
+    """Renderer precomputes K * diag(1,-1,-1) * pose for EVERY reference camera once and indexes it per view
+    (engine.Renderer._pm_all); the rows must be bit-identical to computing the chosen neighbours' matrices per view
+    (trt.py:287-294)."""
+    from pronerf_b200.engine import neighbour_order, projection_matrices
+    rng = np.random.default_rng(5)
+    poses = rng.standard_normal((17, 3, 5)).astype(np.float32)
+    K = np.array([[410.3, 0., 252.], [0., 410.3, 189.], [0., 0., 1.]])
+    pm_all = projection_matrices(K, poses, range(poses.shape[0]))
+    for s in range(4):
+        c2w = rng.standard_normal((3, 4)).astype(np.float32)
+        order = neighbour_order(c2w, poses, 4)
+        assert np.array_equal(pm_all[order], projection_matrices(K, poses, order))
+
+
+def test_head_coefficient_form_matches_the_reference_activations():
+    """The tensor-core tier evaluates the sampler / refine heads (helpers.py:1497-1505, 1530-1538: sigmoid, tanh, identity
+    by column range) as ONE branch-free form y = c*x + (a / (1 + 2^(s*x)) + b) with per-column (s, a, b, c)
+    (mlp_tc.cu: head_coeffs / head_apply_tab).  Restated in numpy fp32: it must equal the torch activations to ~1e-6."""
+    import torch
+    l2e = np.float32(1.4426950408889634)
+    coeffs = {"none": (0., 0., 0., 1.), "sigmoid": (-l2e, 1., 0., 0.), "tanh": (-2 * l2e, 2., -1., 0.)}
+    x = np.concatenate([np.linspace(-30, 30, 2001), [-100., 100., 0.]]).astype(np.float32)
+    ref = {"none": x, "sigmoid": torch.sigmoid(torch.from_numpy(x)).numpy(), "tanh": torch.tanh(torch.from_numpy(x)).numpy()}
+    for kind, (s, a, b, c) in coeffs.items():
+        with np.errstate(over="ignore"):
+            e = np.exp2(x * np.float32(s)).astype(np.float32)
+            y = np.float32(c) * x + (np.float32(a) / (np.float32(1.) + e) + np.float32(b))
+        assert np.isfinite(y).all()
+        assert np.abs(y - ref[kind]).max() <= 2e-6, kind
+
+
+def test_host_pass_chunk_rule():
+    """pn_render_views_host (api.cu) splits a tensor-core batch of n rays into a first chunk of whole MLP waves
+    (wave = sm_count/2 CTA pairs x 512 rays) near 7/8 of the batch and the rest, or does not split at all.  Restated: the
+    split never adds a wave to any of the persistent MLP kernels (units of 512 rays for sampler / refine, 512/S for NeRF)."""
+    def split(n, sm=148):
+        wave = (sm // 2) * 512
+        n_a = (n * 7 // 8) // wave * wave
+        return 0 if n_a >= n else n_a
+    def waves(rays, rays_per_unit, clusters=74):
+        units = -(-rays // rays_per_unit)
+        return -(-units // clusters)
+    for n in (571536, 190512, 63504, 4032 * 3024, 37888, 37889, 1000):
+        n_a = split(n)
+        assert 0 <= n_a < n and n_a % (74 * 512) == 0
+        if n_a:
+            for rpu in (512, 64):               # sampler / refine units, NeRF units at S = 8
+                assert waves(n_a, rpu) + waves(n - n_a, rpu) == waves(n, rpu)
+    assert split(571536) == 13 * 37888 and split(1000) == 0
