@@ -126,9 +126,9 @@ class Recorder:
         return orig
 
 
-def run_reference_view(ref, H, IW, scene, sd, view, record=True):
-    nets = build_reference_nets(H, sd)
-    kw = make_kwargs(ref, H, scene, nets)
+def run_reference_view(ref, H, IW, scene, sd, view, record=True, S=8, P=48, NN=4):
+    nets = build_reference_nets(H, sd, S=S, P=P, NN=NN)
+    kw = make_kwargs(ref, H, scene, nets, S=S, P=P, NN=NN)
     c2w = scene.poses[view]
     with torch.no_grad():
         rays, or_rays, sh, project_mat = reference_prep(ref, H, scene, c2w, kw)
