@@ -244,6 +244,11 @@ typedef struct pn_frame {
   /* Optional cudaEvent_t (NULL = none): the first kernel that reads `texels` waits for it on `stream`, so the caller can
    * upload + pack the reference views on another stream while the sampler MLP (which does not need them) runs. */
   void* texels_ready;
+  /* Banded multi-view batches written straight into a frame set (tile sharding): 0 = dense output rows (row r
+   * of the batch -> row r of rgb / depth).  > 0: rgb / depth point at (view 0, this band's first ray) of a frame set laid out
+   * [n_views][out_view_stride rays]; ray r of view v lands at row v*out_view_stride + r.  With rgb / depth inside a peer-mapped
+   * frame (pn_peer_open) the compositing kernel's stores ARE the tile gather. */
+  int64_t out_view_stride;
 } pn_frame_t;
 #define PN_MAX_VIEWS 16
 
@@ -271,6 +276,21 @@ int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doub
                          const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
                          float* depth_host, void* texels_ready_event, pn_stream_t stream);
 
+/* Pipelined flavour for a serving loop: the same pass for rows [row0, row0+nrows) of every view, returning as soon as everything
+ * is enqueued.  Host frames are laid out [n_views][host_view_stride rays] (0 = dense, nrows*W per view) and rgb_host / depth_host
+ * point at (view 0, the band's first ray) -- a rank of a sharded frame downloads its band straight into the shared host frame.
+ * Results go home on the context's download stream; *ticket identifies the call for pn_wait.  Two calls may be in flight per
+ * context (device frames are double-buffered; a third call's compositing waits on the device for the download two calls back);
+ * the caller keeps rgb_host / depth_host untouched until pn_wait(ticket) returns.  c2w_host / project_mat_host / tex_index_host
+ * may be reused as soon as the call returns. */
+int pn_render_views_host_async(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                               const float* c2w_host, const float* texels, const int* tex_index_host,
+                               const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
+                               float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
+                               pn_stream_t stream, int64_t* ticket);
+/* Block until the frames of `ticket` (and of every earlier call) are in host memory. */
+int pn_wait(pn_ctx_t* ctx, int64_t ticket);
+
 /* ---- peer frame buffers: the final tile gather of a sharded frame as direct stores over NVLink -------------------------
  * One process per GPU.  The destination rank calls pn_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; handle64 = 64 bytes to
  * ship to the other ranks by any means), every other rank pn_peer_open's the handle (cudaIpcOpenMemHandle with lazy peer
@@ -281,6 +301,13 @@ int pn_peer_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handl
 int pn_peer_open(int device, const unsigned char* handle64, void** dev_ptr);
 int pn_peer_close(void* dev_ptr);
 int pn_peer_free(void* dev_ptr);
+/* Completion flags of the peer-store gather, in the same peer-mapped allocation: after its band, rank r enqueues
+ * pn_peer_signal(&flags[r], step) (a system-scope release store over NVLink, ordered after the compositing kernel's stores by
+ * the stream); the destination enqueues pn_peer_wait(flags, n, step, ...), a one-warp kernel that spins (acquire loads) until
+ * every flag is >= step -- the frame is then complete in its memory without any host round trip or collective.  A watchdog
+ * (timeout_ms) writes 1 + the late rank's index to *status_dev and lets the stream go on instead of hanging the GPU. */
+int pn_peer_signal(int* flag_dev, int step, pn_stream_t stream);
+int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -137,8 +137,17 @@ def prep_view(H, W, K, c2w, poses_ref, N_samples=8, N_point_ray_enc=48, num_neig
 
 
 # ----------------------------------------------------------------------------- A.2 / A.6 / A.8 MLPs
+# Test hook: ``OPERAND_ROUND = lambda t: t.to(torch.float16).float()`` (or bfloat16) emulates a reduced-precision MLP tier --
+# operands (activations and weights) rounded, fp32 accumulate, fp32 bias/activation -- so that the tolerance tests can show
+# where the fp16 tensor-core tier SHOULD land and that a bf16-operand kernel would fail them.  None = the reference's fp32.
+OPERAND_ROUND = None
+
+
 def _lin(sd, name, x):
-    return F.linear(x, _t(sd[name + ".weight"]), _t(sd[name + ".bias"]))
+    w, b = _t(sd[name + ".weight"]), _t(sd[name + ".bias"])
+    if OPERAND_ROUND is not None:
+        x, w = OPERAND_ROUND(x), OPERAND_ROUND(w)
+    return F.linear(x, w, b)
 
 
 def sampler_raw(sd, x, depth=6):

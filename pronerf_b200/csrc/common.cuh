@@ -111,6 +111,11 @@ int launch_refine_input_f16(const float* heads, int head_stride, const float* ra
                             int W, const float* project_mat, int64_t N, int S, float* depth, float* add, float* mul,
                             void* refine_in_f16, int32_t* x0y0, cudaStream_t stream, int64_t ray_base = 0);
 
+// raw2outputs (elementwise.cu) with output rows placed for banded multi-view batches (pn_frame_t.out_view_stride)
+int composite_mapped(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                     const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
+                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // Accurate fp32 helpers shared by kernels.  Nothing here may be compiled with --use_fast_math.
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }

@@ -241,12 +241,24 @@ __device__ __forceinline__ float4 clamp_raw(float4 r, float c) {
   return r;
 }
 
+// Where ray r of the batch lands in the output frame.  Dense (view_stride = 0): row r.  Banded multi-view batches (a rank's
+// band of every view written straight into a frame set [n_views][view_stride rays], pn_frame_t.out_view_stride): ray
+// g = ray_base + r belongs to view v = g / rays_per_view and goes to row v * view_stride + (g - v * rays_per_view).
+struct OutMap {
+  int64_t rays_per_view, view_stride, ray_base;
+  __device__ __forceinline__ int64_t row(int64_t r) const {
+    if (view_stride == 0) return r;
+    const int64_t g = r + ray_base, v = g / rays_per_view;
+    return v * view_stride + (g - v * rays_per_view);
+  }
+};
+
 template <int S>
 __global__ void composite_scan_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                       const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                       const float* __restrict__ add, const float* __restrict__ mul, int64_t N,
                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp) {
+                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one (ray, sample) per thread
   int64_t r = t / S;
   int s = (int)(t % S);
@@ -286,8 +298,9 @@ __global__ void composite_scan_kernel(const float* __restrict__ raw, const float
   if (!live) return;
   if (weights) weights[tt] = w;
   if (s == 0) {
-    rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
-    depth[r] = wz;
+    const int64_t ro = om.row(r);
+    rgb[3 * ro] = cr; rgb[3 * ro + 1] = cg; rgb[3 * ro + 2] = cb;
+    depth[ro] = wz;
     if (acc) acc[r] = ws;
     if (disp) disp[r] = disp_of(wz, ws);
   }
@@ -298,7 +311,7 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
                                      const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                      const float* __restrict__ add, const float* __restrict__ mul, int64_t N, int S,
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                     float* __restrict__ acc, float* __restrict__ weights, float raw_clamp) {
+                                     float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   const float* rd = rays + r * ray_stride + ray_d_col;
@@ -317,8 +330,9 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
     wz += w * zc; ws += w;
     if (weights) weights[tt] = w;
   }
-  rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
-  depth[r] = wz;
+  const int64_t ro = om.row(r);
+  rgb[3 * ro] = cr; rgb[3 * ro + 1] = cg; rgb[3 * ro + 2] = cb;
+  depth[ro] = wz;
   if (acc) acc[r] = ws;
   if (disp) disp[r] = disp_of(wz, ws);
 }
@@ -480,16 +494,22 @@ int pn_explore_samples(const float* rays, int ray_stride, const float* depth, in
   return PN_OK;
 }
 
-int pn_composite_stage1(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
-                        const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
-                        float* weights, pn_stream_t stream) {
+}  // extern "C"
+
+namespace pn {
+// raw2outputs with the output rows placed by (rays_per_view, out_view_stride, ray_base): see OutMap
+int composite_mapped(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                     const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
+                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st) {
   if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
   PN_REQUIRE(raw && z && rays && rgb && depth && N >= 0 && S >= 1 && ray_stride >= ray_d_col + 3 && ((add == nullptr) == (mul == nullptr)),
              "pn_composite: bad arguments");
-  cudaStream_t st = as_stream(stream);
+  PN_REQUIRE(out_view_stride == 0 || (rays_per_view >= 1 && out_view_stride >= rays_per_view && !disp && !acc),
+             "pn_composite: out_view_stride=%lld needs rays_per_view in [1, out_view_stride]", (long long)out_view_stride);
+  OutMap om{rays_per_view, out_view_stride, ray_base};
 #define PN_COMP(SS)                                                                                                  \
   composite_scan_kernel<SS><<<blocks_for(N * SS), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, \
-                                                                     rgb, depth, disp, acc, weights, raw_clamp)
+                                                                     rgb, depth, disp, acc, weights, raw_clamp, om)
   switch (S) {
     case 2: PN_COMP(2); break;
     case 4: PN_COMP(4); break;
@@ -498,11 +518,21 @@ int pn_composite_stage1(const float* raw, const float* z, const float* rays, int
     case 32: PN_COMP(32); break;
     default:
       composite_seq_kernel<<<blocks_for(N), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, S, rgb,
-                                                              depth, disp, acc, weights, raw_clamp);
+                                                              depth, disp, acc, weights, raw_clamp, om);
   }
 #undef PN_COMP
   PN_LAUNCH_OK("pn_composite");
   return PN_OK;
+}
+}  // namespace pn
+
+extern "C" {
+
+int pn_composite_stage1(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
+                        const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
+                        float* weights, pn_stream_t stream) {
+  return pn::composite_mapped(raw, z, rays, ray_stride, ray_d_col, add, mul, raw_clamp, N, S, rgb, depth, disp, acc, weights, 0, 0, 0,
+                              as_stream(stream));
 }
 
 int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,

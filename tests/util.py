@@ -88,3 +88,118 @@ def write_synthetic_llff(root, n_views=12, H=24, W=32, factor=2, seed=0, n_point
             for v in seen:
                 fh.write(struct.pack("<ii", int(ids[v]), 0))
     return names
+
+
+# ----------------------------------------------------------------------------- fp16 tensor-core tier vs the reference frame
+TARGET_PSNR_DB = 28.0          # a realistic render quality: the noise target puts the fp32 tier at 25-30 dB
+
+
+def noisy_target(ref_rgb, seed=0, psnr_db=TARGET_PSNR_DB):
+    """The reference (oracle fp32) frame + seeded Gaussian noise of the variance that gives ``psnr_db`` against it: a stand-in
+    ground truth at which a render of realistic quality sits, so that a PSNR delta between two tiers means what it would mean
+    on a trained scene (VERDICT r01 'what's weak' 1: against an unrelated image both tiers sit at single-digit dB and the
+    delta cannot move)."""
+    rs = np.random.RandomState(9000 + seed)
+    sigma = 10.0 ** (-psnr_db / 20.0)
+    return ref_rgb.astype(np.float64) + rs.standard_normal(ref_rgb.shape) * sigma
+
+
+def ops_sort_lift(heads, rays, S):
+    from pronerf_b200 import ops
+    return ops.sort_lift(heads, rays, S)
+
+
+def tier_parity_case(which, S, dev="cuda:0", view_slot=0, emulate=()):
+    """One BASELINE-sized case (fern-shaped 504x378 view, S samples/ray, ``which`` in random|calibrated): the oracle's fp32
+    frame, this package's fp32 and fp16 tiers through the reference call surface, and the numbers the tolerance tests assert.
+    ``emulate``: operand dtypes ('fp16', 'bf16') to ALSO push through the CPU oracle with rounded MLP operands."""
+    import torch
+    from oracle import pronerf_oracle as O
+    from pronerf_b200.render import prepare_view, render
+    scene = synth.make_scene(factor=8)
+    sd = synth.make_weights(seed=0, N_samples=S, calibrated=(which == "calibrated"))
+    view = int(scene.i_test[view_slot])
+    c2w = scene.poses[view]
+    O.OPERAND_ROUND = None
+    ref, _ = O.render_view(sd, scene, c2w, S=S, keep=True)
+    ref_rgb, ref_depth = ref["rgb_map"].numpy().reshape(-1, 3), ref["depth_map"].numpy().reshape(-1)
+    ref_perm = ref["perm"].numpy()
+    out, perm = {}, {}
+    for prec in ("fp32", "bf16"):
+        nets = make_modules(sd, dev, S=S, precision=prec)
+        kw = make_kwargs(nets, scene, dev, S=S, precision=prec)
+        with torch.no_grad():
+            rays, or_rays, sh = prepare_view(c2w, scene.hwf, scene.K, kw)
+            rgb, _, depth, _ = render(rays, or_rays, sh, **call_kwargs(kw))
+            # the tier's own sort order (trt.py:632): where it differs from the reference's, add / mul are gathered from other
+            # slots (trt.py:634-635) -- a DISCONTINUITY of the reference algorithm at near-tied depths, not a rounding error
+            heads = nets[1]._ctx().sampler_forward_rays(rays, S, 48, precision=prec)      # the fused route's sampler call
+            perm[prec] = ops_sort_lift(heads, rays, S)[3].cpu().numpy()
+        out[prec] = (rgb.reshape(-1, 3).cpu().numpy(), depth.reshape(-1).cpu().numpy())
+    gt = noisy_target(ref_rgb, seed=S)
+    m = {"which": which, "S": S, "view": view, "rays": int(ref_rgb.shape[0]),
+         "ref_rgb_range": [float(ref_rgb.min()), float(ref_rgb.max())],
+         "fp32_tier_max_abs_rgb": float(np.abs(out["fp32"][0] - ref_rgb).max()),
+         "fp32_tier_max_abs_depth": float(np.abs(out["fp32"][1] - ref_depth).max()),
+         "fp16_tier_max_abs_rgb": float(np.abs(out["bf16"][0] - ref_rgb).max()),
+         "fp16_tier_max_abs_depth": float(np.abs(out["bf16"][1] - ref_depth).max()),
+         "fp16_tier_cross_psnr_db": psnr(out["bf16"][0], ref_rgb),
+         "fp16_tier_depth_cross_psnr_db": psnr(out["bf16"][1], ref_depth),
+         "fp16_vs_fp32_tier_psnr_db": psnr(out["bf16"][0], out["fp32"][0]),
+         "target_psnr_ref_db": psnr(ref_rgb, gt), "target_psnr_fp32_tier_db": psnr(out["fp32"][0], gt),
+         "target_psnr_fp16_tier_db": psnr(out["bf16"][0], gt),
+         "finite": bool(np.isfinite(out["bf16"][0]).all() and np.isfinite(out["bf16"][1]).all())}
+    m["delta_psnr_db"] = abs(m["target_psnr_fp32_tier_db"] - m["target_psnr_fp16_tier_db"])
+    for prec, name in (("fp32", "fp32_tier"), ("bf16", "fp16_tier")):
+        same = (perm[prec] == ref_perm).all(1)
+        m[f"{name}_rays_with_other_sort_order"] = int((~same).sum())
+        err = np.maximum(np.abs(out[prec][0] - ref_rgb).max(1), np.abs(out[prec][1] - ref_depth))
+        m[f"{name}_max_abs_same_sort_order"] = float(err[same].max())
+        m[f"{name}_rays_over_1e-3"] = int((err > 1e-3).sum())
+        m[f"{name}_rays_over_1e-3_same_sort_order"] = int((err[same] > 1e-3).sum())
+    for name in emulate:
+        dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[name]
+        O.OPERAND_ROUND = lambda t, dt=dt: t.to(dt).float()
+        try:
+            e, _ = O.render_view(sd, scene, c2w, S=S)
+        finally:
+            O.OPERAND_ROUND = None
+        e_rgb = e["rgb_map"].numpy().reshape(-1, 3)
+        m[f"emulated_{name}_operands_cross_psnr_db"] = psnr(e_rgb, ref_rgb)
+        m[f"emulated_{name}_operands_delta_psnr_db"] = abs(psnr(e_rgb, gt) - m["target_psnr_ref_db"])
+    return m, out, (ref_rgb, ref_depth)
+
+
+def mlp_rel_errors(which, g, dev="cuda:0"):
+    """Per-network error of the fp16 tier against the reference's own fp32 outputs on identical inputs (golden small_*.npz):
+    {name: (max-abs / max|ref|, rms / rms(ref))}."""
+    import torch
+    from oracle import pronerf_oracle as O
+    from pronerf_b200 import ops
+    sd = synth.make_weights(seed=0, calibrated=(which == "calibrated"))
+    nerf, samp, refn = make_modules(sd, dev, precision="bf16")
+    H, W = [int(v) for v in g["scene_hw"]]
+    scene = synth.make_small_scene(H=H, W=W)
+    pv = O.prep_view(H, W, scene.K, g["c2w"], scene.poses_ref)
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return (float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-6)),
+                float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-9)))
+    res = {}
+    with torch.no_grad():
+        _, add, mul, depth = samp(pv["mm_input"].to(dev))
+        res["sampler_depth"] = rel(depth.cpu().numpy(), g["sampler_depth"])
+        res["sampler_add"] = rel(add.cpu().numpy(), g["sampler_add"])
+        res["sampler_mul"] = rel(mul.cpu().numpy(), g["sampler_mul"])
+        rd_, _, off_ = refn(T(g["refine_input"], dev))
+        res["refine_depth"] = rel(rd_.cpu().numpy(), g["refine_depth"])
+        res["refine_offsets"] = rel(off_.cpu().numpy(), g["refine_offsets"])
+        q, v = T(g["query_points"], dev), T(g["query_viewdirs"], dev)
+        raw_b = nerf._ctx().run_network(q, v, precision="bf16")
+        res["nerf_raw_fused_encoding"] = rel(raw_b.cpu().numpy(), g["nerf_raw"])
+        e = ops.embed(q.reshape(-1, 3), 10)
+        gd = ops.embed(v[:, None].expand(q.shape).reshape(-1, 3), 4)
+        raw_a = nerf(e, gd).reshape(q.shape[0], q.shape[1], 4)
+        res["nerf_raw_loaded_encoding"] = rel(raw_a.cpu().numpy(), g["nerf_raw"])
+    return res
