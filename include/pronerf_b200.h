@@ -42,7 +42,8 @@ typedef struct pn_ctx pn_ctx_t;   /* owns packed weights + scratch, like the ref
 
 /* arithmetic tier of the three MLPs */
 #define PN_PREC_FP32    0         /* fp32 SIMT FMA: the <=1e-3 max-abs parity tier            */
-#define PN_PREC_BF16    1         /* 16-bit operands (IEEE fp16 since v3 of the kernel; the name is historical), fp32 accumulate in TMEM on tcgen05 */
+#define PN_PREC_F16     1         /* tensor-core tier: IEEE fp16 operands (max 65504), fp32 accumulate in TMEM on tcgen05    */
+#define PN_PREC_BF16    PN_PREC_F16   /* deprecated alias (round-1 name); the operands are fp16, NOT bfloat16                */
 
 int         pn_version(void);
 const char* pn_last_error(void);

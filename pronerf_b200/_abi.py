@@ -15,8 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PN_B200_LIB") or os.path.join(HERE, "libpronerf_b200.so")   # env override: A/B builds while tuning
 
 PN_NET_SAMPLER, PN_NET_REFINE, PN_NET_NERF = 0, 1, 2
-PN_PREC_FP32, PN_PREC_BF16 = 0, 1
-PRECISIONS = {"fp32": PN_PREC_FP32, "bf16": PN_PREC_BF16}
+PN_PREC_FP32, PN_PREC_F16 = 0, 1
+PN_PREC_BF16 = PN_PREC_F16           # deprecated alias: the tensor-core tier multiplies IEEE fp16 operands (fp32 accumulate)
+# 'bf16' is the historical (round-1) name of the 'fp16' tier and selects the same kernels
+PRECISIONS = {"fp32": PN_PREC_FP32, "fp16": PN_PREC_F16, "bf16": PN_PREC_F16}
 
 _i, _i64, _p, _f, _d = C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_double
 
@@ -25,7 +27,8 @@ class Frame(C.Structure):
     """``pn_frame_t``."""
     _fields_ = [("rays", _p), ("or_rays", _p), ("mm_input", _p), ("texels", _p), ("tex_index", _i * 8),
                 ("project_mat", _p), ("N", _i64), ("S", _i), ("NN", _i), ("P", _i), ("H", _i), ("W", _i), ("precision", _i),
-                ("rgb", _p), ("depth", _p), ("n_views", _i), ("rays_per_view", _i64), ("tex_index_views", C.POINTER(_i)), ("texels_ready", _p)]
+                ("rgb", _p), ("depth", _p), ("n_views", _i), ("rays_per_view", _i64), ("tex_index_views", C.POINTER(_i)), ("texels_ready", _p),
+                ("out_view_stride", _i64)]
 
 
 # name -> (restype, argtypes); one entry per symbol declared in include/pronerf_b200.h
@@ -67,9 +70,14 @@ SIGNATURES = {
     "pn_peer_open": (_i, [_i, C.c_char_p, C.POINTER(_p)]),
     "pn_peer_close": (_i, [_p]),
     "pn_peer_free": (_i, [_p]),
+    "pn_peer_signal": (_i, [_p, _i, _p]),
+    "pn_peer_wait": (_i, [_p, _i, _i, _i, _p, _p]),
     "pn_render_rays": (_i, [_p, C.POINTER(Frame), _p]),
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
                                   _p, _p, _p, _p]),
+    "pn_render_views_host_async": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
+                                        _i, _i, _p, _p, _i64, _p, _p, C.POINTER(_i64)]),
+    "pn_wait": (_i, [_p, _i64]),
     "pn_render_view_host": (_i, [_p, _i, _i, _d, _d, _d, _d, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _i,
                                  _p, _p, _p]),
 }

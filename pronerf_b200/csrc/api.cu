@@ -1,6 +1,7 @@
 // C ABI glue: error state, the context (packed weights + scratch), and the composed render path.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -39,9 +40,19 @@ struct pn_ctx {
   float* view_buf = nullptr;
   size_t view_floats = 0;
   float* pm_dev = nullptr;         // projection matrices of the host-buffer entry points: [kMaxViews][8][12]
-  // pn_render_views_host: the first chunk's results go home on this stream while the second chunk renders
+  // host-buffer entry points: results go home on this stream while the next chunk / the next call renders
   cudaStream_t d2h_stream = nullptr;
-  cudaEvent_t chunk_done = nullptr, d2h_done = nullptr;
+  cudaEvent_t chunk_done = nullptr;
+  // device frames of pn_render_views_host_async, double-buffered: call k + 2 may only composite into slot k % 2 once call k's
+  // download has finished (waited for on the device, not on the host)
+  struct HostSlot {
+    float* out = nullptr;            // rgb [n,3] then depth [n]
+    size_t out_floats = 0;
+    cudaEvent_t rendered = nullptr, downloaded = nullptr;
+    bool used = false;
+    int64_t ticket = -1;             // the latest call whose download `downloaded` marks
+  } hs[2];
+  int64_t next_ticket = 0;
   int sm_count = 0;
   // stage timing ring (pn_ctx_profile)
   bool profile = false;
@@ -110,7 +121,11 @@ void pn_ctx_destroy(pn_ctx_t* c) {
   if (c->view_buf) cudaFree(c->view_buf);
   if (c->pm_dev) cudaFree(c->pm_dev);
   if (c->chunk_done) cudaEventDestroy(c->chunk_done);
-  if (c->d2h_done) cudaEventDestroy(c->d2h_done);
+  for (auto& h : c->hs) {
+    if (h.out) cudaFree(h.out);
+    if (h.rendered) cudaEventDestroy(h.rendered);
+    if (h.downloaded) cudaEventDestroy(h.downloaded);
+  }
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -235,7 +250,7 @@ static int run_mlp(pn_ctx_t* c, int net, MlpLaunch& L, int precision, cudaStream
   L.net = &c->f32[net];
   if (!c->f32[net].loaded) { set_error("network %d not loaded (pn_ctx_load_net)", net); return PN_ESTATE; }
   if (precision == PN_PREC_FP32) return launch_mlp_f32(L, st);
-  if (precision == PN_PREC_BF16) return tc_launch_mlp(c->tc[net], L, st);
+  if (precision == PN_PREC_F16) return tc_launch_mlp(c->tc[net], L, st);
   set_error("unknown precision %d", precision);
   return PN_EINVAL;
 }
@@ -287,7 +302,7 @@ int pn_refine_forward_f16(pn_ctx_t* c, const void* x_f16, int64_t N, int S, floa
   L.act = 1; L.input_mode = IN_LOAD16; L.in0 = reinterpret_cast<const float*>(x_f16); L.in1 = nullptr; L.in_stride = n.in_dim[0];
   L.S = S; L.P = 0; L.M = N; L.out = out;
   heads_refine(L, S);
-  return run_mlp(c, PN_NET_REFINE, L, PN_PREC_BF16, as_stream(stream));
+  return run_mlp(c, PN_NET_REFINE, L, PN_PREC_F16, as_stream(stream));
 }
 
 static int check_nerf(const NetF32& n) {
@@ -321,7 +336,7 @@ int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int vie
   PN_REQUIRE(c && pts && viewdirs && raw && N >= 0 && S >= 1 && viewdir_stride >= 3, "pn_run_network: bad arguments");
   if (c->nerf_classic.loaded) {
     PN_CUDA_OK(cudaSetDevice(c->device));
-    if (precision == PN_PREC_BF16)
+    if (precision == PN_PREC_F16)
       return tc_launch_nerf_classic(c->tc[PN_NET_NERF], pts, viewdirs, viewdir_stride, S, N * S, raw, as_stream(stream));
     int rcp = classic_precision_ok(precision, "pn_run_network");
     if (rcp != PN_OK) return rcp;
@@ -356,6 +371,8 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
              "pn_render_rays: rows [%lld, +%lld) are outside n_views=%d x rays_per_view=%lld", (long long)ray_base, (long long)N, nv,
              (long long)f->rays_per_view);
   const int64_t rpv = nv > 1 ? f->rays_per_view : N;
+  PN_REQUIRE(f->out_view_stride == 0 || f->out_view_stride >= rpv, "pn_render_rays: out_view_stride=%lld is smaller than rays_per_view=%lld",
+             (long long)f->out_view_stride, (long long)rpv);
   int tix[kMaxViews * 8];
   for (int v = 0; v < nv; ++v)
     for (int k = 0; k < NN; ++k) tix[v * NN + k] = (nv > 1 && f->tex_index_views) ? f->tex_index_views[v * NN + k] : f->tex_index[k];
@@ -411,7 +428,8 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
   // fp16 tier: sort/lift + Pluecker + project/gather run as ONE kernel that writes the refine input as fp16 rows,
   // which the refine MLP's first-layer operand loads chunk for chunk (timed as the project_gather stage)
   if (f->texels_ready) PN_CUDA_OK(cudaStreamWaitEvent(st, reinterpret_cast<cudaEvent_t>(f->texels_ready), 0));
-  const bool fused_input = f->precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported;
+  // (rows of the fp16 refine input must be whole 16-byte chunks for the refine kernel's loads: otherwise the per-stage route)
+  const bool fused_input = f->precision == PN_PREC_F16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported && ri % 8 == 0;
   if (fused_input) {
     PN_STAGE_MARK(2);
     PN_STAGE_MARK(3);
@@ -454,12 +472,19 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(7);
   // (7) composite  trt.py:694
-  rc = pn_composite(raw, z, f->rays, 11, 3, add, mul, N, S, f->rgb, f->depth, nullptr, nullptr, nullptr, stream);
+  rc = composite_mapped(raw, z, f->rays, 11, 3, add, mul, 0.f, N, S, f->rgb, f->depth, nullptr, nullptr, nullptr, rpv,
+                        f->out_view_stride, ray_base, st);
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(8);
 #undef PN_STAGE_MARK
   return PN_OK;
 }
+
+static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                                  const float* c2w_host, const float* texels, const int* tex_index_host,
+                                  const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
+                                  float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
+                                  pn_stream_t stream, int64_t* ticket, bool two_chunks);
 
 extern "C" {
 
@@ -506,50 +531,91 @@ int pn_render_view_host(pn_ctx_t* c, int H, int W, double fx, double fy, double 
   return PN_OK;
 }
 
-int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
-                         const float* c2w_host, const float* texels, const int* tex_index_host,
-                         const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
-                         float* depth_host, void* texels_ready_event, pn_stream_t stream) {
-  PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host, "pn_render_views_host: null pointer");
+int pn_render_views_host_async(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                               const float* c2w_host, const float* texels, const int* tex_index_host,
+                               const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
+                               float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
+                               pn_stream_t stream, int64_t* ticket) {
+  return render_views_host_impl(c, H, W, fx, fy, cx, cy, n_views, c2w_host, texels, tex_index_host, project_mat_host, NN, S, P, precision,
+                                row0, nrows, rgb_host, depth_host, host_view_stride, texels_ready_event, stream, ticket, false);
+}
+}  // extern "C"
+
+// two_chunks: split the pass so that the first chunk's frames travel while the second renders -- lowers the LATENCY of a lone
+// synchronous call; a pipelined caller overlaps the whole download with the next call instead and renders in one pass.
+static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                                  const float* c2w_host, const float* texels, const int* tex_index_host,
+                                  const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
+                                  float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
+                                  pn_stream_t stream, int64_t* ticket, bool two_chunks) {
+  PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host && ticket, "pn_render_views_host: null pointer");
   PN_REQUIRE(NN >= 1 && NN <= 8 && n_views >= 0 && n_views <= kMaxViews && H >= 2 && W >= 2,
              "pn_render_views_host: bad shape (n_views=%d, at most %d per batch)", n_views, kMaxViews);
-  if (n_views == 0) return PN_OK;
+  PN_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= H, "pn_render_views_host: rows [%d, +%d) outside H=%d", row0, nrows, H);
+  const int64_t npv = (int64_t)nrows * W, n = npv * n_views;
+  const int64_t hvs = host_view_stride > 0 ? host_view_stride : npv;
+  PN_REQUIRE(hvs >= npv, "pn_render_views_host: host_view_stride=%lld is smaller than the band (%lld rays)", (long long)hvs, (long long)npv);
   PN_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = as_stream(stream);
-  const int64_t npv = (int64_t)H * W, n = npv * n_views;
-  int rc = ensure(&c->view_buf, &c->view_floats, (size_t)n * (11 + 11 + 3 + 1));
+  if (!c->d2h_stream) {
+    PN_CUDA_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    PN_CUDA_OK(cudaEventCreateWithFlags(&c->chunk_done, cudaEventDisableTiming));
+    for (auto& h : c->hs) {
+      PN_CUDA_OK(cudaEventCreateWithFlags(&h.rendered, cudaEventDisableTiming));
+      PN_CUDA_OK(cudaEventCreateWithFlags(&h.downloaded, cudaEventDisableTiming));
+    }
+  }
+  const int64_t tk = c->next_ticket++;
+  *ticket = tk;
+  pn_ctx::HostSlot& hs = c->hs[tk & 1];
+  if (n == 0) return PN_OK;            // empty batch: nothing of its own to wait for (pn_wait still covers every earlier call)
+  if (hs.out_floats < (size_t)n * 4) {
+    if (hs.used) PN_CUDA_OK(cudaEventSynchronize(hs.downloaded));      // growing a frame that may still be on its way home
+    int rc = ensure(&hs.out, &hs.out_floats, (size_t)n * 4);
+    if (rc != PN_OK) return rc;
+  }
+  int rc = ensure(&c->view_buf, &c->view_floats, (size_t)n * 22);
   if (rc != PN_OK) return rc;
   float* rays = c->view_buf;
   float* or_rays = rays + n * 11;
-  float* rgb = or_rays + n * 11;
+  float* rgb = hs.out;
   float* depth = rgb + n * 3;
   PN_CUDA_OK(cudaMemcpyAsync(c->pm_dev, project_mat_host, (size_t)n_views * NN * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
   for (int v = 0; v < n_views; ++v) {
-    rc = pn_raygen(H, W, fx, fy, cx, cy, c2w_host + 12 * v, 0.f, 1.f, 1.f, 10.f, 0, H, rays + v * npv * 11, or_rays + v * npv * 11, stream);
+    rc = pn_raygen(H, W, fx, fy, cx, cy, c2w_host + 12 * v, 0.f, 1.f, 1.f, 10.f, row0, nrows, rays + v * npv * 11, or_rays + v * npv * 11, stream);
     if (rc != PN_OK) return rc;
   }
+  if (hs.used) PN_CUDA_OK(cudaStreamWaitEvent(st, hs.downloaded, 0));  // the call two back has left this device frame
   pn_frame_t f;
   memset(&f, 0, sizeof(f));
   f.rays = rays; f.or_rays = or_rays; f.mm_input = nullptr; f.texels = texels; f.project_mat = c->pm_dev;
   for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
   f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
   f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host; f.texels_ready = texels_ready_event;
+  // rows [a, b) of the batch -> the host frame set [n_views][hvs], view by view
+  auto download = [&](int64_t a, int64_t b) -> int {
+    for (int v = 0; v < n_views; ++v) {
+      const int64_t lo = a > v * npv ? a : v * npv, hi = b < (v + 1) * npv ? b : (v + 1) * npv;
+      if (lo >= hi) continue;
+      const int64_t h0 = v * hvs + (lo - v * npv);
+      PN_CUDA_OK(cudaMemcpyAsync(rgb_host + h0 * 3, rgb + lo * 3, (size_t)(hi - lo) * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+      PN_CUDA_OK(cudaMemcpyAsync(depth_host + h0, depth + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
+    return PN_OK;
+  };
   // Two chunks on the tensor-core tier: the first is a whole number of waves of every persistent MLP kernel (one wave =
-  // a 512-ray unit per CTA pair), so splitting adds no tail; its rgb / depth travel to the host on a second stream while
+  // a 512-ray unit per CTA pair), so splitting adds no tail; its rgb / depth travel to the host on the download stream while
   // the second chunk renders.  Every ray is independent: the chunks' results are bit-identical to the single pass.
   int64_t n_a = 0;
-  if (precision == PN_PREC_BF16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported) {
+  static const int env_chunks = getenv("PN_HOST_CHUNKS") ? atoi(getenv("PN_HOST_CHUNKS")) : -1;     // tuning aid: 0 / 1 forces
+  if (env_chunks >= 0) two_chunks = env_chunks != 0;
+  if (two_chunks && precision == PN_PREC_F16 && (S == 4 || S == 8 || S == 16) && c->tc[PN_NET_REFINE].supported && (6 * S + 3 * NN * S) % 8 == 0) {
     if (c->sm_count == 0) PN_CUDA_OK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     const int64_t wave = (int64_t)(c->sm_count / 2) * 512;
     n_a = wave > 0 ? (n * 7 / 8) / wave * wave : 0;      // the rest still renders longer than the first chunk's frames travel
     if (n_a >= n) n_a = 0;
   }
   if (n_a > 0) {
-    if (!c->d2h_stream) {
-      PN_CUDA_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-      PN_CUDA_OK(cudaEventCreateWithFlags(&c->chunk_done, cudaEventDisableTiming));
-      PN_CUDA_OK(cudaEventCreateWithFlags(&c->d2h_done, cudaEventDisableTiming));
-    }
     pn_frame_t fa = f, fb = f;
     fa.N = n_a;
     fb.N = n - n_a;
@@ -558,22 +624,50 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
     if (rc != PN_OK) return rc;
     PN_CUDA_OK(cudaEventRecord(c->chunk_done, st));
     PN_CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, c->chunk_done, 0));
-    PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n_a * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
-    PN_CUDA_OK(cudaMemcpyAsync(depth_host, depth, (size_t)n_a * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
-    PN_CUDA_OK(cudaEventRecord(c->d2h_done, c->d2h_stream));
+    rc = download(0, n_a);
+    if (rc != PN_OK) return rc;
     rc = render_rays_chunk(c, &fb, n_a, stream);
     if (rc != PN_OK) return rc;
-    PN_CUDA_OK(cudaMemcpyAsync(rgb_host + n_a * 3, rgb + n_a * 3, (size_t)(n - n_a) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    PN_CUDA_OK(cudaMemcpyAsync(depth_host + n_a, depth + n_a, (size_t)(n - n_a) * sizeof(float), cudaMemcpyDeviceToHost, st));
-    PN_CUDA_OK(cudaStreamWaitEvent(st, c->d2h_done, 0));       // the caller's stream order covers both chunks
-    PN_CUDA_OK(cudaStreamSynchronize(st));
-    return PN_OK;
+  } else {
+    rc = pn_render_rays(c, &f, stream);
+    if (rc != PN_OK) return rc;
   }
-  rc = pn_render_rays(c, &f, stream);
+  PN_CUDA_OK(cudaEventRecord(hs.rendered, st));
+  PN_CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, hs.rendered, 0));
+  rc = download(n_a, n);
   if (rc != PN_OK) return rc;
-  PN_CUDA_OK(cudaMemcpyAsync(rgb_host, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  PN_CUDA_OK(cudaMemcpyAsync(depth_host, depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  PN_CUDA_OK(cudaStreamSynchronize(st));
+  PN_CUDA_OK(cudaEventRecord(hs.downloaded, c->d2h_stream));
+  hs.used = true;
+  hs.ticket = tk;
+  return PN_OK;
+}
+
+extern "C" {
+
+int pn_wait(pn_ctx_t* c, int64_t ticket) {
+  PN_REQUIRE(c && ticket >= 0 && ticket < c->next_ticket, "pn_wait: unknown ticket %lld", (long long)ticket);
+  PN_CUDA_OK(cudaSetDevice(c->device));
+  // The download stream is in order.  A slot whose latest download belongs to this call or an earlier one is waited for; the
+  // other slot may already carry a LATER call, which a pipelined caller does not want to wait for -- unless it is this
+  // ticket's own slot, reused since (then its event is the only handle left on that download).
+  for (int s = 0; s < 2; ++s) {
+    pn_ctx::HostSlot& hs = c->hs[s];
+    if (hs.used && (hs.ticket <= ticket || s == (int)(ticket & 1))) PN_CUDA_OK(cudaEventSynchronize(hs.downloaded));
+  }
+  return PN_OK;
+}
+
+int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double cx, double cy, int n_views,
+                         const float* c2w_host, const float* texels, const int* tex_index_host,
+                         const float* project_mat_host, int NN, int S, int P, int precision, float* rgb_host,
+                         float* depth_host, void* texels_ready_event, pn_stream_t stream) {
+  int64_t ticket = 0;
+  int rc = render_views_host_impl(c, H, W, fx, fy, cx, cy, n_views, c2w_host, texels, tex_index_host, project_mat_host, NN, S, P,
+                                  precision, 0, H, rgb_host, depth_host, 0, texels_ready_event, stream, &ticket, true);
+  if (rc != PN_OK) return rc;
+  rc = pn_wait(c, ticket);
+  if (rc != PN_OK) return rc;
+  PN_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));      // synchronous flavour: the caller's stream is idle on return, as before
   return PN_OK;
 }
 
@@ -602,6 +696,51 @@ int pn_peer_open(int device, const unsigned char* handle64, void** dev_ptr) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   PN_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PN_OK;
+}
+
+}  // extern "C"
+
+namespace pn {
+__global__ void peer_signal_kernel(int* flag, int step) {
+  // the compositing kernel's stores into the peer frame are complete (stream order); publish the step at system scope
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
+}
+
+__global__ void peer_wait_kernel(const int* flags, int n, int step, unsigned long long timeout_ns, int* status) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    if (v >= step) break;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) {                       // a rank is late or gone: report instead of hanging the GPU
+      if (status) atomicExch(status, 1 + i);
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+}  // namespace pn
+
+extern "C" {
+
+int pn_peer_signal(int* flag_dev, int step, pn_stream_t stream) {
+  PN_REQUIRE(flag_dev, "pn_peer_signal: flag is NULL");
+  peer_signal_kernel<<<1, 1, 0, as_stream(stream)>>>(flag_dev, step);
+  PN_LAUNCH_OK("pn_peer_signal");
+  return PN_OK;
+}
+
+int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, pn_stream_t stream) {
+  PN_REQUIRE(flags_dev && n_flags >= 1 && n_flags <= 32 && timeout_ms > 0, "pn_peer_wait: bad arguments (n_flags=%d)", n_flags);
+  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(flags_dev, n_flags, step, (unsigned long long)timeout_ms * 1000000ull, status_dev);
+  PN_LAUNCH_OK("pn_peer_wait");
   return PN_OK;
 }
 

@@ -229,10 +229,13 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
   __syncthreads();
   // coalesced copy-out of the block's rows (contiguous in global memory; K0 * 2 bytes per row is a multiple of 16)
   const int64_t live_rays = (N - ray0) < RPB ? (N - ray0) : RPB;
-  const int chunks = (int)(live_rays * K0 * 2 / 16);
+  const int halves = (int)(live_rays * K0);
+  const int chunks = halves / 8;
   const uint4* s4 = reinterpret_cast<const uint4*>(stage);
   uint4* g4 = reinterpret_cast<uint4*>(rin + ray0 * K0);
   for (int c = threadIdx.x; c < chunks; c += blockDim.x) g4[c] = s4[c];
+  // rows of K0 % 8 != 0 halves (S = 4 with an odd neighbour count): the last block's tail is not a whole 16-byte chunk
+  for (int e = chunks * 8 + threadIdx.x; e < halves; e += blockDim.x) rin[ray0 * K0 + e] = stage[e];
 }
 
 // ------------------------------------------------------------------------------------------------

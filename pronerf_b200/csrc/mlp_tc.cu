@@ -1384,6 +1384,7 @@ int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, cons
 }
 
 static int tc_max_clusters(const void* func, int* out);
+constexpr int kMaxDevices = 64;
 
 // run_network with the classic NeRF: pts [M,3] (M = N*S rows), per-ray view directions, both encoded in-kernel -> raw [M,4]
 int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, int viewdir_stride, int S, int64_t M, float* raw,
@@ -1411,7 +1412,11 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
     P.act_none = c.act_none; P.more_src = c.more_src; P.side = c.side;
   }
   auto kern = tc::mlp_tc_kernel<0, IN_CLASSIC>;
-  static int max_clusters = 0;
+  static int max_clusters_dev[kMaxDevices] = {0};          // per device: attribute + occupancy are set / queried on the current one
+  int dev_id = 0;
+  PN_CUDA_OK(cudaGetDevice(&dev_id));
+  PN_REQUIRE(dev_id >= 0 && dev_id < kMaxDevices, "tc: device index %d out of range", dev_id);
+  int& max_clusters = max_clusters_dev[dev_id];
   if (max_clusters == 0) {
     PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
     int rc = tc_max_clusters((const void*)kern, &max_clusters);
@@ -1532,10 +1537,14 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   }
 
   const long long units = (Lc.M + tc::UNIT_M - 1) / tc::UNIT_M;
+  int dev_id = 0;
+  PN_CUDA_OK(cudaGetDevice(&dev_id));
+  PN_REQUIRE(dev_id >= 0 && dev_id < kMaxDevices, "tc: device index %d out of range", dev_id);
 #define PN_TC_LAUNCH(ACT, MODE)                                                                                            \
   do {                                                                                                                     \
     auto kern = tc::mlp_tc_kernel<ACT, MODE>;                                                                              \
-    static int max_clusters = 0;                                                                                           \
+    static int max_clusters_dev[kMaxDevices] = {0};                                                                        \
+    int& max_clusters = max_clusters_dev[dev_id];                                                                          \
     if (max_clusters == 0) {                                                                                               \
       PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));                 \
       int rc = tc_max_clusters((const void*)kern, &max_clusters);                                                          \

@@ -84,7 +84,6 @@ class Renderer:
         if self._staging is None or self._staging.shape != t.shape:
             self._staging = torch.empty(t.shape, dtype=torch.float32, device=self.device)
             self.texels = torch.empty(tuple(t.shape[:3]) + (4,), dtype=torch.float32, device=self.device)
-        self._tex_event = None
         with torch.cuda.device(self.device):
             if overlap:
                 if self._copy_stream is None:
@@ -98,9 +97,23 @@ class Renderer:
                     self._tex_done.record(self._copy_stream)
                 self._tex_event = self._tex_done
             else:
+                # an earlier overlapped upload may still be writing the staging buffer / the texels on the copy stream
+                self._join_texels()
                 self._staging.copy_(t, non_blocking=non_blocking)
                 ops.pack_images(self._staging, out=self.texels)
         self.image_bytes = t.numel() * 4
+
+    def _join_texels(self):
+        """Make the current stream wait for an overlapped ``set_images`` still in flight on the copy stream.  Every entry point
+        that reads (or rewrites) the texels on the main stream calls this; ``render_views_host*`` instead hand the event to the
+        library, which waits right before the first kernel that reads the texels (the sampler MLP runs under the upload)."""
+        if self._tex_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._tex_event)
+            self._tex_event = None
+
+    def _take_tex_event(self):
+        ev, self._tex_event = self._tex_event, None      # once a pass on the main stream has waited, later ones are ordered behind it
+        return ev
 
     # -- per view ---------------------------------------------------------------------------------
     def view_params(self, c2w):
@@ -116,15 +129,17 @@ class Renderer:
                     rgb=torch.empty((rays.shape[0], 3), device=self.device), depth=torch.empty((rays.shape[0],), device=self.device))
 
     def render_prepared(self, prep):
-        """One pass of the hot path (8 kernels) over a prepared view; returns (rgb [n,3], depth [n]) CUDA tensors."""
+        """One pass of the hot path over a prepared view / batch of views; returns (rgb [n,3], depth [n]) CUDA tensors.
+        ``prep['out_view_stride']`` (optional): the outputs are a band inside a frame set, see ``pn_frame_t.out_view_stride``."""
+        self._join_texels()
         return self.ctx.render_rays(prep["rays"], prep["or_rays"], self.texels, prep["project_mat"], self.S, self.P,
                                     self.H, self.W, tex_index=prep["tex_index"], precision=self.precision,
-                                    out_rgb=prep["rgb"], out_depth=prep["depth"])
+                                    out_rgb=prep["rgb"], out_depth=prep["depth"], out_view_stride=prep.get("out_view_stride", 0))
 
     # -- batches of views (render_path's loop over poses as one pass) --------------------------------
-    def prepare_views(self, c2ws):
-        """Device-resident inputs of a batch of full views, rays stacked view after view."""
-        preps = [self.prepare_view(c) for c in c2ws]
+    def prepare_views(self, c2ws, row0: int = 0, nrows=None):
+        """Device-resident inputs of a batch of views (rows [row0, row0+nrows) of each), rays stacked view after view."""
+        preps = [self.prepare_view(c, row0, nrows) for c in c2ws]
         n = sum(p["rays"].shape[0] for p in preps)
         return dict(rays=torch.cat([p["rays"] for p in preps], 0), or_rays=torch.cat([p["or_rays"] for p in preps], 0),
                     project_mat=torch.stack([p["project_mat"] for p in preps], 0), tex_index=[p["tex_index"] for p in preps],
@@ -137,7 +152,19 @@ class Renderer:
         return self.ctx.render_views_host(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
                                           np.stack([p[2] for p in params], 0), self.S, self.P,
                                           tex_index=[p[1] for p in params], precision=self.precision, rgb_host=rgb_host,
-                                          depth_host=depth_host, texels_ready=self._tex_event)
+                                          depth_host=depth_host, texels_ready=self._take_tex_event())
+
+    def render_views_host_async(self, c2ws, rgb_host, depth_host, row0: int = 0, nrows=None, host_view_stride: int = 0) -> int:
+        """Pipelined flavour (``pn_render_views_host_async``): returns a ticket as soon as the pass is enqueued; up to two calls
+        in flight, ``wait(ticket)`` blocks until that call's frames are in ``rgb_host`` / ``depth_host``."""
+        params = [self.view_params(c) for c in c2ws]
+        return self.ctx.render_views_host_async(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
+                                                np.stack([p[2] for p in params], 0), self.S, self.P, rgb_host, depth_host,
+                                                tex_index=[p[1] for p in params], precision=self.precision, row0=row0, nrows=nrows,
+                                                host_view_stride=host_view_stride, texels_ready=self._take_tex_event())
+
+    def wait(self, ticket: int):
+        self.ctx.wait(ticket)
 
     def render_view(self, c2w, row0: int = 0, nrows=None):
         return self.render_prepared(self.prepare_view(c2w, row0, nrows))
@@ -145,6 +172,7 @@ class Renderer:
     def render_view_host(self, c2w, rgb_host=None, depth_host=None, row0: int = 0, nrows=None):
         """End to end with HOST buffers: uploads the pose + matrices, renders, downloads rgb/depth (synchronous)."""
         c2w, order, pm = self.view_params(c2w)
+        self._join_texels()
         return self.ctx.render_view_host(self.H, self.W, self.K, c2w, self.texels, pm, self.S, self.P, tex_index=order,
                                          precision=self.precision, row0=row0, nrows=nrows, rgb_host=rgb_host,
                                          depth_host=depth_host)
@@ -157,6 +185,19 @@ def flops_per_ray(S: int = 8, P: int = 48, NN: int = 4, W: int = 256) -> dict:
     refine = 2 * ((6 * S + 3 * NN * S) * W + 5 * W * W + W * (4 * S + 3))
     nerf = S * 2 * (63 * W + 6 * W * W + (W + 27) * 4)
     return dict(sampler=sampler, refine=refine, nerf=nerf, total=sampler + refine + nerf)
+
+
+def executed_flops_per_ray(S: int = 8, P: int = 48, NN: int = 4, W: int = 256) -> dict:
+    """Flops the tensor-core tier actually ISSUES per ray: K padded to whole 16-wide MMA steps, N padded to a
+    multiple of 16; the sampler's first layer folded from 6P to 6 inputs (one K = 16 step); the NeRF last layer's 27
+    view-direction inputs evaluated once per ray on the CUDA cores (``dirterm_kernel``) instead of per sample."""
+    pad = lambda v, m: (v + m - 1) // m * m
+    sampler = 2 * (16 * W + 5 * W * W + W * pad(3 * S + 3, 16))
+    refine = 2 * (pad(6 * S + 3 * NN * S, 16) * W + 5 * W * W + W * pad(4 * S + 3, 16))
+    nerf = S * 2 * (64 * W + 6 * W * W + W * 16) + 2 * 27 * 4
+    return dict(sampler=sampler, refine=refine, nerf=nerf, total=sampler + refine + nerf,
+                note="tensor-core MMA flops incl. padding + the per-ray CUDA-core view-direction term; roofline figures divide the "
+                     "ALGORITHMIC flops by time, never these")
 
 
 def gather_bytes_per_ray(S: int = 8, NN: int = 4, H: int = 378, W: int = 504, n_rays=None) -> float:

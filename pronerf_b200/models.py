@@ -25,7 +25,7 @@ def _weights_key(linears):
 class _PackedNet(nn.Module):
     """Shared plumbing: a lazily created per-module context and a weight-version cache."""
     NET_ID = -1
-    precision = "fp32"          # "fp32" (parity tier) or "bf16" (tcgen05 tier); set per module or via render kwargs
+    precision = "fp32"          # "fp32" (parity tier) or "fp16" (tcgen05 tier; "bf16" = deprecated alias); set per module or via render kwargs
 
     def _linears(self):
         raise NotImplementedError

@@ -24,8 +24,12 @@ def _cuda_guard(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
-def bf16_tier_available() -> bool:
+def fp16_tier_available() -> bool:
+    """True when the tensor-core tier (fp16 operands, fp32 accumulate) is compiled into the library."""
     return bool(lib().pn_has_bf16_tier())
+
+
+bf16_tier_available = fp16_tier_available          # round-1 name
 
 
 # ----------------------------------------------------------------------------- context
@@ -42,6 +46,7 @@ class Context:
         check(lib().pn_ctx_create(self.index, C.byref(h)), "pn_ctx_create")
         self._h = h
         self._keys = {}
+        self._in_dims = {}                 # net id -> first-layer width, checked before every forward (nn.Linear would raise)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -74,6 +79,7 @@ class Context:
         with torch.cuda.device(self.device):
             check(lib().pn_ctx_load_net(self.handle, net_id, n, ind, outd, wp, bp, stream_ptr(self.device)), "pn_ctx_load_net")
         self._keys[net_id] = key
+        self._in_dims[net_id] = int(ws[0].shape[1])
 
     def load_nerf_classic(self, weights, biases, key=None):
         """The classic NeRF as this context's shading network: 12 nn.Linear tensors in checkpoint order (pts_linears.0..7,
@@ -118,8 +124,14 @@ class Context:
             raise ValueError(f"out must be a dense fp32 tensor of shape {tuple(shape)} on {like.device}")
         return out
 
+    def _check_width(self, net_id, x, what):
+        want = self._in_dims.get(net_id)
+        if want is not None and x.shape[1] != want:
+            raise ValueError(f"{what}: input rows are {x.shape[1]} wide, the loaded network expects {want}")
+
     def sampler_forward(self, x, S, precision="fp32", out=None):
         x = as_f32c(x)
+        self._check_width(_abi.PN_NET_SAMPLER, x, "sampler_forward")
         out = self._out(out, (x.shape[0], 3 * S + 3), x)
         with _cuda_guard(x):
             check(lib().pn_sampler_forward(self.handle, dptr(x, "x"), x.shape[0], S, dptr(out), PRECISIONS[precision],
@@ -137,6 +149,7 @@ class Context:
 
     def refine_forward(self, x, S, precision="fp32", out=None):
         x = as_f32c(x)
+        self._check_width(_abi.PN_NET_REFINE, x, "refine_forward")
         out = self._out(out, (x.shape[0], 4 * S + 3), x)
         with _cuda_guard(x):
             check(lib().pn_refine_forward(self.handle, dptr(x, "x"), x.shape[0], S, dptr(out), PRECISIONS[precision],
@@ -147,6 +160,7 @@ class Context:
         """Tensor-core refine MLP on the fp16 rows written by ``refine_input_f16`` -> [N, 4S+3] fp32."""
         if x16.dtype != torch.float16:
             raise TypeError("x16 must be torch.float16")
+        self._check_width(_abi.PN_NET_REFINE, x16, "refine_forward_f16")
         out = _empty((x16.shape[0], 4 * S + 3), x16)
         with _cuda_guard(x16):
             check(lib().pn_refine_forward_f16(self.handle, dptr(x16, "x16", torch.float16), x16.shape[0], S, dptr(out),
@@ -175,16 +189,32 @@ class Context:
 
     # -- whole path -------------------------------------------------------------------------------
     def render_rays(self, rays, or_rays, texels, project_mat, S, P, H, W, mm_input=None, tex_index=None,
-                    precision="fp32", out_rgb=None, out_depth=None):
+                    precision="fp32", out_rgb=None, out_depth=None, out_view_stride=0):
         """``project_mat`` [NN,3,4] for one view, or [V,NN,3,4] for a batch of V views whose rays are stacked view after
-        view (then ``tex_index`` is a [V][NN] table)."""
+        view (then ``tex_index`` is a [V][NN] table).  ``out_view_stride`` > 0: ``out_rgb`` / ``out_depth`` start at (view 0, this
+        band's first ray) of a frame set laid out [V][out_view_stride rays] (``pn_frame_t.out_view_stride``)."""
         rays, or_rays = as_f32c(rays), as_f32c(or_rays)
         N = rays.shape[0]
+        if rays.shape[1] != 11 or or_rays.shape != rays.shape:
+            raise ValueError(f"rays / or_rays must be [N,11] (o, d, near, far, viewdir), got {tuple(rays.shape)} / {tuple(or_rays.shape)}")
+        if project_mat.dim() == 4 and project_mat.shape[0] == 1:           # a batch of one view: the single-view form
+            project_mat = project_mat[0]
+            if tex_index is not None and len(tex_index) == 1 and isinstance(tex_index[0], (list, tuple)):
+                tex_index = tex_index[0]
         n_views = project_mat.shape[0] if project_mat.dim() == 4 else 1
         NN = project_mat.shape[-3]
+        if mm_input is not None and tuple(mm_input.shape) != (N, 6 * P):
+            raise ValueError(f"mm_input must be [{N},{6 * P}], got {tuple(mm_input.shape)}")
+        used = [int(v) for row in tex_index for v in row] if (tex_index is not None and n_views > 1) else \
+            ([int(v) for v in tex_index] if tex_index is not None else list(range(NN)))
+        if used and (min(used) < 0 or max(used) >= texels.shape[0]):
+            raise ValueError(f"tex_index {used} outside the {texels.shape[0]} packed reference views")
+        if out_view_stride and (out_rgb is None or out_depth is None):
+            raise ValueError("out_view_stride needs caller-owned out_rgb / out_depth inside the frame set")
         rgb = out_rgb if out_rgb is not None else _empty((N, 3), rays)
         depth = out_depth if out_depth is not None else _empty((N,), rays)
         f = _abi.Frame()
+        f.out_view_stride = int(out_view_stride)
         f.rays, f.or_rays = dptr(rays, "rays"), dptr(or_rays, "or_rays")
         f.mm_input = dptr(mm_input, "mm_input") if mm_input is not None else None
         f.texels = dptr(texels, "texels")
@@ -232,6 +262,37 @@ class Context:
                                              texels_ready.cuda_event if texels_ready is not None else None,
                                              stream_ptr(self.device)), "pn_render_views_host")
         return rgb_host, depth_host
+
+    def render_views_host_async(self, H, W, K, c2ws, texels, project_mats_host, S, P, rgb_host, depth_host, tex_index=None,
+                                precision="fp32", row0=0, nrows=None, host_view_stride=0, texels_ready=None) -> int:
+        """Pipelined ``render_views_host`` (``pn_render_views_host_async``): enqueues the pass for rows [row0, row0+nrows) of every
+        view and returns a ticket for ``wait``; ``rgb_host`` / ``depth_host`` (pinned CPU tensors) start at (view 0, the band's
+        first ray) of a host frame set laid out [V][host_view_stride rays] (0 = dense) and must stay untouched until ``wait``."""
+        import numpy as np
+        c2ws = np.ascontiguousarray(np.asarray(c2ws, dtype=np.float32)[:, :3, :4])
+        pms = np.ascontiguousarray(np.asarray(project_mats_host, dtype=np.float32))
+        V, NN = pms.shape[0], pms.shape[1]
+        nrows = H - row0 if nrows is None else nrows
+        hvs = host_view_stride if host_view_stride else nrows * W
+        need = ((V - 1) * hvs + nrows * W) if V else 0
+        if rgb_host.is_cuda or depth_host.is_cuda or rgb_host.numel() < need * 3 or depth_host.numel() < need:
+            raise ValueError(f"rgb_host / depth_host must be CPU tensors holding at least {need} rays from the band's first ray on")
+        ti = None
+        if tex_index is not None:
+            ti = (C.c_int * (V * NN))(*[int(v) for row in tex_index for v in row])
+        ticket = C.c_int64(-1)
+        with torch.cuda.device(self.device):
+            check(lib().pn_render_views_host_async(self.handle, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), V,
+                                                   c2ws.ctypes.data_as(C.POINTER(C.c_float)), dptr(texels, "texels"), ti,
+                                                   pms.ctypes.data_as(C.POINTER(C.c_float)), NN, S, P, PRECISIONS[precision],
+                                                   int(row0), int(nrows), rgb_host.data_ptr(), depth_host.data_ptr(), int(hvs),
+                                                   texels_ready.cuda_event if texels_ready is not None else None,
+                                                   stream_ptr(self.device), C.byref(ticket)), "pn_render_views_host_async")
+        return int(ticket.value)
+
+    def wait(self, ticket: int):
+        """Block until the frames of ``ticket`` (and of every earlier call) are in host memory."""
+        check(lib().pn_wait(self.handle, int(ticket)), "pn_wait")
 
     def render_view_host(self, H, W, K, c2w, texels, project_mat_host, S, P, tex_index=None, precision="fp32",
                          row0=0, nrows=None, rgb_host=None, depth_host=None):
@@ -459,6 +520,8 @@ def composite(raw, z_vals, rays_d, add, mul, extras: bool = True):
     """raw2outputs (trt.py:564-597) -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
     raw, z_vals, rays_d, add, mul = (as_f32c(t) for t in (raw, z_vals, rays_d, add, mul))
     N, S = z_vals.shape
+    if raw.shape[-1] != 4 or raw.numel() != N * S * 4:
+        raise ValueError(f"raw must be [N,S,4] (rgb + sigma logits; N_importance > 0 / output_ch = 5 is not built), got {tuple(raw.shape)}")
     rgb = _empty((N, 3), raw)
     depth = _empty((N,), raw)
     disp = _empty((N,), raw) if extras else None

@@ -124,14 +124,14 @@ def _texels_from_kwargs(kwargs, S):
     if kwargs.get('texels') is not None and kwargs.get('project_mat') is not None:
         return kwargs['texels'], kwargs['project_mat'], kwargs.get('tex_index')
     ref_rgb, ref_pose = kwargs['ref_rgb'], kwargs['ref_pose']
-    k = (ref_rgb.data_ptr(), ref_rgb._version, tuple(ref_rgb.shape))
-    tex = _texel_cache.get(k)
-    if tex is None:
-        if len(_texel_cache) > 4:
-            _texel_cache.clear()
-        tex = ops.pack_images(ref_rgb[::S].permute(0, 2, 3, 1).contiguous())
-        _texel_cache[k] = tex
-    return tex, ref_pose[::S].contiguous(), None
+    # Packed once per TENSOR OBJECT and version: the entry keeps the source tensor alive and is only hit by that very
+    # object (`is`), unmodified since (`_version`).  A key made of data_ptr / shape alone would be hit again when
+    # render_path builds a new ref_rgb per view (trt.py:296-302) and the caching allocator hands the freed block back.
+    ent = _texel_cache.get('last')
+    if ent is None or ent[0] is not ref_rgb or ent[1] != ref_rgb._version:
+        ent = (ref_rgb, ref_rgb._version, ops.pack_images(ref_rgb[::S].permute(0, 2, 3, 1).contiguous()))
+        _texel_cache['last'] = ent
+    return ent[2], ref_pose[::S].contiguous(), None
 
 
 # ----------------------------------------------------------------------------- trt.py:599-696
@@ -145,7 +145,8 @@ def render_rays(ray_batch, or_ray_batch, network_fn, network_query_fn, N_samples
     Consumed kwargs: ``mm_input`` (optional here: generated in-kernel from the rays when absent),
     ``num_neighbor``, ``texels``+``project_mat`` or ``ref_rgb``+``ref_pose``, ``use_trt`` (+ ``mm_engine``,
     ``refine_engine``, ``nerf_engine``: the reference's engine seam, served by ``pronerf_b200.trt_infer_v2``),
-    ``precision`` ('fp32' | 'bf16', default = the modules' ``precision``), ``fused`` (default True).
+    ``precision`` ('fp32' | 'fp16'; 'bf16' is a deprecated alias of 'fp16'; default = the modules' ``precision``), ``fused``
+    (default True).
     """
     use_trt = bool(kwargs.get('use_trt'))
     if use_trt and any(kwargs.get(k) is None for k in ('mm_engine', 'refine_engine', 'nerf_engine')):
@@ -261,13 +262,15 @@ def prepare_view(c2w, hwf, K, render_kwargs, near=0., far=1., or_near=1., or_far
     render_kwargs['project_mat'] = torch.from_numpy(pm).to(dev)
     # reference images: resident RGBA texels for the whole i_ref set, packed once
     images = render_kwargs['images']
-    ik = (id(images), getattr(images, 'shape', None))
     cached = render_kwargs.get('_texel_set')
-    if cached is None or cached[0] != ik:
+    # the entry holds the source object itself (an id() can be reused by a new array); tensors are also checked for in-place
+    # edits through _version.  A numpy array edited in place is not detectable: pass a new array (or drop '_texel_set').
+    ver = images._version if isinstance(images, torch.Tensor) else None
+    if cached is None or cached[0] is not images or cached[1] != ver:
         img_t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32))
-        cached = (ik, ops.pack_images(img_t.to(dev)))
+        cached = (images, ver, ops.pack_images(img_t.to(dev)))
         render_kwargs['_texel_set'] = cached
-    render_kwargs['texels'] = cached[1]
+    render_kwargs['texels'] = cached[2]
     render_kwargs['tex_index'] = [int(i) for i in ref_nos]
     if render_kwargs.get('materialize_mm_input') or render_kwargs.get('use_trt'):
         render_kwargs['mm_input'] = ops.sampler_input(rays, render_kwargs['N_point_ray_enc'])
@@ -381,8 +384,8 @@ def config_parser():
     p.add_argument("--expname", type=str, default='fern_8samples_b200')
     p.add_argument("--basedir", type=str, default='./logs_minmax/')
     p.add_argument("--datadir", type=str, default='synthetic:fern',
-                   help="'synthetic:fern' renders the seeded fern-shaped scene; real LLFF directories are not loaded "
-                        "by this package (SURVEY.md section 8, row f5)")
+                   help="an LLFF / COLMAP capture directory (poses_bounds.npy, images_<factor>/, sparse/0/*.bin; loaded by "
+                        "pronerf_b200.llff_io), or 'synthetic:fern' for the seeded fern-shaped scene")
     p.add_argument("--netdepth", type=int, default=8)
     p.add_argument("--netwidth", type=int, default=256)
     p.add_argument("--netdepth_fine", type=int, default=8)
@@ -425,8 +428,10 @@ def config_parser():
     p.add_argument("--export_only", action='store_true')
     p.add_argument("--max_images", type=int, default=None)
     # additions of this package
-    p.add_argument("--precision", type=str, default='bf16', choices=['fp32', 'bf16'],
-                   help="MLP arithmetic: fp32 SIMT (<=1e-3 parity tier) or bf16 tcgen05 (throughput tier)")
+    p.add_argument("--precision", type=str, default='fp16', choices=['fp32', 'fp16', 'bf16'],
+                   help="MLP arithmetic: fp32 SIMT (<=1e-3 parity tier) or fp16 operands / fp32 accumulate on tcgen05 (throughput tier; "
+                        "IEEE half: finite range 65504, so activations of an unnormalised checkpoint can saturate).  'bf16' is the "
+                        "deprecated round-1 name of the fp16 tier and selects the same kernels")
     p.add_argument("--timing_repeats", type=int, default=20, help="renders per view inside the timed loop (reference: 20)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--calibrated_init", action='store_true', help="synthetic weights with a wide output range")

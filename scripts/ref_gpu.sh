@@ -17,6 +17,7 @@ case "$1" in
     mkdir -p $out gpurun_out
     python scripts/ref_gpu.py ref $out  > gpurun_out/r02_ref_gpu_ref.log 2>&1 || { tail -30 gpurun_out/r02_ref_gpu_ref.log; exit 1; }
     python scripts/ref_gpu.py ours $out > gpurun_out/r02_ref_gpu_ours.log 2>&1 || { tail -30 gpurun_out/r02_ref_gpu_ours.log; exit 1; }
+    python tests/parity_report.py gpurun_out/r02_parity.json $out > gpurun_out/r02_parity.log 2>&1 || { tail -30 gpurun_out/r02_parity.log; exit 1; }
     tail -3 gpurun_out/r02_ref_gpu_ours.log ;;
   *) echo "usage: $0 stage|run"; exit 2 ;;
 esac

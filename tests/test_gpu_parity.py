@@ -450,7 +450,7 @@ def test_nerf_classic_topology(ops):
         mx = np.abs(raw16 - want).max() / max(np.abs(want).max(), 1e-6)
         rms = np.sqrt(np.mean((raw16 - want) ** 2)) / max(np.sqrt(np.mean(want ** 2)), 1e-9)
         print(f"classic NeRF, tensor-core tier [{tag}]: max {mx:.2e} rms {rms:.2e} of the output scale")
-        assert mx < 5e-2 and rms < 1.5e-2, (mx, rms)
+        assert mx < 1e-3 and rms < 5e-4, (mx, rms)             # 2x measured on B200 (4.5e-4 / 2.5e-4; r02 test log)
         big = torch.cat([pts] * 9, 0)[:800]                                                 # > one 512-row unit, ragged tail
         bigv = torch.cat([vd] * 9, 0)[:800]
         raw_big = run_network(big, bigv, net, embed_fn, embeddirs_fn)
@@ -460,7 +460,7 @@ def test_nerf_classic_topology(ops):
     from tests.util import psnr
     p16 = psnr(rgb16.cpu().numpy(), rgb_r.cpu().numpy())
     print(f"classic NeRF view, tensor-core tier vs fp32 tier: {p16:.1f} dB")
-    assert torch.isfinite(rgb16).all() and p16 >= 38.0
+    assert torch.isfinite(rgb16).all() and p16 >= 84.0             # measured 87.5 dB
 
 
 def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
@@ -484,7 +484,9 @@ def test_infer_driver_loads_a_stage2_checkpoint(ops, tmp_path):
     np.testing.assert_allclose(res["rgbs"][0].reshape(-1, 3), ref["rgb_map"].numpy(), atol=1e-3, rtol=0)
     res16 = train(common + ["--expname", "classic16", "--precision", "bf16"])
     from tests.util import psnr
-    assert psnr(res16["rgbs"][0], res["rgbs"][0]) >= 38.0
+    p16 = psnr(res16["rgbs"][0], res["rgbs"][0])
+    print(f"infer driver on a stage-2 checkpoint, tensor-core tier vs fp32 tier: {p16:.1f} dB")
+    assert p16 >= 60.0
 
 
 @pytest.mark.parametrize("n_mult", [1, 3, 8])
@@ -512,7 +514,9 @@ def test_stage1_style_forward(ops, n_mult):
     if ops.bf16_tier_available():
         R16 = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
         rgb16, _, _ = stage1_forward(R16.ctx, rays, 8, 48, n_mult, "bf16")
-        assert torch.isfinite(rgb16).all() and psnr(rgb16.cpu().numpy(), ref["rgb_map"].numpy()) >= 38.0
+        p16 = psnr(rgb16.cpu().numpy(), ref["rgb_map"].numpy())
+        print(f"stage-1 style forward n_mult={n_mult}, tensor-core tier vs the oracle: {p16:.1f} dB")
+        assert torch.isfinite(rgb16).all() and p16 >= 60.0
 
 
 def test_training_warp_and_mean_fill(ops):
@@ -570,7 +574,7 @@ def test_stage2_eval_forward(ops):
         else:
             p = psnr(r["rgb_map1"].cpu().numpy(), g["rgb_map1"])
             print(f"stage-2 eval forward, tensor-core tier vs the reference: {p:.1f} dB")
-            assert torch.isfinite(r["rgb_map1"]).all() and p >= 38.0
+            assert torch.isfinite(r["rgb_map1"]).all() and p >= 84.0           # measured 87.0 dB
     # stage 1 (base.py:554-761, randomize=False, train_sampler=False) against ITS reference output
     from pronerf_b200.stage2 import stage1_eval_forward
     g1 = load_golden("stage1_eval.npz")
@@ -585,7 +589,7 @@ def test_stage2_eval_forward(ops):
         else:
             p = psnr(r["rgb_map1"].cpu().numpy(), g1["rgb_map1"])
             print(f"stage-1 eval forward, tensor-core tier vs the reference: {p:.1f} dB")
-            assert torch.isfinite(r["rgb_map1"]).all() and p >= 38.0
+            assert torch.isfinite(r["rgb_map1"]).all() and p >= 83.5           # measured 86.5 dB
 
 
 # ================================================================================================
@@ -598,39 +602,16 @@ def _bf16_ready(ops):
 
 @pytest.mark.parametrize("which", ["random", "calibrated"])
 def test_mlps_bf16_vs_reference(ops, which, golden_small_random, golden_small_calibrated):
-    """Each network in bf16 (fp32 accumulate) against the reference's fp32 outputs on identical inputs.
-    Tolerance: bf16 has 8 mantissa bits; through 7-8 layers the observed error is ~1e-2 of the output scale."""
+    """Each network on the tensor-core tier (fp16 operands, fp32 accumulate) against the reference's own fp32 outputs on identical
+    inputs.  Bounds = 2x the values measured on B200 (profiles/r02_parity.json: max <= 1.2e-3, rms <= 5.2e-4 of the output
+    scale); the CPU oracle with bf16-rounded operands sits at ~8x these values, i.e. a bf16 kernel fails here."""
     _bf16_ready(ops)
+    from tests.util import FP16_TIER_MLP_REL_BOUND, mlp_rel_errors
     g = golden_small_random if which == "random" else golden_small_calibrated
-    sd = synth.make_weights(seed=0, calibrated=(which == "calibrated"))
-    nerf, samp, refn = make_modules(sd, DEV, precision="bf16")
-    H, W = [int(v) for v in g["scene_hw"]]
-    scene = synth.make_small_scene(H=H, W=W)
-    pv = O.prep_view(H, W, scene.K, g["c2w"], scene.poses_ref)
-
-    def rel(a, b):
-        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-6), np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-9)
-
-    with torch.no_grad():
-        _, add, mul, depth = samp(pv["mm_input"].to(DEV))
-        for got, want in ((depth, g["sampler_depth"]), (add, g["sampler_add"]), (mul, g["sampler_mul"])):
-            mx, rms = rel(got.cpu().numpy(), want)
-            assert mx < 4e-2 and rms < 1e-2, (mx, rms)
-        # sampler with the input generated inside the kernel (replicated Pluecker block) == loaded input, to bf16 resolution
-        ctx = samp._ctx()
-        rd_, _, off_ = refn(T(g["refine_input"], DEV))
-        for got, want in ((rd_, g["refine_depth"]), (off_, g["refine_offsets"])):
-            mx, rms = rel(got.cpu().numpy(), want)
-            assert mx < 4e-2 and rms < 1e-2, (mx, rms)
-        q, v = T(g["query_points"], DEV), T(g["query_viewdirs"], DEV)
-        raw_b = nerf._ctx().run_network(q, v, precision="bf16")
-        e = ops.embed(q.reshape(-1, 3), 10)
-        gd = ops.embed(v[:, None].expand(q.shape).reshape(-1, 3), 4)
-        raw_a = nerf(e, gd).reshape(q.shape[0], q.shape[1], 4)
-        for got in (raw_a, raw_b):
-            mx, rms = rel(got.cpu().numpy(), g["nerf_raw"])
-            assert mx < 5e-2 and rms < 1.5e-2, (mx, rms)
+    errs = mlp_rel_errors(which, g, DEV)
+    print(which, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in errs.items()})
+    for name, (mx, rms) in errs.items():
+        assert mx < FP16_TIER_MLP_REL_BOUND[0] and rms < FP16_TIER_MLP_REL_BOUND[1], (name, mx, rms)
 
 
 @pytest.mark.parametrize("S", [4, 8, 16])
@@ -691,36 +672,31 @@ def test_refine_forward_f16_input(ops, golden_small_calibrated):
         ctx.refine_forward_f16(x.to(torch.float16).reshape(-1)[4:4 + 144 * 8].reshape(8, 144), 8)
 
 
+@pytest.mark.parametrize("S", [4, 8, 16])
 @pytest.mark.parametrize("which", ["random", "calibrated"])
-def test_render_bf16_delta_psnr(ops, which, golden_fern):
-    """BASELINE frame in the bf16 tier: |PSNR(ours, gt) - PSNR(fp32 tier, gt)| <= 0.05 dB (north-star bound);
-    the fp32 tier itself is pinned to the reference at 1e-3 by test_full_frame_504x378."""
+def test_render_bf16_delta_psnr(ops, which, S, golden_fern):
+    """The north-star tolerance of the tensor-core tier on the BASELINE frame (504x378), both weight sets, S in {4, 8, 16}:
+
+    * |PSNR(fp16 tier, target) - PSNR(fp32 tier, target)| <= 0.05 dB against a target at which the render sits at ~28 dB (the
+      reference's fp32 frame + seeded noise, tests/util.noisy_target) -- at that quality 0.05 dB needs a cross-PSNR of ~47 dB;
+    * PSNR(fp16 tier, reference fp32 frame) >= measured - 3 dB (tests/util.FP16_TIER_CROSS_PSNR_FLOOR_DB): rejects bf16 operands
+      in ANY of the three networks (CPU-emulated bf16: 12-22 dB below the floors; tests/test_oracle_properties.py shows it);
+    * the fp32 tier on the same frame: <= 1e-3 on every ray whose sort order (trt.py:632) equals the reference's; the few rays
+      where near-tied depths sort the other way are a discontinuity of the reference algorithm itself (add / mul are gathered
+      by the permutation, trt.py:634-635) and the reference's own CUDA run flips them against its CPU run just the same."""
     _bf16_ready(ops)
-    from pronerf_b200.render import prepare_view, render
-    from tests.util import psnr
-    scene = synth.make_scene(factor=8)
-    sd = synth.make_weights(seed=0, calibrated=(which == "calibrated"))
-    out = {}
-    view = int(scene.i_test[0])
-    for prec in ("fp32", "bf16"):
-        nets = make_modules(sd, DEV, precision=prec)
-        kw = make_kwargs(nets, scene, DEV, precision=prec)
-        with torch.no_grad():
-            rays, or_rays, sh = prepare_view(scene.poses[view], scene.hwf, scene.K, kw)
-            rgb, _, depth, _ = render(rays, or_rays, sh, **call_kwargs(kw))
-        out[prec] = (rgb.cpu().numpy(), depth.cpu().numpy())
-    gt = scene.gt_image(view)
-    p32, p16 = psnr(out["fp32"][0], gt), psnr(out["bf16"][0], gt)
-    cross = psnr(out["bf16"][0], out["fp32"][0])
-    print(f"[{which}] PSNR vs gt: fp32 {p32:.4f} dB, bf16 {p16:.4f} dB, delta {abs(p32 - p16):.4f}; bf16 vs fp32 {cross:.1f} dB, "
-          f"max-abs rgb diff {np.abs(out['bf16'][0] - out['fp32'][0]).max():.3e}")
-    assert abs(p32 - p16) <= 0.05
-    assert cross >= (38.0 if which == "calibrated" else 70.0)      # calibrated = deliberately ill-conditioned heads (x30, x60)
-    assert np.isfinite(out["bf16"][0]).all() and np.isfinite(out["bf16"][1]).all()
-    if which == "calibrated":
+    from tests.util import FP16_TIER_CROSS_PSNR_FLOOR_DB, psnr, tier_parity_case
+    m, out, _ = tier_parity_case(which, S, DEV)
+    print(m)
+    assert m["finite"]
+    assert 25.0 <= m["target_psnr_fp32_tier_db"] <= 30.0
+    assert m["delta_psnr_db"] <= 0.05
+    assert m["fp16_tier_cross_psnr_db"] >= FP16_TIER_CROSS_PSNR_FLOOR_DB[(which, S)]
+    assert m["fp32_tier_max_abs_same_sort_order"] <= 1e-3
+    assert m["fp32_tier_rays_with_other_sort_order"] <= 2e-4 * m["rays"]
+    if which == "calibrated" and S == 8:
         g = golden_fern
-        idx = g["idx"]
-        assert psnr(out["bf16"][0].reshape(-1, 3)[idx], g["rgb_subset"]) >= 38.0          # vs the reference's own render
+        assert psnr(out["bf16"][0][g["idx"]], g["rgb_subset"]) >= FP16_TIER_CROSS_PSNR_FLOOR_DB[(which, S)] - 3.0    # vs the reference's own render
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

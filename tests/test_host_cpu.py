@@ -154,11 +154,18 @@ def _gloo_worker(rank, world, port, H, W, q):
         row0, nrows = shard_rows(H, world, rank)
         band = full[row0 * W:(row0 + nrows) * W]
         rgb, depth = gather_frame(band[:, :3].contiguous(), band[:, 3].contiguous(), H, W, dst=0)
+        # a batch of V views, each rank holding its band of every view (view after view): the bench's sharded step
+        V = 3
+        fullv = torch.arange(V * H * W * 4, dtype=torch.float32).reshape(V, H * W, 4)
+        bandv = fullv[:, row0 * W:(row0 + nrows) * W].reshape(-1, 4)
+        rgbv, depthv = gather_frame(bandv[:, :3].contiguous(), bandv[:, 3].contiguous(), H, W, dst=0, n_views=V)
         if rank == 0:
             ok = torch.equal(rgb.reshape(-1, 3), full[:, :3]) and torch.equal(depth.reshape(-1), full[:, 3])
+            ok = ok and rgbv.shape == (V, H, W, 3) and torch.equal(rgbv.reshape(V, -1, 3), fullv[..., :3]) \
+                and torch.equal(depthv.reshape(V, -1), fullv[..., 3])
             q.put(bool(ok))
         else:
-            assert rgb is None and depth is None
+            assert rgb is None and depth is None and rgbv is None
     finally:
         dist.destroy_process_group()
 

@@ -7,6 +7,7 @@ import torch
 from hypothesis import given, settings, strategies as st
 
 from oracle import pronerf_oracle as O
+from pronerf_b200 import synth
 
 S = 8
 
@@ -83,3 +84,32 @@ def test_frequency_encoding_is_bounded(seed):
     e = O.embed(x, 10)
     assert e.shape == (33, 63) and torch.equal(e[:, :3], x) and float(e[:, 3:].abs().max()) <= 1.0
     assert torch.allclose(e[:, 3:6] ** 2 + e[:, 6:9] ** 2, torch.ones(33, 3), atol=1e-5)
+
+
+def test_fp16_tier_floor_rejects_bf16_operands():
+    """The cross-PSNR floor the GPU test asserts for the tensor-core tier (tests/util.FP16_TIER_CROSS_PSNR_FLOOR_DB, measured on
+    B200 - 3 dB) sits BETWEEN what fp16-rounded and bf16-rounded MLP operands give on the same frame: the CPU oracle with
+    fp16-rounded operands passes it, with bf16-rounded operands it fails it by > 10 dB -- so does the 0.05 dB delta-PSNR bound.
+    (One case on CPU for time: calibrated weights, S = 4, the full 504x378 view.)"""
+    import torch
+    from oracle import pronerf_oracle as O
+    from tests.util import FP16_TIER_CROSS_PSNR_FLOOR_DB, noisy_target, psnr
+    which, S = "calibrated", 4
+    scene = synth.make_scene(factor=8)
+    sd = synth.make_weights(seed=0, N_samples=S, calibrated=True)
+    c2w = scene.poses[int(scene.i_test[0])]
+    got = {}
+    try:
+        for name, dt in (("fp32", None), ("fp16", torch.float16), ("bf16", torch.bfloat16)):
+            O.OPERAND_ROUND = None if dt is None else (lambda t, dt=dt: t.to(dt).float())
+            with torch.no_grad():
+                got[name] = O.render_view(sd, scene, c2w, S=S)[0]["rgb_map"].numpy().reshape(-1, 3)
+    finally:
+        O.OPERAND_ROUND = None
+    floor = FP16_TIER_CROSS_PSNR_FLOOR_DB[(which, S)]
+    assert psnr(got["fp16"], got["fp32"]) >= floor
+    assert psnr(got["bf16"], got["fp32"]) <= floor - 10.0
+    gt = noisy_target(got["fp32"], seed=S)
+    base = psnr(got["fp32"], gt)
+    assert 25.0 <= base <= 30.0
+    assert abs(psnr(got["fp16"], gt) - base) <= 0.05 < abs(psnr(got["bf16"], gt) - base)

@@ -91,6 +91,13 @@ def write_synthetic_llff(root, n_views=12, H=24, W=32, factor=2, seed=0, n_point
 
 
 # ----------------------------------------------------------------------------- fp16 tensor-core tier vs the reference frame
+# Floors of PSNR(fp16 tier, reference fp32 frame) at 504x378 = measured on B200 (profiles/r02_parity.json) - 3 dB.  The CPU oracle
+# with fp16-ROUNDED operands lands within 1.3 dB of the measured values (the kernel is as exact as fp16 operands allow); with
+# bf16-rounded operands it gives 83.3 / 79.4 / 71.5 (random) and 45.1 / 41.7 / 47.8 dB (calibrated): every floor rejects a bf16 kernel.
+FP16_TIER_CROSS_PSNR_FLOOR_DB = {("random", 4): 94.0, ("random", 8): 94.0, ("random", 16): 79.5,
+                                 ("calibrated", 4): 58.5, ("calibrated", 8): 61.0, ("calibrated", 16): 63.5}
+# fp16 tier, per network, against the reference's fp32 outputs on identical inputs: 2x the measured (max, rms) relative errors
+FP16_TIER_MLP_REL_BOUND = (2.5e-3, 1.1e-3)
 TARGET_PSNR_DB = 28.0          # a realistic render quality: the noise target puts the fp32 tier at 25-30 dB
 
 
