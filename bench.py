@@ -52,7 +52,7 @@ S, P, NN = 8, 48, 4
 WORKLOAD = ("ProNeRF stage-2 infer, fern-shaped 504x378, 3 test views (571536 rays/step), S=8, P=48, NN=4, "
             "random-init sampler+refine+DoNeRFTRT")
 # kernels launched by one pn_render_rays call: fp16 tier = sampler MLP, fused refine-input, refine MLP, interval refine,
-# dirterm pre-pass, NeRF MLP, composite; fp32 tier = 8 stage kernels + one extra gather per additional view
+# view-direction pre-pass, NeRF MLP, composite; fp32 tier = 8 stage kernels + one extra gather per additional view
 LAUNCHES_PER_STEP = {"fp16": 7, "fp32": 10}
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_nerf_traffic.json")
 

@@ -214,6 +214,14 @@ int pn_composite_stage1(const float* raw, const float* z, const float* rays, int
 int pn_explore_samples(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, float* z,
                        float* query, pn_stream_t stream);
 
+/* The same step as the stage-1 TRAINING forward runs it (base.py:689-730, randomize=True, train_sampler=False), with the
+ * reference's random draws as inputs so that it is reproducible: n_mult (random.randint(1, 64/S), base.py:690-691),
+ * dir1_forward (random.random() > 0.5, base.py:697: spread towards the next sample / far, else towards the previous / near),
+ * noise [N, S*n_mult] = abs(normal(0,1)/5) clamped at 0.99 (base.py:716-718; NULL = no jitter), dir2_forward (base.py:719).
+ * z [N, S*n_mult] (replicas sorted like torch.sort, base.py:709; the jittered values are not re-sorted), query = o + dir * z. */
+int pn_explore_samples_rand(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, int dir1_forward,
+                            const float* noise, int dir2_forward, float* z, float* query, pn_stream_t stream);
+
 /* ---- per-view prep (trt.py:245-278; helpers.py:2705-2714, 2776-2793) ---------------------------- */
 /* get_rays + viewdir normalise + ndc_rays for one H x W view.  c2w [3,4] row-major HOST floats,
  * K: fx, fy, cx, cy as doubles.  rays [N,11] = (o_ndc, d_ndc, near, far, viewdir); or_rays [N,11] =

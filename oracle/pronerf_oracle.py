@@ -13,7 +13,9 @@ restatement against those vectors (bit-exact for the sort permutation, the proje
 coordinates and the bilinear tap indices; <=1e-6 for floating-point stages).  The reference has no
 tests or golden vectors of its own.
 
-Later additions: ``nerf_classic_forward`` is pinned to the reference's own ``NeRF`` module
+Later additions: ``explore_samples_random`` (the stage-1 exploration step with its random draws as arguments) is pinned to
+the reference's own training-mode ``render_rays`` under fixed seeds (``oracle/make_golden_explore.py`` ->
+``tests/golden/stage1_explore.npz``); ``nerf_classic_forward`` is pinned to the reference's own ``NeRF`` module
 (``oracle/make_golden_nerf_classic.py`` -> ``tests/golden/nerf_classic.npz``); the LLFF loader restatement lives in the
 package (host-side I/O, ``pronerf_b200/llff_io.py``) and is pinned to the reference's loader by
 ``oracle/make_golden_llff.py``.  **Parity unpinned** for ``explore_samples`` / ``stage1_forward``: the reference's
@@ -397,6 +399,33 @@ def explore_samples(rays_o, rays_d, depth, far, n_mult):
         z, _ = torch.sort(z, dim=-1)
     else:
         z = depth
+    return z, rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+
+
+def explore_samples_random(rays_o, rays_d, depth, near, far, n_mult, dir1_forward, noise, dir2_forward):
+    """run_S_eS_eN_alter_base.py:689-730 (randomize=True, train_sampler=False) with the reference's random draws as arguments:
+    ``n_mult`` (:690-691), ``dir1_forward`` (:697), ``noise`` = the clamped abs(normal/5) tensor [N, S*n_mult] (:716-718, or None)
+    and ``dir2_forward`` (:719).  Pinned to the reference's own render_rays by oracle/make_golden_explore.py."""
+    N, S = depth.shape
+    if n_mult > 1:
+        mults = torch.linspace(0, 1 - 1 / n_mult, n_mult).to(depth).unsqueeze(0)
+        if dir1_forward:
+            diff = torch.abs(depth - torch.cat((depth[:, 1:], far * torch.ones(N, 1).type_as(depth)), 1))
+            noise_ = mults[:, None, :] * diff[:, :, None]
+        else:
+            diff = torch.abs(depth - torch.cat((near * torch.ones(N, 1), depth[:, 0:-1].type_as(depth)), 1))
+            noise_ = -mults[:, None, :] * diff[:, :, None]
+        z = (depth[:, :, None] + noise_).view(N, S * n_mult)
+        z, _ = torch.sort(z, dim=-1)
+    else:
+        z = depth
+    if noise is not None:
+        if dir2_forward:
+            diff = torch.abs(z - torch.cat((z[:, 1:], far * torch.ones(N, 1).type_as(z)), 1))
+            z = z + noise * diff
+        else:
+            diff = torch.abs(z - torch.cat((near * torch.ones(N, 1), z[:, 0:-1].type_as(z)), 1))
+            z = z + (-noise) * diff
     return z, rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
 
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "pn_composite": (_i, [_p, _p, _p, _i, _i, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pn_composite_stage1": (_i, [_p, _p, _p, _i, _i, _p, _p, _f, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "pn_explore_samples": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _p]),
+    "pn_explore_samples_rand": (_i, [_p, _i, _p, _i64, _i, _i, _i, _p, _i, _p, _p, _p]),
     "pn_raygen": (_i, [_i, _i, _d, _d, _d, _d, C.POINTER(_f), _f, _f, _f, _f, _i, _i, _p, _p, _p]),
     "pn_peer_alloc": (_i, [_i, C.c_size_t, C.POINTER(_p), C.c_char_p]),
     "pn_peer_open": (_i, [_i, C.c_char_p, C.POINTER(_p)]),

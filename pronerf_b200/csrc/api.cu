@@ -233,6 +233,9 @@ static int classic_precision_ok(int precision, const char* who) {
 }
 
 // ------------------------------------------------------------------------------------------------ MLP entry points
+static int run_network_impl(pn_ctx_t* c, const float* pts, const float* viewdirs, int viewdir_stride, int64_t N, int S, float* raw,
+                            int precision, pn_stream_t stream, const float* dirterm_ready);
+
 static void heads_sampler(MlpLaunch& L, int S) {
   L.head_lo[0] = 0; L.head_lo[1] = S; L.head_lo[2] = 3 * S; L.head_lo[3] = 3 * S + 3;
   L.head_act[0] = HEAD_SIGMOID; L.head_act[1] = HEAD_NONE; L.head_act[2] = HEAD_SIGMOID;
@@ -332,6 +335,13 @@ int pn_nerf_forward(pn_ctx_t* c, const float* embedded, const float* embedded_di
 
 int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int viewdir_stride, int64_t N, int S, float* raw,
                    int precision, pn_stream_t stream) {
+  return run_network_impl(c, pts, viewdirs, viewdir_stride, N, S, raw, precision, stream, nullptr);
+}
+}  // extern "C"
+
+// dirterm_ready: the per-ray view-direction term of DoNeRFTRT's last layer, already on the device (composed path), or NULL
+static int run_network_impl(pn_ctx_t* c, const float* pts, const float* viewdirs, int viewdir_stride, int64_t N, int S, float* raw,
+                            int precision, pn_stream_t stream, const float* dirterm_ready) {
   if (N == 0) return PN_OK;            // empty batch
   PN_REQUIRE(c && pts && viewdirs && raw && N >= 0 && S >= 1 && viewdir_stride >= 3, "pn_run_network: bad arguments");
   if (c->nerf_classic.loaded) {
@@ -346,9 +356,12 @@ int pn_run_network(pn_ctx_t* c, const float* pts, const float* viewdirs, int vie
   if (rc != PN_OK) return rc;
   MlpLaunch L{};
   L.act = 0; L.input_mode = IN_ENCODE; L.in0 = pts; L.in1 = viewdirs; L.in_stride = 3; L.in1_stride = viewdir_stride; L.S = S; L.P = 0; L.M = N * S; L.out = raw;
+  L.dirterm_ready = dirterm_ready;
   heads_none(L);
   return run_mlp(c, PN_NET_NERF, L, precision, as_stream(stream));
 }
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------------ the whole path
 // Scratch layout per ray (floats): heads 3S+3 | depth S | add S | mul S | depth3d S | refine_in 6S+3NN*S |
@@ -391,7 +404,7 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
   // carve the arena; every sub-buffer starts on a 256-byte boundary (float4 / bulk accesses need 16)
   auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
   const size_t nN = (size_t)N;
-  const size_t total = al(nN * hs) + 4 * al(nN * S) + al(nN * ri) + al(nN * ro) + al(nN * S) + al(nN * 3 * S) + al(nN * 4 * S);
+  const size_t total = al(nN * hs) + 4 * al(nN * S) + al(nN * ri) + al(nN * ro) + al(nN * S) + al(nN * 3 * S) + al(nN * 4 * S) + al(nN);
   rc = ensure(&c->scratch, &c->scratch_floats, total);
   if (rc != PN_OK) return rc;
   float* p = c->scratch;
@@ -404,7 +417,8 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
   float* rout = p;       p += al(nN * ro);
   float* z = p;          p += al(nN * S);
   float* query = p;      p += al(nN * 3 * S);
-  float* raw = p;
+  float* raw = p;        p += al(nN * 4 * S);
+  float* dnorm = p;
 
   cudaEvent_t* pe = nullptr;
   if (c->profile) {
@@ -464,16 +478,19 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
   }
   PN_STAGE_MARK(5);
   // (5) interval refinement + offsets  trt.py:671-681
-  rc = pn_interval_refine(f->rays, 11, depth, rout, ro, N, S, z, query, stream);
+  // (the same kernel leaves ||d_ndc|| for the compositing kernel.  Measured and dropped: also computing the NeRF last layer's
+  //  per-ray view-direction term here -- one lane of a ray's S doing 12 sincosf + 108 FMAs while the others idle made this
+  //  kernel 0.088 ms longer per 3-view step to save a 0.030 ms launch)
+  rc = interval_refine_dnorm(f->rays, 11, depth, rout, ro, N, S, z, query, dnorm, st);
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(6);
   // (6) encode + NeRF MLP  trt.py:691 ; viewdirs = rays[:, 8:11]
-  rc = pn_run_network(c, query, f->rays + 8, 11, N, S, raw, f->precision, stream);
+  rc = run_network_impl(c, query, f->rays + 8, 11, N, S, raw, f->precision, stream, nullptr);
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(7);
   // (7) composite  trt.py:694
   rc = composite_mapped(raw, z, f->rays, 11, 3, add, mul, 0.f, N, S, f->rgb, f->depth, nullptr, nullptr, nullptr, rpv,
-                        f->out_view_stride, ray_base, st);
+                        f->out_view_stride, ray_base, st, dnorm);
   if (rc != PN_OK) return rc;
   PN_STAGE_MARK(8);
 #undef PN_STAGE_MARK

@@ -77,6 +77,8 @@ struct MlpLaunch {
   float* out;              // [M, out_dim]
   int head_lo[4];          // column ranges [head_lo[i], head_lo[i+1]) get head_act[i]
   int head_act[3];
+  const float* dirterm_ready;   // tensor-core NeRF (IN_ENCODE): the per-ray view-direction term [M/S,4] has already been computed
+                                // (by the interval-refinement kernel of the composed path): skip the pre-pass launch
 };
 
 int launch_mlp_f32(const MlpLaunch& L, cudaStream_t stream);
@@ -114,7 +116,41 @@ int launch_refine_input_f16(const float* heads, int head_stride, const float* ra
 // raw2outputs (elementwise.cu) with output rows placed for banded multi-view batches (pn_frame_t.out_view_stride)
 int composite_mapped(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
                      const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
-                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st);
+                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st,
+                     const float* dnorm = nullptr);
+// pn_interval_refine that also writes ||d_ndc|| per ray (dnorm [N]) for composite_mapped: the compositing kernel then reads 4 B
+// per ray instead of pulling a 44-byte ray row through 32-byte sectors for 12 of its bytes
+// ... and, when wdir != NULL, the NeRF last layer's per-ray view-direction term dirterm [N,4] = W7[:, 256:283] . gamma_4(viewdir)
+// (viewdir = rays[:, 8:11]; wdir = the 4 x 27 fp32 weights, tc_wdir()), which saves the tensor-core tier its pre-pass launch
+int interval_refine_dnorm(const float* rays, int ray_stride, const float* depth, const float* refine_out, int refine_stride, int64_t N,
+                          int S, float* z, float* query, float* dnorm, cudaStream_t st, const float* wdir = nullptr,
+                          float* dirterm = nullptr);
+
+// View-direction term of DoNeRFTRT's last layer for one ray, fp32: o[k] = sum_j W7[k][256 + j] * gamma_4(v)[j]
+// (helpers.py:666-671 with L = 4: [v, sin(2^l v), cos(2^l v)]_{l<4}; s_w = the 4 x 27 weights)
+__device__ __forceinline__ float4 dirterm_of(const float* __restrict__ v, const float* __restrict__ s_w) {
+  const float d[3] = {v[0], v[1], v[2]};
+  float g[27];
+  g[0] = d[0]; g[1] = d[1]; g[2] = d[2];
+#pragma unroll
+  for (int l = 0; l < 4; ++l)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(d[c] * (float)(1 << l), &s, &co);
+      g[3 + 6 * l + c] = s;
+      g[6 + 6 * l + c] = co;
+    }
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 27; ++j) a = fmaf(s_w[k * 27 + j], g[j], a);
+    o[k] = a;
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Accurate fp32 helpers shared by kernels.  Nothing here may be compiled with --use_fast_math.

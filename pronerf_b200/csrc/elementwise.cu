@@ -178,9 +178,21 @@ __global__ void refine_pluecker_kernel(const float* __restrict__ rays, int ray_s
 }
 
 // ------------------------------------------------------------------------------------------------ interval refine
+// ||d|| of the NDC direction, the factor of raw2outputs' distances (trt.py:578): ONE definition for the kernel that can precompute
+// it (interval refinement reads the ray row anyway) and the compositing kernel, so that both forms give the same bits
+__device__ __forceinline__ float ray_dir_norm(const float* __restrict__ rd) {
+  return sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+}
+
 __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth,
                                        const float* __restrict__ ro, int ro_stride, int64_t N, int S,
-                                       float* __restrict__ z, float* __restrict__ q) {
+                                       float* __restrict__ z, float* __restrict__ q, float* __restrict__ dnorm,
+                                       const float* __restrict__ wdir, float* __restrict__ dirterm) {
+  __shared__ float s_w[4 * 27];
+  if (wdir) {                                                // uniform over the grid
+    if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];
+    __syncthreads();
+  }
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * S) return;
   int64_t r = t / S;
@@ -194,6 +206,9 @@ __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_s
   float frac = ro[r * ro_stride + s];
   float zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), frac));
   if (z) z[t] = zz;
+  if (dnorm && s == 0) dnorm[r] = ray_dir_norm(ray + 3);     // for the compositing kernel: 4 B/ray instead of a 44-byte ray row
+  // the NeRF last layer's view-direction term, once per ray, by the ray's LAST sample lane (the first one wrote dnorm)
+  if (dirterm && s == S - 1) *reinterpret_cast<float4*>(dirterm + r * 4) = dirterm_of(ray + 8, s_w);
   const float* off = ro + r * ro_stride + S + 3 * s;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -222,6 +237,75 @@ __global__ void explore_samples_kernel(const float* __restrict__ rays, int ray_s
   z[t] = zz;
 #pragma unroll
   for (int c = 0; c < 3; ++c) q[t * 3 + c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+}
+
+// The TRAINING-time form of the same step (base.py:689-729, randomize=True, train_sampler=False) with the reference's random draws
+// as INPUTS: n_mult = random.randint(1, 64/S); dir1 = random.random() > 0.5 (spread towards the next sample / far, else back
+// towards the previous sample / near); noise [N, S*n_mult] = the |N(0,1)|/5 draw clamped at 0.99 (base.py:716-718; NULL = none);
+// dir2 = the second random.random() > 0.5.  One warp per ray:
+//   z1[s*n+m] = d_s +- mult_m * |d_s - d_(s+-1)|   (base.py:694-707),  sorted ascending (torch.sort, base.py:709),
+//   z [j]     = z1[j] +- noise[j] * |z1[j] - z1[j+-1]|   with far / near beyond the ends (base.py:719-728; NOT re-sorted),
+//   q [j]     = o + dir * z[j]                           (base.py:730).
+// The sort is a rank sort through shared memory (<= 64 values): in the forward case the values are ascending by construction
+// except where a rounded gap lifts the last replica of a sample one ulp above the next sample; torch.sort orders those too.
+__global__ void __launch_bounds__(256)
+explore_samples_rand_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth, int64_t N, int S,
+                            int n_mult, float mult_end, int dir1_fwd, const float* __restrict__ noise, int dir2_fwd,
+                            float* __restrict__ z, float* __restrict__ q) {
+  __shared__ float s_a[8][64], s_b[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + w;
+  if (r >= N) return;
+  const int So = S * n_mult;
+  const float* ray = rays + r * ray_stride;
+  const float* d = depth + r * S;
+  const float near_ = ray[6], far_ = ray[7];
+  for (int j = lane; j < So; j += 32) {
+    const int s = j / n_mult, m = j - s * n_mult;
+    const float dc = d[s];
+    float v = dc;
+    if (n_mult > 1) {
+      const float mult = linspace_step(m, n_mult, mult_end);
+      if (dir1_fwd) {
+        const float dn = (s + 1 < S) ? d[s + 1] : far_;
+        v = __fadd_rn(dc, __fmul_rn(mult, fabsf(__fsub_rn(dc, dn))));
+      } else {
+        const float dp = (s > 0) ? d[s - 1] : near_;
+        v = __fadd_rn(dc, __fmul_rn(-mult, fabsf(__fsub_rn(dc, dp))));
+      }
+    }
+    s_a[w][j] = v;
+  }
+  __syncwarp();
+  for (int j = lane; j < So; j += 32) {                      // stable ascending rank (NaN last, like torch.sort)
+    const float v = s_a[w][j];
+    int rank = 0;
+    for (int i = 0; i < So; ++i) {
+      const float u = s_a[w][i];
+      const bool before = (u < v) || (!(u != u) && (v != v)) || ((u == v || ((u != u) && (v != v))) && i < j);
+      rank += before ? 1 : 0;
+    }
+    s_b[w][rank] = v;
+  }
+  __syncwarp();
+  for (int j = lane; j < So; j += 32) {
+    const float zc = (n_mult > 1) ? s_b[w][j] : s_a[w][j];
+    float zz = zc;
+    if (noise) {
+      const float* zs = (n_mult > 1) ? s_b[w] : s_a[w];
+      const float nz = noise[r * So + j];
+      if (dir2_fwd) {
+        const float zn = (j + 1 < So) ? zs[j + 1] : far_;
+        zz = __fadd_rn(zc, __fmul_rn(nz, fabsf(__fsub_rn(zc, zn))));
+      } else {
+        const float zp = (j > 0) ? zs[j - 1] : near_;
+        zz = __fadd_rn(zc, __fmul_rn(-nz, fabsf(__fsub_rn(zc, zp))));
+      }
+    }
+    z[r * So + j] = zz;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) q[(r * So + j) * 3 + c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ compositing
@@ -258,7 +342,8 @@ __global__ void composite_scan_kernel(const float* __restrict__ raw, const float
                                       const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                       const float* __restrict__ add, const float* __restrict__ mul, int64_t N,
                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om) {
+                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om,
+                                      const float* __restrict__ dnorm) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one (ray, sample) per thread
   int64_t r = t / S;
   int s = (int)(t % S);
@@ -268,8 +353,7 @@ __global__ void composite_scan_kernel(const float* __restrict__ raw, const float
   float4 rw = clamp_raw(reinterpret_cast<const float4*>(raw)[tt], raw_clamp);
   float zc = z[tt];
   float zn = __shfl_down_sync(0xffffffffu, zc, 1);                  // z_{s+1} (same segment when s < S-1)
-  const float* rd = rays + rr * ray_stride + ray_d_col;
-  float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  float dn = dnorm ? dnorm[rr] : ray_dir_norm(rays + rr * ray_stride + ray_d_col);
   float dist = (s == S - 1) ? 1e10f : (zn - zc);
   dist *= dn;
   float sig = fmaxf(rw.w + (add ? add[tt] : 0.f), 0.f);
@@ -311,11 +395,11 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
                                      const float* __restrict__ rays, int ray_stride, int ray_d_col,
                                      const float* __restrict__ add, const float* __restrict__ mul, int64_t N, int S,
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
-                                     float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om) {
+                                     float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om,
+                                     const float* __restrict__ dnorm) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
-  const float* rd = rays + r * ray_stride + ray_d_col;
-  float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  float dn = dnorm ? dnorm[r] : ray_dir_norm(rays + r * ray_stride + ray_d_col);
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wz = 0.f, ws = 0.f;
   for (int s = 0; s < S; ++s) {
     int64_t tt = r * S + s;
@@ -477,10 +561,28 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
   PN_REQUIRE(rays && depth && refine_out && query && N >= 0 && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S,
              "pn_interval_refine: bad arguments");
   interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, refine_out,
-                                                                               refine_stride, N, S, z, query);
+                                                                               refine_stride, N, S, z, query, nullptr, nullptr, nullptr);
   PN_LAUNCH_OK("pn_interval_refine");
   return PN_OK;
 }
+
+}  // extern "C"
+
+namespace pn {
+// pn_interval_refine for the composed path: also leaves ||d_ndc|| per ray for the compositing kernel
+int interval_refine_dnorm(const float* rays, int ray_stride, const float* depth, const float* refine_out, int refine_stride, int64_t N,
+                          int S, float* z, float* query, float* dnorm, cudaStream_t st, const float* wdir, float* dirterm) {
+  if (N == 0) return PN_OK;
+  PN_REQUIRE(rays && depth && refine_out && query && dnorm && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S, "interval_refine: bad arguments");
+  PN_REQUIRE((wdir == nullptr) == (dirterm == nullptr) && (!wdir || ray_stride >= 11), "interval_refine: wdir and dirterm go together (rays [N,11])");
+  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, st>>>(rays, ray_stride, depth, refine_out, refine_stride, N, S, z, query, dnorm,
+                                                                 wdir, dirterm);
+  PN_LAUNCH_OK("pn_interval_refine");
+  return PN_OK;
+}
+}  // namespace pn
+
+extern "C" {
 
 int pn_explore_samples(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, float* z, float* query,
                        pn_stream_t stream) {
@@ -494,13 +596,26 @@ int pn_explore_samples(const float* rays, int ray_stride, const float* depth, in
   return PN_OK;
 }
 
+int pn_explore_samples_rand(const float* rays, int ray_stride, const float* depth, int64_t N, int S, int n_mult, int dir1_forward,
+                            const float* noise, int dir2_forward, float* z, float* query, pn_stream_t stream) {
+  if (N == 0) return PN_OK;            // empty batch
+  PN_REQUIRE(rays && depth && z && query && N >= 0 && S >= 1 && n_mult >= 1 && S * n_mult <= 64 && ray_stride >= 8,
+             "pn_explore_samples_rand: bad arguments (S=%d n_mult=%d; S * n_mult <= 64 as in the reference, base.py:690)", S, n_mult);
+  const float mult_end = (float)(1.0 - 1.0 / (double)n_mult);
+  explore_samples_rand_kernel<<<(unsigned)((N + 7) / 8), 256, 0, as_stream(stream)>>>(rays, ray_stride, depth, N, S, n_mult, mult_end,
+                                                                                    dir1_forward ? 1 : 0, noise, dir2_forward ? 1 : 0, z, query);
+  PN_LAUNCH_OK("pn_explore_samples_rand");
+  return PN_OK;
+}
+
 }  // extern "C"
 
 namespace pn {
 // raw2outputs with the output rows placed by (rays_per_view, out_view_stride, ray_base): see OutMap
 int composite_mapped(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,
                      const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
-                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st) {
+                     float* weights, int64_t rays_per_view, int64_t out_view_stride, int64_t ray_base, cudaStream_t st,
+                     const float* dnorm) {
   if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
   PN_REQUIRE(raw && z && rays && rgb && depth && N >= 0 && S >= 1 && ray_stride >= ray_d_col + 3 && ((add == nullptr) == (mul == nullptr)),
              "pn_composite: bad arguments");
@@ -509,7 +624,7 @@ int composite_mapped(const float* raw, const float* z, const float* rays, int ra
   OutMap om{rays_per_view, out_view_stride, ray_base};
 #define PN_COMP(SS)                                                                                                  \
   composite_scan_kernel<SS><<<blocks_for(N * SS), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, \
-                                                                     rgb, depth, disp, acc, weights, raw_clamp, om)
+                                                                     rgb, depth, disp, acc, weights, raw_clamp, om, dnorm)
   switch (S) {
     case 2: PN_COMP(2); break;
     case 4: PN_COMP(4); break;
@@ -518,7 +633,7 @@ int composite_mapped(const float* raw, const float* z, const float* rays, int ra
     case 32: PN_COMP(32); break;
     default:
       composite_seq_kernel<<<blocks_for(N), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, S, rgb,
-                                                              depth, disp, acc, weights, raw_clamp, om);
+                                                              depth, disp, acc, weights, raw_clamp, om, dnorm);
   }
 #undef PN_COMP
   PN_LAUNCH_OK("pn_composite");
@@ -532,7 +647,7 @@ int pn_composite_stage1(const float* raw, const float* z, const float* rays, int
                         const float* mul, float raw_clamp, int64_t N, int S, float* rgb, float* depth, float* disp, float* acc,
                         float* weights, pn_stream_t stream) {
   return pn::composite_mapped(raw, z, rays, ray_stride, ray_d_col, add, mul, raw_clamp, N, S, rgb, depth, disp, acc, weights, 0, 0, 0,
-                              as_stream(stream));
+                              as_stream(stream), nullptr);
 }
 
 int pn_composite(const float* raw, const float* z, const float* rays, int ray_stride, int ray_d_col, const float* add,

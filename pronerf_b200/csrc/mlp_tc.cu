@@ -1193,24 +1193,13 @@ __global__ void dirterm_kernel(const float* __restrict__ in, int stride, int mod
   if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float g[27];
     if (mode == 0) {
-      const float* v = in + i * stride;
-      const float d[3] = {v[0], v[1], v[2]};
-      g[0] = d[0]; g[1] = d[1]; g[2] = d[2];
-#pragma unroll
-      for (int l = 0; l < 4; ++l)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float s, co;
-          sincosf(d[c] * (float)(1 << l), &s, &co);
-          g[3 + 6 * l + c] = s;
-          g[6 + 6 * l + c] = co;
-        }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 27; ++j) g[j] = in[i * stride + j];
+      *reinterpret_cast<float4*>(out + i * 4) = dirterm_of(in + i * stride, s_w);
+      continue;
     }
+    float g[27];
+#pragma unroll
+    for (int j = 0; j < 27; ++j) g[j] = in[i * stride + j];
     float o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1262,6 +1251,12 @@ static TcLayout tc_layout(int net_id, int n_layers, const int* in_dims, const in
   L.wdir_off = L.bias_off + (size_t)n_layers * kHidden * 4;
   L.total = L.wdir_off + 4 * 28 * 4;
   return L;
+}
+
+const float* tc_wdir(const NetTC& n) {
+  if (!n.loaded || n.classic || n.net_id != PN_NET_NERF || !n.blob) return nullptr;
+  const TcLayout L = tc_layout(n.net_id, n.n_layers, n.in_dim, n.out_dim);
+  return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(n.blob) + L.wdir_off);
 }
 
 void tc_free_net(NetTC& n) {
@@ -1519,7 +1514,10 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   if (p.shift > np - 1) p.shift = np - 1;
 
   // NeRF: view-direction term of the last layer, fp32, one row per ray (run_network) or per sample (forward)
-  if (n.net_id == PN_NET_NERF) {
+  if (n.net_id == PN_NET_NERF && Lc.input_mode == IN_ENCODE && Lc.dirterm_ready) {
+    p.dirterm = Lc.dirterm_ready;                           // computed upstream (interval_refine_dnorm)
+    p.dir_div = Lc.S > 0 ? Lc.S : 1;
+  } else if (n.net_id == PN_NET_NERF) {
     const long long rows = Lc.input_mode == IN_ENCODE ? Lc.M / (Lc.S > 0 ? Lc.S : 1) : Lc.M;
     if ((size_t)rows > n.dirterm_rows) {
       if (n.dirterm) cudaFree(n.dirterm);

@@ -26,6 +26,8 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
 bool tc_available();
 void tc_set_timeline(long long* dev_buf);   // debug: clock64 stamps of CTA 0's second tile (208 slots)
 int tc_launch_mlp(NetTC& n, const MlpLaunch& L, cudaStream_t stream);
+// device pointer to the 4 x 27 fp32 view-direction weights of a loaded DoNeRFTRT (NULL: not loaded / classic topology)
+const float* tc_wdir(const NetTC& n);
 // classic NeRF (helpers.py:792-847) on the tensor-core tier: 12 tensors in checkpoint order; run_network form only
 int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, const float* const* W, const float* const* b,
                          cudaStream_t stream);

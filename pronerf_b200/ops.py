@@ -561,6 +561,26 @@ def explore_samples(rays, depth, n_mult: int):
     return z, q
 
 
+def explore_samples_rand(rays, depth, n_mult: int, dir1_forward: bool, noise=None, dir2_forward: bool = True):
+    """Stage-1 exploration sampling as the training forward runs it (base.py:689-730) with the random draws as inputs:
+    ``n_mult``, the two direction coin flips and ``noise`` [N, S*n_mult] (= abs(normal/5) clamped at 0.99; None = no jitter)
+    -> z [N, S*n_mult], query [N, S*n_mult, 3]."""
+    rays, depth = as_f32c(rays), as_f32c(depth)
+    N, S = depth.shape
+    So = S * int(n_mult)
+    if noise is not None:
+        noise = as_f32c(noise)
+        if tuple(noise.shape) != (N, So):
+            raise ValueError(f"noise must be [{N},{So}], got {tuple(noise.shape)}")
+    z = _empty((N, So), depth)
+    q = _empty((N, So, 3), depth)
+    with _cuda_guard(depth):
+        check(lib().pn_explore_samples_rand(dptr(rays, "rays"), rays.shape[1], dptr(depth, "depth"), N, S, int(n_mult), int(bool(dir1_forward)),
+                                            dptr(noise, "noise") if noise is not None else None, int(bool(dir2_forward)), dptr(z), dptr(q),
+                                            stream_ptr(depth.device)), "pn_explore_samples_rand")
+    return z, q
+
+
 def raygen(H, W, K, c2w, device, near=0., far=1., or_near=1., or_far=10., row0=0, nrows=None):
     """get_rays + ndc_rays for one view -> (rays [n,11], or_rays [n,11])  (trt.py:245-271)."""
     nrows = H - row0 if nrows is None else nrows

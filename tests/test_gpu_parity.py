@@ -519,6 +519,38 @@ def test_stage1_style_forward(ops, n_mult):
         assert torch.isfinite(rgb16).all() and p16 >= 60.0
 
 
+def test_exploration_sampling_random_branch(ops):
+    """SURVEY 8 f4, the randomised branch of the stage-1 forward (base.py:689-730): ``pn_explore_samples_rand`` fed the draws the
+    reference itself made under fixed seeds (tests/golden/stage1_explore.npz: n_mult, both coin flips, the normal jitter, recorded
+    while its unmodified ``render_rays(randomize=True)`` ran) -> sample depths and query points BIT-EXACT against what reached the
+    reference's NeRF; then classic NeRF + stage-1 compositing on them <= 1e-3 against the reference's returned rgb / depth maps."""
+    from pronerf_b200.engine import Renderer
+    from tests.conftest import load_golden
+    g = load_golden("stage1_explore.npz")
+    scene = synth.make_small_scene(H=12, W=16)
+    sd = synth.make_weights(seed=0, calibrated=True)
+    sd["network_fine_state_dict"] = synth.make_nerf_classic_weights(seed=0, calibrated=True)
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    rays = pv["rays"].to(DEV)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="fp32", device=DEV)
+    for i in range(int(g["n_cases"])):
+        n_mult, d1, d2 = int(g[f"c{i}_n_mult"]), bool(g[f"c{i}_dir1"]), bool(g[f"c{i}_dir2"])
+        z, q = ops.explore_samples_rand(rays, T(g[f"c{i}_depth_in"], DEV), n_mult, d1, T(g[f"c{i}_noise"], DEV), d2)
+        assert np.array_equal(z.cpu().numpy(), g[f"c{i}_z"]), (i, n_mult, d1, d2, np.abs(z.cpu().numpy() - g[f"c{i}_z"]).max())
+        assert np.array_equal(q.cpu().numpy(), g[f"c{i}_q"]), (i, n_mult, d1, d2)
+        raw = R.ctx.run_network(q, rays[:, 8:11].contiguous(), precision="fp32")
+        rgb, depth, _ = ops.composite_stage1(raw, z, rays[:, 3:6].contiguous())
+        np.testing.assert_allclose(rgb.cpu().numpy(), g[f"c{i}_rgb"], atol=1e-3, rtol=0, err_msg=f"case {i}")
+        np.testing.assert_allclose(depth.cpu().numpy(), g[f"c{i}_depth"], atol=1e-3, rtol=0, err_msg=f"case {i}")
+    # without jitter and forwards it is the deterministic variant
+    d_in = T(g["c0_depth_in"], DEV)
+    z0, q0 = ops.explore_samples(rays, d_in, 4)
+    z1, q1 = ops.explore_samples_rand(rays, d_in, 4, True, None, True)
+    assert torch.equal(torch.sort(z0, -1)[0], z1)
+    with pytest.raises(RuntimeError, match="n_mult"):
+        ops.explore_samples_rand(rays, d_in, 9, True, None, True)               # S * n_mult > 64: outside the reference's range
+
+
 def test_training_warp_and_mean_fill(ops):
     """the stage-2 training warp (iw.py:515-581) and the masked mean fill of its features (refine2.py:616-626):
     output vs the reference's own function (<= 2e-6), floor indices bit-exact vs the oracle, features vs the oracle."""

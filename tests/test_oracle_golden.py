@@ -223,3 +223,26 @@ def test_other_sample_counts_against_reference(S):
     np.testing.assert_allclose(r["rgb_map"].numpy().reshape(H, W, 3), g["rgb"], atol=1e-4, rtol=0)
     np.testing.assert_allclose(r["depth_map"].numpy().reshape(H, W), g["depth"], atol=1e-4, rtol=0)
     assert g["rgb"].max() - g["rgb"].min() > 0.2          # the calibrated weights exercise the range
+
+
+def test_exploration_sampling_against_reference_training_forward():
+    """SURVEY 8 f4, the randomised branch: ``oracle.explore_samples_random`` fed the reference's OWN draws (n_mult, both coin flips,
+    the normal jitter -- recorded while its unmodified stage-1 ``render_rays(randomize=True)`` ran under fixed seeds,
+    oracle/make_golden_explore.py) reproduces the sample depths and query points that reached the reference's NeRF, bit for bit;
+    6 cases covering n_mult = 1 / 2 / 3 / 5 and both directions of both flips."""
+    from pronerf_b200 import synth
+    from tests.conftest import load_golden
+    g = load_golden("stage1_explore.npz")
+    scene = synth.make_small_scene(H=12, W=16)
+    pv = O.prep_view(scene.H, scene.W, scene.K, g["c2w"], scene.poses_ref)
+    o, d = pv["rays"][:, 0:3], pv["rays"][:, 3:6]
+    near, far = pv["rays"][:, 6:7], pv["rays"][:, 7:8]
+    seen = set()
+    for i in range(int(g["n_cases"])):
+        n_mult, d1, d2 = int(g[f"c{i}_n_mult"]), bool(g[f"c{i}_dir1"]), bool(g[f"c{i}_dir2"])
+        seen.add((n_mult > 1, d1, d2))
+        z, q = O.explore_samples_random(o, d, torch.from_numpy(g[f"c{i}_depth_in"]), near, far, n_mult, d1, torch.from_numpy(g[f"c{i}_noise"]), d2)
+        assert z.shape == (o.shape[0], 8 * n_mult)
+        assert np.array_equal(z.numpy(), g[f"c{i}_z"]), (i, np.abs(z.numpy() - g[f"c{i}_z"]).max())
+        assert np.array_equal(q.numpy(), g[f"c{i}_q"]), i
+    assert len(seen) >= 5
