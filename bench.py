@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=190512, help="rays of the cpu_baseline sample (one full view)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (gather_nccl, view_parallel, config4, fp32_tier)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sharded step kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -254,14 +255,15 @@ def main():
     peer = multigpu.PeerFrame(H, W, dev, n_views=V) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     images_pinned = torch.from_numpy(np.ascontiguousarray(scene.images_ref)).pin_memory()
-    counter = [0]
+    graph = [None]
 
     def step_sharded():
         if peer is None:
             R.render_prepared(prep)
+        elif graph[0] is not None:
+            graph[0].replay()
         else:
-            counter[0] += 1
-            multigpu.render_views_sharded_p2p(R, prep, peer, counter[0])
+            multigpu.render_views_sharded_p2p(R, prep, peer)      # frame numbers are kept on the device (graph-replayable)
 
     def barrier():
         if dist is not None:
@@ -297,13 +299,38 @@ def main():
         clocks.start()
     for _ in range(args.warmup):
         step_sharded()
-    R.ctx.profile(True)
+    use_graph = peer is not None and not args.no_graph
+    if use_graph:
+        # N > 1: a rank's step is ~0.5 ms of kernels at N = 8, so the whole step (7 kernels + flag store + flag wait) is captured
+        # once and replayed; the per-stage events cannot live inside a graph, so the stage times come from a profiled leg below
+        barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            multigpu.render_views_sharded_p2p(R, prep, peer)
+        graph[0] = g
+        barrier()
+        for _ in range(2):
+            step_sharded()
+    else:
+        R.ctx.profile(True)
     t_wall0 = time.perf_counter()
     step_ms = timed(step_sharded, args.steps, 0)
     t_wall = time.perf_counter() - t_wall0
+    clock_info = clocks.stop() if rank == 0 else None
+    if use_graph:
+        graph[0] = None
+        R.ctx.profile(True)
+        timed(step_sharded, args.steps, 0)
     stage_frames = R.ctx.profile_read(256)
     R.ctx.profile(False)
-    clock_info = clocks.stop() if rank == 0 else None
+    # every rank's own kernel time per step (sum of its stage events): the spread is what rank 0's flag wait sees
+    own_ms = float(np.mean([sum(f.values()) for f in stage_frames[-args.steps:]])) if stage_frames else 0.0
+    if dist is not None:
+        own_all = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(own_all, torch.tensor([own_ms], device=dev, dtype=torch.float64))
+        own_all = [float(t.item()) for t in own_all]
+    else:
+        own_all = [own_ms]
     ms_per_step = max_over_ranks(sum(step_ms) / args.steps)
     value = n_rays_step / (ms_per_step / 1e3) / 1e6
     late = peer.late_rank() if peer is not None else None
@@ -402,7 +429,9 @@ def main():
             ms = max_over_ranks(sum(ms_all) / len(ms_all))
             n_big = big.H * big.W
             g_ms = float(np.mean([f["project_gather"] for f in fr[-3:]]))
-            bpr = refine_input_bytes_per_ray(S, NN, big.H, big.W, n_rays=n_big // world) if precision == "fp16" else gather_bytes_per_ray(S, NN, big.H, big.W, n_rays=n_big // world)
+            # compulsory bytes of this rank's tile: per-ray terms + its share of the texel set (a tile's rays project into about the
+            # same fraction of every reference view)
+            bpr = refine_input_bytes_per_ray(S, NN, big.H, big.W, n_rays=n_big) if precision == "fp16" else gather_bytes_per_ray(S, NN, big.H, big.W, n_rays=n_big)
             extras["config4"] = {"workload": f"one {big.W}x{big.H} fern-shaped frame ({n_big} rays), tiles over {world} GPU(s), gathered on rank 0",
                                  "value": n_big / ms / 1e3, "unit": UNIT, "ms_per_frame": ms, "gather_bytes": n_big * 16,
                                  "refine_input_kernel_ms_rank0": g_ms, "refine_input_gbs_rank0": bpr * (n_big / world) / g_ms / 1e6,
@@ -464,6 +493,8 @@ def main():
         "precision_tier": precision + (" operands, fp32 accumulate (tcgen05)" if precision == "fp16" else " SIMT"),
         "fps_504x378": value * 1e6 / n_view, "ms_per_view": ms_per_step / V, "wall_s_timed_region": t_wall,
         "rays_per_gpu_per_step": n_rays_rank, "gathered_frame_bit_identical_to_single_gpu": check,
+        "step_launch": ("one CUDA graph per rank (7 kernels + flag store + flag wait), replayed" if use_graph else "kernel by kernel"),
+        "kernel_ms_per_step_by_rank": own_all,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (R.image_bytes + V * (12 + 12 * NN) * 4)),
                 "d2h_bytes_per_step": int(n_rays_step * 16), "ms_per_step": e2e_step_ms, "frame_matches_device_path": e2e_check,
                 "api": "per rank: Renderer.set_images (pinned H2D + pack, copy stream) + Renderer.render_views_host_async -> "
@@ -472,6 +503,8 @@ def main():
         "gpu_launches": int(args.steps * launches),
         "roofline": roof, "roofline_gather": gather,
         "stage_ms_per_step_rank0": stage_avg,
+        "stage_ms_source": ("a separate profiled leg of K kernel-by-kernel steps (per-stage events cannot be recorded inside the replayed graph)"
+                            if use_graph else "per-stage CUDA events inside the timed region"),
         "mlp_tflops_all_three": (fl["total"] * n_rays_rank / (mlp_total_ms / 1e3) / 1e12) if mlp_total_ms else None,
         "algorithmic_flops_per_ray": fl, "executed_flops_per_ray": executed_flops_per_ray(S, P, NN),
         "cpu_baseline": cpu, "clocks": clock_info,

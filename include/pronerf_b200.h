@@ -314,9 +314,12 @@ int pn_peer_free(void* dev_ptr);
  * pn_peer_signal(&flags[r], step) (a system-scope release store over NVLink, ordered after the compositing kernel's stores by
  * the stream); the destination enqueues pn_peer_wait(flags, n, step, ...), a one-warp kernel that spins (acquire loads) until
  * every flag is >= step -- the frame is then complete in its memory without any host round trip or collective.  A watchdog
- * (timeout_ms) writes 1 + the late rank's index to *status_dev and lets the stream go on instead of hanging the GPU. */
-int pn_peer_signal(int* flag_dev, int step, pn_stream_t stream);
-int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, pn_stream_t stream);
+ * (timeout_ms) writes 1 + the late rank's index to *status_dev and lets the stream go on instead of hanging the GPU.
+ * step <= 0: the step number is kept on the device instead -- *counter_dev (local memory of the calling rank, zero-initialised;
+ * one counter for the signals, another for the waits) is advanced by the kernel itself, so that a CUDA graph holding the whole
+ * sharded step (render + signal + wait) can be captured once and replayed. */
+int pn_peer_signal(int* flag_dev, int step, int* counter_dev, pn_stream_t stream);
+int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, int* counter_dev, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,8 +71,8 @@ SIGNATURES = {
     "pn_peer_open": (_i, [_i, C.c_char_p, C.POINTER(_p)]),
     "pn_peer_close": (_i, [_p]),
     "pn_peer_free": (_i, [_p]),
-    "pn_peer_signal": (_i, [_p, _i, _p]),
-    "pn_peer_wait": (_i, [_p, _i, _i, _i, _p, _p]),
+    "pn_peer_signal": (_i, [_p, _i, _p, _p]),
+    "pn_peer_wait": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "pn_render_rays": (_i, [_p, C.POINTER(Frame), _p]),
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
                                   _p, _p, _p, _p]),

@@ -719,14 +719,21 @@ int pn_peer_open(int device, const unsigned char* handle64, void** dev_ptr) {
 }  // extern "C"
 
 namespace pn {
-__global__ void peer_signal_kernel(int* flag, int step) {
+__global__ void peer_signal_kernel(int* flag, int step, int* counter) {
+  // step <= 0: the step number lives on the device (counter, advanced here), so that a captured CUDA graph can be replayed
+  if (step <= 0) step = ++(*counter);
   // the compositing kernel's stores into the peer frame are complete (stream order); publish the step at system scope
   __threadfence_system();
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
 }
 
-__global__ void peer_wait_kernel(const int* flags, int n, int step, unsigned long long timeout_ns, int* status) {
+__global__ void peer_wait_kernel(const int* flags, int n, int step, unsigned long long timeout_ns, int* status, int* counter) {
   const int i = threadIdx.x;
+  if (step <= 0) {                                   // device-resident step number (graph replay): every lane reads, lane 0 advances
+    step = *counter + 1;
+    __syncwarp();
+    if (i == 0) *counter = step;
+  }
   if (i >= n) return;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -747,16 +754,18 @@ __global__ void peer_wait_kernel(const int* flags, int n, int step, unsigned lon
 
 extern "C" {
 
-int pn_peer_signal(int* flag_dev, int step, pn_stream_t stream) {
-  PN_REQUIRE(flag_dev, "pn_peer_signal: flag is NULL");
-  peer_signal_kernel<<<1, 1, 0, as_stream(stream)>>>(flag_dev, step);
+int pn_peer_signal(int* flag_dev, int step, int* counter_dev, pn_stream_t stream) {
+  PN_REQUIRE(flag_dev && (step > 0 || counter_dev), "pn_peer_signal: flag is NULL, or step <= 0 without a device counter");
+  peer_signal_kernel<<<1, 1, 0, as_stream(stream)>>>(flag_dev, step, counter_dev);
   PN_LAUNCH_OK("pn_peer_signal");
   return PN_OK;
 }
 
-int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, pn_stream_t stream) {
-  PN_REQUIRE(flags_dev && n_flags >= 1 && n_flags <= 32 && timeout_ms > 0, "pn_peer_wait: bad arguments (n_flags=%d)", n_flags);
-  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(flags_dev, n_flags, step, (unsigned long long)timeout_ms * 1000000ull, status_dev);
+int pn_peer_wait(const int* flags_dev, int n_flags, int step, int timeout_ms, int* status_dev, int* counter_dev, pn_stream_t stream) {
+  PN_REQUIRE(flags_dev && n_flags >= 1 && n_flags <= 32 && timeout_ms > 0 && (step > 0 || counter_dev),
+             "pn_peer_wait: bad arguments (n_flags=%d)", n_flags);
+  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(flags_dev, n_flags, step, (unsigned long long)timeout_ms * 1000000ull, status_dev,
+                                                    counter_dev);
   PN_LAUNCH_OK("pn_peer_wait");
   return PN_OK;
 }

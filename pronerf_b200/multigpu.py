@@ -136,6 +136,8 @@ class PeerFrame:
         self.depth = flat[n * 3:].view(n)
         self._flags_ptr = self._ptr + n * 16
         self._status_ptr = self._flags_ptr + self.MAX_RANKS * 4
+        # device-resident step numbers (this rank's own memory): [0] signals sent, [1] waits done -- for graph-replayed steps
+        self._counters = torch.zeros(2, dtype=torch.int32, device=self.device)
 
     def band(self, row0: int, nrows: int):
         """This rank's output tensors.  One view: the rows [row0, row0+nrows) of the destination frame.  V views: tensors that
@@ -153,21 +155,23 @@ class PeerFrame:
             return self.rgb.view(self.H, self.W, 3), self.depth.view(self.H, self.W)
         return self.rgb.view(self.V, self.H, self.W, 3), self.depth.view(self.V, self.H, self.W)
 
-    def signal(self, step: int):
-        """Enqueue 'my band of frame ``step`` has landed' (system-scope release store into the destination's flag)."""
+    def signal(self, step: int = 0):
+        """Enqueue 'my band of frame ``step`` has landed' (system-scope release store into the destination's flag).
+        ``step = 0``: the frame number is kept on the device and advanced by the kernel (graph-replayable); use one form only."""
         from . import _abi
         with torch.cuda.device(self.device):
-            _abi.check(self._lib.pn_peer_signal(C.c_void_p(self._flags_ptr + 4 * self.rank), int(step), _abi.stream_ptr(self.device)),
-                       "pn_peer_signal")
+            _abi.check(self._lib.pn_peer_signal(C.c_void_p(self._flags_ptr + 4 * self.rank), int(step), C.c_void_p(self._counters.data_ptr()),
+                                                _abi.stream_ptr(self.device)), "pn_peer_signal")
 
-    def wait_all(self, step: int, timeout_ms: int = 5000):
-        """Destination rank: make the current stream wait (on the device) until every rank has signalled ``step``."""
+    def wait_all(self, step: int = 0, timeout_ms: int = 5000):
+        """Destination rank: make the current stream wait (on the device) until every rank has signalled ``step``
+        (``step = 0``: the next frame of the device-resident count)."""
         from . import _abi
         if not self._owner:
             return
         with torch.cuda.device(self.device):
-            _abi.check(self._lib.pn_peer_wait(C.c_void_p(self._flags_ptr), self.world, int(step), int(timeout_ms),
-                                              C.c_void_p(self._status_ptr), _abi.stream_ptr(self.device)), "pn_peer_wait")
+            _abi.check(self._lib.pn_peer_wait(C.c_void_p(self._flags_ptr), self.world, int(step), int(timeout_ms), C.c_void_p(self._status_ptr),
+                                              C.c_void_p(self._counters.data_ptr() + 4), _abi.stream_ptr(self.device)), "pn_peer_wait")
 
     def late_rank(self):
         """Destination rank, after a synchronise: None, or the index of a rank whose flag the watchdog gave up on."""
@@ -178,7 +182,7 @@ class PeerFrame:
 
     def close(self):
         if getattr(self, "_ptr", None):
-            self.rgb = self.depth = self._ctl = None
+            self.rgb = self.depth = self._ctl = self._counters = None
             (self._lib.pn_peer_free if self._owner else self._lib.pn_peer_close)(C.c_void_p(self._ptr))
             self._ptr = None
 
@@ -205,7 +209,7 @@ def prepare_views_sharded(renderer, c2ws, rank: int, world: int):
     return prep
 
 
-def render_views_sharded_p2p(renderer, prep, peer: PeerFrame, step: int):
+def render_views_sharded_p2p(renderer, prep, peer: PeerFrame, step: int = 0):
     """One sharded step with the gather fused into the compositing stores: this rank's band of every view is written straight
     into the destination's frame set over NVLink, then its flag is raised; the destination's stream additionally waits for all
     flags.  Entirely asynchronous (stream-ordered); after the destination's stream reaches this point the frame set is complete."""
