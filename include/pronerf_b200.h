@@ -258,6 +258,10 @@ typedef struct pn_frame {
    * [n_views][out_view_stride rays]; ray r of view v lands at row v*out_view_stride + r.  With rgb / depth inside a peer-mapped
    * frame (pn_peer_open) the compositing kernel's stores ARE the tile gather. */
   int64_t out_view_stride;
+  /* Optional cudaEvent_t (NULL = none) recorded on `stream` right after the LAST kernel of the pass that reads `texels`: a caller
+   * that re-uploads the reference views for the next pass (the reference does so per view, trt.py:286) can start the upload as
+   * soon as this event has fired instead of after the whole pass. */
+  void* texels_done;
 } pn_frame_t;
 #define PN_MAX_VIEWS 16
 
@@ -291,12 +295,12 @@ int pn_render_views_host(pn_ctx_t* ctx, int H, int W, double fx, double fy, doub
  * Results go home on the context's download stream; *ticket identifies the call for pn_wait.  Two calls may be in flight per
  * context (device frames are double-buffered; a third call's compositing waits on the device for the download two calls back);
  * the caller keeps rgb_host / depth_host untouched until pn_wait(ticket) returns.  c2w_host / project_mat_host / tex_index_host
- * may be reused as soon as the call returns. */
+ * may be reused as soon as the call returns.  texels_ready_event / texels_done_event: as pn_frame_t.texels_ready / .texels_done. */
 int pn_render_views_host_async(pn_ctx_t* ctx, int H, int W, double fx, double fy, double cx, double cy, int n_views,
                                const float* c2w_host, const float* texels, const int* tex_index_host,
                                const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
                                float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
-                               pn_stream_t stream, int64_t* ticket);
+                               void* texels_done_event, pn_stream_t stream, int64_t* ticket);
 /* Block until the frames of `ticket` (and of every earlier call) are in host memory. */
 int pn_wait(pn_ctx_t* ctx, int64_t ticket);
 

@@ -28,7 +28,7 @@ class Frame(C.Structure):
     _fields_ = [("rays", _p), ("or_rays", _p), ("mm_input", _p), ("texels", _p), ("tex_index", _i * 8),
                 ("project_mat", _p), ("N", _i64), ("S", _i), ("NN", _i), ("P", _i), ("H", _i), ("W", _i), ("precision", _i),
                 ("rgb", _p), ("depth", _p), ("n_views", _i), ("rays_per_view", _i64), ("tex_index_views", C.POINTER(_i)), ("texels_ready", _p),
-                ("out_view_stride", _i64)]
+                ("out_view_stride", _i64), ("texels_done", _p)]
 
 
 # name -> (restype, argtypes); one entry per symbol declared in include/pronerf_b200.h
@@ -77,7 +77,7 @@ SIGNATURES = {
     "pn_render_views_host": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
                                   _p, _p, _p, _p]),
     "pn_render_views_host_async": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i,
-                                        _i, _i, _p, _p, _i64, _p, _p, C.POINTER(_i64)]),
+                                        _i, _i, _p, _p, _i64, _p, _p, _p, C.POINTER(_i64)]),
     "pn_wait": (_i, [_p, _i64]),
     "pn_render_view_host": (_i, [_p, _i, _i, _d, _d, _d, _d, C.POINTER(_f), _p, C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _i,
                                  _p, _p, _p]),

@@ -450,6 +450,7 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
     rc = launch_refine_input_f16(heads, hs, f->rays, f->or_rays, 11, f->texels, tix, nv, rpv, NN, f->H, f->W, f->project_mat, N, S,
                                  depth, add, mul, rin, nullptr, st, ray_base);
     if (rc != PN_OK) return rc;
+    if (f->texels_done) PN_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(f->texels_done), st));
   } else {
   PN_REQUIRE(ray_base == 0, "pn_render_rays: chunked passes need the fused refine-input kernel (tensor-core tier, S in 4/8/16)");
   // (2) sort + lift  trt.py:631-637
@@ -466,6 +467,7 @@ static int render_rays_chunk(pn_ctx_t* c, const pn_frame_t* f, int64_t ray_base,
                            f->or_rays + o * 11 + 3, 11, depth3d + o * S, rpv, S, rin + o * ri, ri, 6 * S, nullptr, stream);
     if (rc != PN_OK) return rc;
   }
+  if (f->texels_done) PN_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(f->texels_done), st));
   }
   PN_STAGE_MARK(4);
   // (4) refine MLP  trt.py:668
@@ -501,7 +503,7 @@ static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double f
                                   const float* c2w_host, const float* texels, const int* tex_index_host,
                                   const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
                                   float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
-                                  pn_stream_t stream, int64_t* ticket, bool two_chunks);
+                                  void* texels_done_event, pn_stream_t stream, int64_t* ticket, bool two_chunks);
 
 extern "C" {
 
@@ -552,9 +554,10 @@ int pn_render_views_host_async(pn_ctx_t* c, int H, int W, double fx, double fy, 
                                const float* c2w_host, const float* texels, const int* tex_index_host,
                                const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
                                float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
-                               pn_stream_t stream, int64_t* ticket) {
+                               void* texels_done_event, pn_stream_t stream, int64_t* ticket) {
   return render_views_host_impl(c, H, W, fx, fy, cx, cy, n_views, c2w_host, texels, tex_index_host, project_mat_host, NN, S, P, precision,
-                                row0, nrows, rgb_host, depth_host, host_view_stride, texels_ready_event, stream, ticket, false);
+                                row0, nrows, rgb_host, depth_host, host_view_stride, texels_ready_event, texels_done_event, stream, ticket,
+                                false);
 }
 }  // extern "C"
 
@@ -564,7 +567,7 @@ static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double f
                                   const float* c2w_host, const float* texels, const int* tex_index_host,
                                   const float* project_mat_host, int NN, int S, int P, int precision, int row0, int nrows,
                                   float* rgb_host, float* depth_host, int64_t host_view_stride, void* texels_ready_event,
-                                  pn_stream_t stream, int64_t* ticket, bool two_chunks) {
+                                  void* texels_done_event, pn_stream_t stream, int64_t* ticket, bool two_chunks) {
   PN_REQUIRE(c && c2w_host && texels && project_mat_host && rgb_host && depth_host && ticket, "pn_render_views_host: null pointer");
   PN_REQUIRE(NN >= 1 && NN <= 8 && n_views >= 0 && n_views <= kMaxViews && H >= 2 && W >= 2,
              "pn_render_views_host: bad shape (n_views=%d, at most %d per batch)", n_views, kMaxViews);
@@ -609,6 +612,7 @@ static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double f
   for (int k = 0; k < 8; ++k) f.tex_index[k] = (tex_index_host && k < NN) ? tex_index_host[k] : k;
   f.N = n; f.S = S; f.NN = NN; f.P = P; f.H = H; f.W = W; f.precision = precision; f.rgb = rgb; f.depth = depth;
   f.n_views = n_views; f.rays_per_view = npv; f.tex_index_views = tex_index_host; f.texels_ready = texels_ready_event;
+  f.texels_done = texels_done_event;
   // rows [a, b) of the batch -> the host frame set [n_views][hvs], view by view
   auto download = [&](int64_t a, int64_t b) -> int {
     for (int v = 0; v < n_views; ++v) {
@@ -634,6 +638,7 @@ static int render_views_host_impl(pn_ctx_t* c, int H, int W, double fx, double f
   }
   if (n_a > 0) {
     pn_frame_t fa = f, fb = f;
+    fa.texels_done = nullptr;                            // the second chunk holds the pass's last texel reader
     fa.N = n_a;
     fb.N = n - n_a;
     fb.rays = rays + n_a * 11; fb.or_rays = or_rays + n_a * 11; fb.rgb = rgb + n_a * 3; fb.depth = depth + n_a;
@@ -680,7 +685,7 @@ int pn_render_views_host(pn_ctx_t* c, int H, int W, double fx, double fy, double
                          float* depth_host, void* texels_ready_event, pn_stream_t stream) {
   int64_t ticket = 0;
   int rc = render_views_host_impl(c, H, W, fx, fy, cx, cy, n_views, c2w_host, texels, tex_index_host, project_mat_host, NN, S, P,
-                                  precision, 0, H, rgb_host, depth_host, 0, texels_ready_event, stream, &ticket, true);
+                                  precision, 0, H, rgb_host, depth_host, 0, texels_ready_event, nullptr, stream, &ticket, true);
   if (rc != PN_OK) return rc;
   rc = pn_wait(c, ticket);
   if (rc != PN_OK) return rc;

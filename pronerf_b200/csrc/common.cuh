@@ -120,11 +120,8 @@ int composite_mapped(const float* raw, const float* z, const float* rays, int ra
                      const float* dnorm = nullptr);
 // pn_interval_refine that also writes ||d_ndc|| per ray (dnorm [N]) for composite_mapped: the compositing kernel then reads 4 B
 // per ray instead of pulling a 44-byte ray row through 32-byte sectors for 12 of its bytes
-// ... and, when wdir != NULL, the NeRF last layer's per-ray view-direction term dirterm [N,4] = W7[:, 256:283] . gamma_4(viewdir)
-// (viewdir = rays[:, 8:11]; wdir = the 4 x 27 fp32 weights, tc_wdir()), which saves the tensor-core tier its pre-pass launch
 int interval_refine_dnorm(const float* rays, int ray_stride, const float* depth, const float* refine_out, int refine_stride, int64_t N,
-                          int S, float* z, float* query, float* dnorm, cudaStream_t st, const float* wdir = nullptr,
-                          float* dirterm = nullptr);
+                          int S, float* z, float* query, float* dnorm, cudaStream_t st);
 
 // View-direction term of DoNeRFTRT's last layer for one ray, fp32: o[k] = sum_j W7[k][256 + j] * gamma_4(v)[j]
 // (helpers.py:666-671 with L = 4: [v, sin(2^l v), cos(2^l v)]_{l<4}; s_w = the 4 x 27 weights)

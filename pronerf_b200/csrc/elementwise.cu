@@ -186,13 +186,7 @@ __device__ __forceinline__ float ray_dir_norm(const float* __restrict__ rd) {
 
 __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth,
                                        const float* __restrict__ ro, int ro_stride, int64_t N, int S,
-                                       float* __restrict__ z, float* __restrict__ q, float* __restrict__ dnorm,
-                                       const float* __restrict__ wdir, float* __restrict__ dirterm) {
-  __shared__ float s_w[4 * 27];
-  if (wdir) {                                                // uniform over the grid
-    if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];
-    __syncthreads();
-  }
+                                       float* __restrict__ z, float* __restrict__ q, float* __restrict__ dnorm) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * S) return;
   int64_t r = t / S;
@@ -207,8 +201,6 @@ __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_s
   float zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), frac));
   if (z) z[t] = zz;
   if (dnorm && s == 0) dnorm[r] = ray_dir_norm(ray + 3);     // for the compositing kernel: 4 B/ray instead of a 44-byte ray row
-  // the NeRF last layer's view-direction term, once per ray, by the ray's LAST sample lane (the first one wrote dnorm)
-  if (dirterm && s == S - 1) *reinterpret_cast<float4*>(dirterm + r * 4) = dirterm_of(ray + 8, s_w);
   const float* off = ro + r * ro_stride + S + 3 * s;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -561,7 +553,7 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
   PN_REQUIRE(rays && depth && refine_out && query && N >= 0 && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S,
              "pn_interval_refine: bad arguments");
   interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, refine_out,
-                                                                               refine_stride, N, S, z, query, nullptr, nullptr, nullptr);
+                                                                               refine_stride, N, S, z, query, nullptr);
   PN_LAUNCH_OK("pn_interval_refine");
   return PN_OK;
 }
@@ -571,12 +563,10 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
 namespace pn {
 // pn_interval_refine for the composed path: also leaves ||d_ndc|| per ray for the compositing kernel
 int interval_refine_dnorm(const float* rays, int ray_stride, const float* depth, const float* refine_out, int refine_stride, int64_t N,
-                          int S, float* z, float* query, float* dnorm, cudaStream_t st, const float* wdir, float* dirterm) {
+                          int S, float* z, float* query, float* dnorm, cudaStream_t st) {
   if (N == 0) return PN_OK;
   PN_REQUIRE(rays && depth && refine_out && query && dnorm && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S, "interval_refine: bad arguments");
-  PN_REQUIRE((wdir == nullptr) == (dirterm == nullptr) && (!wdir || ray_stride >= 11), "interval_refine: wdir and dirterm go together (rays [N,11])");
-  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, st>>>(rays, ray_stride, depth, refine_out, refine_stride, N, S, z, query, dnorm,
-                                                                 wdir, dirterm);
+  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, st>>>(rays, ray_stride, depth, refine_out, refine_stride, N, S, z, query, dnorm);
   PN_LAUNCH_OK("pn_interval_refine");
   return PN_OK;
 }

@@ -46,6 +46,8 @@ class Renderer:
         self._staging = None
         self._copy_stream = None
         self._tex_event = None
+        self._tex_free = None              # event of the last pass's final texel read, when that pass recorded one
+        self._tex_free_ev = None
         self.set_images(images_ref)
 
     # -- state ------------------------------------------------------------------------------------
@@ -90,7 +92,12 @@ class Renderer:
                     self._copy_stream = torch.cuda.Stream(self.device)
                     self._tex_done = torch.cuda.Event()
                 main = torch.cuda.current_stream(self.device)
-                self._copy_stream.wait_stream(main)            # earlier renders may still be reading the texels
+                if self._tex_free is not None:
+                    # the last pass was a pipelined host call that marked its last texel read: the upload may start right
+                    # behind THAT kernel instead of behind the whole pass (the event also orders everything before it)
+                    self._copy_stream.wait_event(self._tex_free)
+                else:
+                    self._copy_stream.wait_stream(main)        # earlier renders may still be reading the texels
                 with torch.cuda.stream(self._copy_stream):
                     self._staging.copy_(t, non_blocking=True)
                     ops.pack_images(self._staging, out=self.texels)
@@ -132,6 +139,7 @@ class Renderer:
         """One pass of the hot path over a prepared view / batch of views; returns (rgb [n,3], depth [n]) CUDA tensors.
         ``prep['out_view_stride']`` (optional): the outputs are a band inside a frame set, see ``pn_frame_t.out_view_stride``."""
         self._join_texels()
+        self._tex_free = None              # this pass reads the texels without marking its last read
         return self.ctx.render_rays(prep["rays"], prep["or_rays"], self.texels, prep["project_mat"], self.S, self.P,
                                     self.H, self.W, tex_index=prep["tex_index"], precision=self.precision,
                                     out_rgb=prep["rgb"], out_depth=prep["depth"], out_view_stride=prep.get("out_view_stride", 0))
@@ -149,6 +157,7 @@ class Renderer:
         """End to end with HOST buffers for a batch of poses: one upload of poses + matrices, one pass
         (two wave-aligned chunks on the tensor-core tier, the first chunk's download overlapping the second's compute)."""
         params = [self.view_params(c) for c in c2ws]
+        self._tex_free = None
         return self.ctx.render_views_host(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
                                           np.stack([p[2] for p in params], 0), self.S, self.P,
                                           tex_index=[p[1] for p in params], precision=self.precision, rgb_host=rgb_host,
@@ -158,10 +167,17 @@ class Renderer:
         """Pipelined flavour (``pn_render_views_host_async``): returns a ticket as soon as the pass is enqueued; up to two calls
         in flight, ``wait(ticket)`` blocks until that call's frames are in ``rgb_host`` / ``depth_host``."""
         params = [self.view_params(c) for c in c2ws]
-        return self.ctx.render_views_host_async(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
-                                                np.stack([p[2] for p in params], 0), self.S, self.P, rgb_host, depth_host,
-                                                tex_index=[p[1] for p in params], precision=self.precision, row0=row0, nrows=nrows,
-                                                host_view_stride=host_view_stride, texels_ready=self._take_tex_event())
+        if self._tex_free_ev is None:
+            self._tex_free_ev = torch.cuda.Event()
+            self._tex_free_ev.record(torch.cuda.current_stream(self.device))     # materialise the handle before the library records it
+        nr = self.H - row0 if nrows is None else nrows
+        tk = self.ctx.render_views_host_async(self.H, self.W, self.K, np.stack([p[0] for p in params], 0), self.texels,
+                                              np.stack([p[2] for p in params], 0), self.S, self.P, rgb_host, depth_host,
+                                              tex_index=[p[1] for p in params], precision=self.precision, row0=row0, nrows=nrows,
+                                              host_view_stride=host_view_stride, texels_ready=self._take_tex_event(),
+                                              texels_done=self._tex_free_ev)
+        self._tex_free = self._tex_free_ev if (nr > 0 and len(params) > 0) else None
+        return tk
 
     def wait(self, ticket: int):
         self.ctx.wait(ticket)
@@ -173,6 +189,7 @@ class Renderer:
         """End to end with HOST buffers: uploads the pose + matrices, renders, downloads rgb/depth (synchronous)."""
         c2w, order, pm = self.view_params(c2w)
         self._join_texels()
+        self._tex_free = None
         return self.ctx.render_view_host(self.H, self.W, self.K, c2w, self.texels, pm, self.S, self.P, tex_index=order,
                                          precision=self.precision, row0=row0, nrows=nrows, rgb_host=rgb_host,
                                          depth_host=depth_host)

@@ -264,7 +264,7 @@ class Context:
         return rgb_host, depth_host
 
     def render_views_host_async(self, H, W, K, c2ws, texels, project_mats_host, S, P, rgb_host, depth_host, tex_index=None,
-                                precision="fp32", row0=0, nrows=None, host_view_stride=0, texels_ready=None) -> int:
+                                precision="fp32", row0=0, nrows=None, host_view_stride=0, texels_ready=None, texels_done=None) -> int:
         """Pipelined ``render_views_host`` (``pn_render_views_host_async``): enqueues the pass for rows [row0, row0+nrows) of every
         view and returns a ticket for ``wait``; ``rgb_host`` / ``depth_host`` (pinned CPU tensors) start at (view 0, the band's
         first ray) of a host frame set laid out [V][host_view_stride rays] (0 = dense) and must stay untouched until ``wait``."""
@@ -287,6 +287,7 @@ class Context:
                                                    pms.ctypes.data_as(C.POINTER(C.c_float)), NN, S, P, PRECISIONS[precision],
                                                    int(row0), int(nrows), rgb_host.data_ptr(), depth_host.data_ptr(), int(hvs),
                                                    texels_ready.cuda_event if texels_ready is not None else None,
+                                                   texels_done.cuda_event if texels_done is not None else None,
                                                    stream_ptr(self.device), C.byref(ticket)), "pn_render_views_host_async")
         return int(ticket.value)
 

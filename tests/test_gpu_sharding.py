@@ -80,6 +80,29 @@ def test_pipelined_host_entry_points(precision):
         last = R.render_views_host_async(sets[0], h_rgb[a:], h_depth[a:], row0=row0, nrows=nrows, host_view_stride=n)
     R.wait(last)
     assert torch.equal(h_rgb, want[0][0]) and torch.equal(h_depth, want[0][1])
+    # the serving loop of the bench: every step re-uploads the reference views on the copy stream (a DIFFERENT image set per step
+    # here) and renders pipelined; the upload of step k+1 may start as soon as step k's last texel read has fired
+    # (pn_frame_t.texels_done) and must be complete before step k+1's first texel read (texels_ready)
+    base = torch.from_numpy(np.ascontiguousarray(scene.images_ref))
+    variants = [(base * sc).pin_memory() for sc in (1.0, 0.6, 0.3)]
+    want_v = []
+    for img in variants:
+        R.set_images(img)
+        r, d = R.render_views_host(sets[1])
+        want_v.append((r.clone(), d.clone()))
+    assert not torch.equal(want_v[0][0], want_v[1][0])
+    outs = [(torch.empty((V * n, 3)).pin_memory(), torch.empty((V * n,)).pin_memory()) for _ in range(9)]
+    prev = None
+    for k, (r, d) in enumerate(outs):
+        R.set_images(variants[k % 3], overlap=True)
+        tk = R.render_views_host_async(sets[1], r, d)
+        if prev is not None:
+            R.wait(prev)
+        prev = tk
+    R.wait(prev)
+    for k, (r, d) in enumerate(outs):
+        assert torch.equal(r, want_v[k % 3][0]) and torch.equal(d, want_v[k % 3][1]), k
+    R.set_images(variants[0])
     with pytest.raises(RuntimeError, match="ticket"):
         R.wait(10 ** 6)
     with pytest.raises(ValueError):
