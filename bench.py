@@ -155,6 +155,37 @@ def cpu_oracle_rate(scene, weights, n_rays, repeats, threads):
     return n / min(times) / 1e6, n, times
 
 
+def torch_eager_gpu_rate(scene, weights, dev, repeats=3):
+    """The CPU oracle port -- the reference's op sequence in plain PyTorch fp32 -- executed with stock eager kernels on the GPU: one
+    full 504x378 view, CUDA events, best of `repeats`.  A same-box stand-in for the reference's own PyTorch path (which is not on
+    the GPU box; measured once by scripts/ref_gpu.py: profiles/r02_ref_gpu.json).  Baseline leg only."""
+    from oracle import pronerf_oracle as O
+    pv = O.prep_view(scene.H, scene.W, scene.K, scene.poses[scene.i_test[0]], scene.poses_ref, N_samples=S)
+    images = scene.images_ref[pv["ref_nos"].numpy()]
+    O.DEVICE = str(dev)
+    torch.set_default_device(dev)
+    try:
+        w = {net: {k: torch.as_tensor(v, dtype=torch.float32).to(dev) for k, v in sd.items()} for net, sd in weights.items()}
+        a = [pv[k].to(dev) for k in ("rays", "mm_input")] + [torch.from_numpy(images).to(dev)] + [pv[k].to(dev) for k in ("project_mat", "ro_w", "rd_w")]
+        times = []
+        with torch.no_grad():
+            for i in range(repeats + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                O.render_rays(w, *a, S=S, keep=False)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                if i:
+                    times.append(e0.elapsed_time(e1))
+    finally:
+        O.DEVICE = "cpu"
+        torch.set_default_device("cpu")
+    n = scene.H * scene.W
+    return {"value": n / min(times) / 1e3, "unit": UNIT, "ms_per_view": min(times), "kind": "port on cuda",
+            "what": "the oracle port (the reference's PyTorch fp32 op sequence) run with stock eager kernels on cuda:0, one 504x378 view, "
+                    "best of %d; the unmodified reference itself on a B200: 54.6 ms/view = 3.49 Mrays/s (profiles/r02_ref_gpu.json)" % repeats}
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU port of the reference path, all host threads; each step = ONE full 504x378 view of the
     workload (a bounded sample: a third of the 3-view batch), so that K steps end within a few minutes."""
@@ -485,6 +516,13 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{n} rays (test view 0, 504x378), best of 2 runs: " + ", ".join(f"{t:.2f}s" for t in times)}
 
+    eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            eager = torch_eager_gpu_rate(scene, weights, dev)
+        except Exception as e:                              # a baseline leg must not take the headline down
+            eager = {"error": repr(e)[:300]}
+
     launches = LAUNCHES_PER_STEP[precision] + (2 if world > 1 else 0)           # + flag store and flag wait (rank 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -507,7 +545,7 @@ def main():
                             if use_graph else "per-stage CUDA events inside the timed region"),
         "mlp_tflops_all_three": (fl["total"] * n_rays_rank / (mlp_total_ms / 1e3) / 1e12) if mlp_total_ms else None,
         "algorithmic_flops_per_ray": fl, "executed_flops_per_ray": executed_flops_per_ray(S, P, NN),
-        "cpu_baseline": cpu, "clocks": clock_info,
+        "cpu_baseline": cpu, "torch_eager_gpu": eager, "clocks": clock_info,
     }
     line.update(extras)
     print(json.dumps(line))

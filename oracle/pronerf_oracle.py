@@ -42,12 +42,16 @@ import torch
 import torch.nn.functional as F
 
 ORACLE_KIND = "port"          # a restatement ("port"), not the reference binary itself
+# Where the restatement runs.  "cpu" for everything that CHECKS (tests, smoke, golden pins).  bench.py's baseline leg may set it to a
+# CUDA device (together with torch.set_default_device) to time the same PyTorch op sequence as stock eager kernels on the GPU --
+# a same-box stand-in for the reference's own PyTorch path (`torch_eager_gpu` key); never a checker in that mode.
+DEVICE = "cpu"
 
 
 def _t(x, dtype=torch.float32):
     if isinstance(x, torch.Tensor):
-        return x.detach().to("cpu", dtype)
-    return torch.as_tensor(np.asarray(x), dtype=dtype)
+        return x.detach().to(DEVICE, dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(DEVICE)
 
 
 # ----------------------------------------------------------------------------- A.1 per-view prep

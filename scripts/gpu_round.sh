@@ -1,22 +1,16 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list, one full capture of the dominant kernel.
-# Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag>
-TAG=${1:-r01}
+# One 1xB200 box visit: parity tests, smoke, bench (both arms), parity report, reference-on-GPU comparison.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag>      (ncu passes: scripts/ncu_r02.sh)
+TAG=${1:-r02}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
-tail -5 $OUT/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+tail -4 $OUT/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke exit $?" >> $OUT/smoke.log
-tail -6 $OUT/smoke.log
+tail -5 $OUT/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
-cat $OUT/bench.json
-if [ "${SKIP_NCU:-0}" != "1" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 6 -c 3 -o $OUT/prof_mlp \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:refine_input_kernel|composite_scan_kernel|interval_refine_kernel" -s 9 -c 3 -o $OUT/prof_gather \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_gather.log 2>&1
-fi
+tail -c 400 $OUT/bench.json; echo
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "reference arm exit $?"
+if [ -d baseline/_ref ]; then bash scripts/ref_gpu.sh run; cp gpurun_out/r02_ref_gpu.json gpurun_out/r02_parity.json $OUT/ 2>/dev/null; fi
 ls -la $OUT
