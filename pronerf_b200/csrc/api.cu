@@ -19,6 +19,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("PN_PDL") && atoi(getenv("PN_PDL")) != 0;      // opt-in: measured slower
+  return on;
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
   return PN_ECUDA;
@@ -210,6 +215,9 @@ int pn_ctx_load_net(pn_ctx_t* c, int net, int n_layers, const int* in_dims, cons
   n.loaded = true;
   int rc = tc_load_net(c->tc[net], net, n_layers, in_dims, out_dims, W, b, st);
   if (rc != PN_OK) return rc;
+  // the kernels of the composed path read their (static) weights BEFORE the programmatic-dependency wait: packing must be
+  // complete, not merely ordered, when the first of them is launched
+  PN_CUDA_OK(cudaStreamSynchronize(st));
   return PN_OK;
 }
 

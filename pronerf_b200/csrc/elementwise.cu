@@ -187,6 +187,8 @@ __device__ __forceinline__ float ray_dir_norm(const float* __restrict__ rd) {
 __global__ void interval_refine_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ depth,
                                        const float* __restrict__ ro, int ro_stride, int64_t N, int S,
                                        float* __restrict__ z, float* __restrict__ q, float* __restrict__ dnorm) {
+  pdl_wait();
+  pdl_launch();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N * S) return;
   int64_t r = t / S;
@@ -336,6 +338,8 @@ __global__ void composite_scan_kernel(const float* __restrict__ raw, const float
                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
                                       float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om,
                                       const float* __restrict__ dnorm) {
+  pdl_wait();
+  pdl_launch();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one (ray, sample) per thread
   int64_t r = t / S;
   int s = (int)(t % S);
@@ -389,6 +393,8 @@ __global__ void composite_seq_kernel(const float* __restrict__ raw, const float*
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ disp,
                                      float* __restrict__ acc, float* __restrict__ weights, float raw_clamp, OutMap om,
                                      const float* __restrict__ dnorm) {
+  pdl_wait();
+  pdl_launch();
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   float dn = dnorm ? dnorm[r] : ray_dir_norm(rays + r * ray_stride + ray_d_col);
@@ -552,8 +558,8 @@ int pn_interval_refine(const float* rays, int ray_stride, const float* depth, co
   if (N == 0) return PN_OK;            // empty batch: nothing to validate or launch
   PN_REQUIRE(rays && depth && refine_out && query && N >= 0 && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S,
              "pn_interval_refine: bad arguments");
-  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, as_stream(stream)>>>(rays, ray_stride, depth, refine_out,
-                                                                               refine_stride, N, S, z, query, nullptr);
+  PN_CUDA_OK(launch_chain(interval_refine_kernel, dim3(blocks_for(N * S)), dim3(kThreads), 0, as_stream(stream), rays, ray_stride, depth,
+                          refine_out, refine_stride, N, S, z, query, (float*)nullptr));
   PN_LAUNCH_OK("pn_interval_refine");
   return PN_OK;
 }
@@ -566,7 +572,8 @@ int interval_refine_dnorm(const float* rays, int ray_stride, const float* depth,
                           int S, float* z, float* query, float* dnorm, cudaStream_t st) {
   if (N == 0) return PN_OK;
   PN_REQUIRE(rays && depth && refine_out && query && dnorm && S >= 1 && ray_stride >= 8 && refine_stride >= 4 * S, "interval_refine: bad arguments");
-  interval_refine_kernel<<<blocks_for(N * S), kThreads, 0, st>>>(rays, ray_stride, depth, refine_out, refine_stride, N, S, z, query, dnorm);
+  PN_CUDA_OK(launch_chain(interval_refine_kernel, dim3(blocks_for(N * S)), dim3(kThreads), 0, st, rays, ray_stride, depth, refine_out,
+                          refine_stride, N, S, z, query, dnorm));
   PN_LAUNCH_OK("pn_interval_refine");
   return PN_OK;
 }
@@ -612,9 +619,9 @@ int composite_mapped(const float* raw, const float* z, const float* rays, int ra
   PN_REQUIRE(out_view_stride == 0 || (rays_per_view >= 1 && out_view_stride >= rays_per_view && !disp && !acc),
              "pn_composite: out_view_stride=%lld needs rays_per_view in [1, out_view_stride]", (long long)out_view_stride);
   OutMap om{rays_per_view, out_view_stride, ray_base};
-#define PN_COMP(SS)                                                                                                  \
-  composite_scan_kernel<SS><<<blocks_for(N * SS), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, \
-                                                                     rgb, depth, disp, acc, weights, raw_clamp, om, dnorm)
+#define PN_COMP(SS)                                                                                                         \
+  PN_CUDA_OK(launch_chain(composite_scan_kernel<SS>, dim3(blocks_for(N * SS)), dim3(kThreads), 0, st, raw, z, rays, ray_stride, \
+                          ray_d_col, add, mul, N, rgb, depth, disp, acc, weights, raw_clamp, om, dnorm))
   switch (S) {
     case 2: PN_COMP(2); break;
     case 4: PN_COMP(4); break;
@@ -622,8 +629,8 @@ int composite_mapped(const float* raw, const float* z, const float* rays, int ra
     case 16: PN_COMP(16); break;
     case 32: PN_COMP(32); break;
     default:
-      composite_seq_kernel<<<blocks_for(N), kThreads, 0, st>>>(raw, z, rays, ray_stride, ray_d_col, add, mul, N, S, rgb,
-                                                              depth, disp, acc, weights, raw_clamp, om, dnorm);
+      PN_CUDA_OK(launch_chain(composite_seq_kernel, dim3(blocks_for(N)), dim3(kThreads), 0, st, raw, z, rays, ray_stride, ray_d_col, add, mul,
+                              N, S, rgb, depth, disp, acc, weights, raw_clamp, om, dnorm));
   }
 #undef PN_COMP
   PN_LAUNCH_OK("pn_composite");

@@ -155,6 +155,8 @@ refine_input_kernel(const float* __restrict__ heads, int head_stride, const floa
   __shared__ __align__(16) __half stage[RPB * KMAX];
   const int NN = NN_T > 0 ? NN_T : NNr;
   const int K0 = 6 * S + 3 * NN * S;
+  pdl_wait();                                               // the sampler MLP's heads (and, first in a pass, the previous pass) are done
+  pdl_launch();
   for (int i = threadIdx.x; i < n_views * NN * 12; i += blockDim.x) sM[i] = pm[i];
   __syncthreads();
   const int64_t ray0 = (int64_t)blockIdx.x * RPB;
@@ -384,8 +386,9 @@ int launch_refine_input_f16(const float* heads, int head_stride, const float* ra
   const float4* tx = reinterpret_cast<const float4*>(texels);
   __half* rin = reinterpret_cast<__half*>(refine_in_f16);
 #define PN_RI(SS, NT)                                                                                                    \
-  refine_input_kernel<SS, NT><<<(unsigned)((N + (256 / SS) - 1) / (256 / SS)), 256, 0, st>>>(                            \
-      heads, head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, n_views, rays_per_view, N, depth, add, mul, rin, x0y0, ray_base)
+  PN_CUDA_OK(launch_chain(refine_input_kernel<SS, NT>, dim3((unsigned)((N + (256 / SS) - 1) / (256 / SS))), dim3(256), 0, st, heads, \
+                          head_stride, rays, or_rays, ray_stride, tx, ti, NN, H, W, project_mat, n_views, rays_per_view, N, depth, add, \
+                          mul, rin, x0y0, ray_base))
   if (NN == 4) {
     if (S == 4) PN_RI(4, 4); else if (S == 8) PN_RI(8, 4); else PN_RI(16, 4);
   } else {

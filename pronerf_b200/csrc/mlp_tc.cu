@@ -471,6 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) pdl_launch();                      // the successor's CTAs may take over SMs as this grid's CTAs exit
   if (kTimeline && p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
 
   // Every role walks the same (slot, phase) sequence: the two slots alternate, slot 1 running `shift` phases (half a
@@ -822,6 +823,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       return d;
     };
 
+    // Everything above -- barrier init, TMEM allocation, the bias table -- and the weight producer's first blocks touch only
+    // this network's static weights: with programmatic dependent launch they run while the previous kernel of the stream drains.
+    // The inputs (and every output buffer) belong to the dependency chain: wait for the predecessor's completion here.
+    pdl_wait();
     // prologue: first operands of both slots
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -1190,7 +1195,9 @@ __global__ void pack_tc_wdir_kernel(const float* __restrict__ W, int in_dim, flo
 __global__ void dirterm_kernel(const float* __restrict__ in, int stride, int mode, const float* __restrict__ wdir, long long n,
                                float* __restrict__ out) {
   __shared__ float s_w[4 * 27];
-  if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];
+  if (threadIdx.x < 4 * 27) s_w[threadIdx.x] = wdir[threadIdx.x];      // static weights: before the dependency wait
+  pdl_wait();
+  pdl_launch();
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (mode == 0) {
@@ -1420,7 +1427,7 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   }
   const long long units = (M + tc::UNIT_M - 1) / tc::UNIT_M;
   const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);
-  kern<<<2 * clusters, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);
+  PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::NTHREADS), tc::SMEM_ALLOC, stream, p));
   PN_LAUNCH_OK("mlp_tc_kernel(classic)");
   return PN_OK;
 }
@@ -1527,8 +1534,8 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     }
     const float* wdir = reinterpret_cast<const float*>(blob + L.wdir_off);
     const unsigned blocks = (unsigned)((rows + 255) / 256 < 148 * 8 ? (rows + 255) / 256 : 148 * 8);
-    if (Lc.input_mode == IN_ENCODE) tc::dirterm_kernel<<<blocks, 256, 0, stream>>>(Lc.in1, Lc.in1_stride, 0, wdir, rows, n.dirterm);
-    else tc::dirterm_kernel<<<blocks, 256, 0, stream>>>(Lc.in1, 27, 1, wdir, rows, n.dirterm);
+    if (Lc.input_mode == IN_ENCODE) PN_CUDA_OK(launch_chain(tc::dirterm_kernel, dim3(blocks), dim3(256), 0, stream, Lc.in1, Lc.in1_stride, 0, wdir, rows, n.dirterm));
+    else PN_CUDA_OK(launch_chain(tc::dirterm_kernel, dim3(blocks), dim3(256), 0, stream, Lc.in1, 27, 1, wdir, rows, n.dirterm));
     PN_LAUNCH_OK("dirterm_kernel");
     p.dirterm = n.dirterm;
     p.dir_div = Lc.input_mode == IN_ENCODE ? (Lc.S > 0 ? Lc.S : 1) : 1;
@@ -1550,7 +1557,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
       if (max_clusters <= 0) { set_error("tc: no co-resident CTA pair fits on this device"); return PN_ECUDA; }            \
     }                                                                                                                      \
     const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);                                     \
-    kern<<<2 * clusters, tc::NTHREADS, tc::SMEM_ALLOC, stream>>>(p);                                                       \
+    PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::NTHREADS), tc::SMEM_ALLOC, stream, p));                     \
   } while (0)
   if (Lc.act == 0 && Lc.input_mode == IN_ENCODE) PN_TC_LAUNCH(0, IN_ENCODE);
   else if (Lc.act == 0 && Lc.input_mode == IN_LOAD2) PN_TC_LAUNCH(0, IN_LOAD2);
