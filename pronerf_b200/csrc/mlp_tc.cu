@@ -15,21 +15,30 @@
 // Pipeline (per slot the layers are strictly sequential; the two slots are half a period apart, so the tensor pipe
 // runs slot Y's layer while the CUDA cores drain slot X's accumulator):
 //
-//   warp 8      weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
+//   warp 12     weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
 //               consumption order, through a 5-slot ring with cp.async.bulk + mbarrier complete_tx; the global image
 //               is pre-swizzled into the UMMA canonical layout so a linear copy lands a ready B operand.
-//   warp 9      leader: MMA issuer -- per (layer, slot): wait "operand ready", then per K block wait "weights
+//   warp 13     leader: MMA issuer -- per (layer, slot): wait "operand ready", then per K block wait "weights
 //               landed in both CTAs", issue 4 MMAs (M256 N256 K16), tcgen05.commit frees the ring slot in both CTAs;
-//               after the last block commit "accumulator full" to both CTAs.
+//               after the last block commit "accumulator full" (hidden layers) or "output full" to both CTAs.
 //               follower: relay -- forwards "my half of the weights landed" to the leader's full barrier.
-//   warps 0-7   epilogue / operand producers (8 warps; warp = TMEM lane quadrant x 128-column half; thread = row):
+//   warps 0-7   hidden epilogues (8 warps; warp = TMEM lane quadrant x 128-column half; thread = row):
 //               tcgen05.ld the accumulator, bias + ReLU/ELU, convert to fp16 and store straight into the slot's
 //               A operand for the next layer (the swizzle makes row-per-thread 16-byte stores conflict free), then
 //               fence.proxy.async and arrive on the leader's "operand ready" barrier (remote arrive from the follower).
+//   warps 8-11  tile hand-over (one warp per TMEM lane quadrant; thread = row): everything that is NOT a hidden epilogue --
+//               the output layer's accumulator, head activations / view-direction term, the stores to global memory, and
+//               the NEXT tile's first-layer operand (encoded / generated / loaded), which they prepare in registers while
+//               the slot's last layers run and publish a few hundred cycles after "output full".  The hidden-epilogue
+//               warps never see a tile boundary: they go from the last hidden layer of one tile straight to the first
+//               hidden layer of the next.
+//   warps 14-15 exist to lend their registers (setmaxnreg works on whole warpgroups): the CTA launches with 128 registers
+//               per thread, warps 12-15 drop to 64, warps 8-11 to 112, warps 0-7 grow to 168.
 //
 // The first-layer operand is generated in the kernel (frequency encoding, Pluecker features) or loaded; the NeRF
 // view-direction term (27 inputs of the last layer, identical for a ray's samples) is a per-ray fp32 pre-pass added in
 // the output epilogue, so the tensor-core part of the last layer is a clean K = 256, N = 16 GEMM.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -62,19 +71,30 @@ constexpr int OFF_RING = OFF_A + 2 * A_SLOT_BYTES;
 constexpr int OFF_BIAS = OFF_RING + N_RING * RING_SLOT_BYTES;
 constexpr int OFF_STAGE = OFF_BIAS + STAGE_BIAS_ROW0 * kHidden * 4;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_REGION;
-// barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2 slots][2 halves], acc_full[2]
-constexpr int N_BARS = 2 * N_RING + 6;
+// barriers (8 bytes each): full[N_RING], empty[N_RING], a_ready[2 slots][2 halves], acc_full[2], out_full[2], in_full[2]
+constexpr int N_BARS = 2 * N_RING + 10;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;           // slack to align the base to 1024 B (swizzle atom)
 static_assert(SMEM_ALLOC <= 232448, "over the 227 KB per-CTA shared-memory limit of sm_100");
-constexpr int N_EPI_WARPS = 8;                          // lane quadrant x column half.  Register budget: the register file is per SM
-                                                        // sub-partition (16 K), and with 10 warps one sub-partition holds 3 -> 168 per thread
-constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;        // 320
-// The two single-thread roles get the HIGHEST warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
+constexpr int N_EPI_WARPS = 8;                          // hidden epilogues: lane quadrant x column half (warpgroups 0, 1)
+constexpr int N_OUT_WARPS = 4;                          // tile hand-over: one warp per lane quadrant (warpgroup 2)
+constexpr int W_OUT0 = N_EPI_WARPS;                     // warps 8..11
+constexpr int NTHREADS = 16 * 32;                       // 512: four warpgroups
+// Register budget.  The register file is per SM sub-partition (16 K registers = 512 per lane), a sub-partition holds one warp of
+// every warpgroup, and setmaxnreg moves registers between warpgroups INSIDE the launch allocation (512 threads x 128 = all of
+// it): 2 x 168 (hidden epilogues: 128 live accumulator columns) + 112 / 96 (hand-over) + 64 / 80 (single-thread roles) = 512.
+// The split between the hand-over and the role warps is per instantiation (out_regs / role_regs below): ptxas' allocation around
+// the 32-register tcgen05.ld blocks is brittle, and these are the splits that compile without spills in the hot loops.
+constexpr int kEpiRegs = 168;
+__host__ __device__ constexpr int out_regs(bool nerf) { return nerf ? 96 : 128; }
+__host__ __device__ constexpr int role_regs(bool nerf) { return nerf ? 80 : 48; }
+static_assert(2 * kEpiRegs + out_regs(true) + role_regs(true) <= 512 && 2 * kEpiRegs + out_regs(false) + role_regs(false) <= 512,
+              "register budget per SM sub-partition lane");
+// The two single-thread roles get the HIGHEST active warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
 // issuer (or weight producer) stalls the whole pair (measured: 2x slower issue as warp 1 behind four epilogue warps).
-constexpr int W_PRODUCER = N_EPI_WARPS;                 // warp 8 (scheduler 0)
-constexpr int W_MMA = N_EPI_WARPS + 1;                  // warp 9 (scheduler 1)
+constexpr int W_PRODUCER = W_OUT0 + N_OUT_WARPS;        // warp 12 (scheduler 0)
+constexpr int W_MMA = W_PRODUCER + 1;                   // warp 13 (scheduler 1)
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_PHASES = 14;
 
@@ -116,8 +136,10 @@ struct Params {
   long long M;
   float* out;
   float4 head_tab[96];          // output column c: y = x * .w + (.y / (1 + 2^(x * .x)) + .z), x = accumulator + bias (head_coeffs)
-  int shift;                    // phases slot 1 runs behind slot 0 (0 = in step)
-  int split;                    // 1: hidden epilogues publish their first K block early (two-step operand hand-over)
+  uint32_t head_linear;         // bit b: output columns [8b, 8b + 8) are all linear (or padding): y = x
+  alignas(64) CUtensorMap tmap_in;   // IN_LOAD16: the [M, K0] fp16 input as a 2-D tensor, box = 64 columns x 128 rows, 128-byte swizzle
+  int reorder;                  // 1: slot 0's first layer of its next tile is issued BEFORE slot 1's output layer (see PN_WALK)
+  int split;                    // hidden epilogues publish their first two K blocks early (two-step operand hand-over): bit 0 = all, bit 1 = first layer only
   int out_rpp;                  // rows per staging pass of the head output (multiple of 4)
   int* error_flag;
   long long* timeline;          // debug: leader CTA of cluster 0 stamps clock64() of its second iteration
@@ -161,9 +183,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug must not hang the GPU (it traps and reports instead).  The first probe is inline
-// (it usually succeeds); the spin loop with the watchdog lives out of line to keep the role loops compact.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+// Spin with a watchdog: a protocol bug must not hang the GPU (it traps and reports instead).  Inlined: once the warpgroups'
+// register budgets differ (setmaxnreg) ptxas cannot allocate across a real call (C7600).
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) {
@@ -176,9 +198,30 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, code);
 }
+// The hand-over warps wait for most of a tile's lifetime: they poll with a back-off so that their probes do not compete with the
+// epilogue warps' shared-memory traffic (a tight try_wait loop of 128 threads slowed the MMAs and the hidden epilogues by 30 %).
+__device__ __forceinline__ void mbar_wait_polite(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > (1u << 22)) {
+      if (error_flag) atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// One [128 rows x 64 halves] box of a row-major fp16 tensor -> one K block of an A operand.  The tensor map's 128-byte swizzle is the
+// UMMA K-major SWIZZLE_128B layout (16-byte chunk index ^ row % 8), columns / rows outside the tensor arrive as zeros, and the whole
+// box (16 KB) counts towards the barrier's transaction bytes.
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* tmap, int col, int row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(row), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -444,7 +487,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (N_RING + s); };
   auto bar_aready = [&](int t, int h) { return bar0 + 8u * (2 * N_RING + 2 * t + h); };   // h = 0: K blocks {0,1} + accumulator drained; 1: K blocks {2,3}
-  auto bar_accfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 4 + t); };
+  auto bar_accfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 4 + t); };      // a hidden layer's accumulator is complete
+  auto bar_outfull = [&](int t) { return bar0 + 8u * (2 * N_RING + 6 + t); };      // the output layer's accumulator is complete
+  auto bar_infull = [&](int t) { return bar0 + 8u * (2 * N_RING + 8 + t); };       // IN_LOAD16: the next tile's rows have landed (TMA)
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -452,13 +497,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
   const long long n_pairs = (p.M + PAIR_M - 1) / PAIR_M;          // 256-row MMA tiles
   // iteration `it` of this cluster covers pair tiles T0 = (it * n_clusters + cluster_id) * 2 (slot 0) and T0 + 1 (slot 1)
-  auto pair0 = [&](long long it) { return (it * n_clusters + cluster_id) * 2; };
 
   // ---- one-time setup ----
   if (warp == W_MMA && lane == 0) {
     for (int s = 0; s < N_RING; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_aready(t, 0), 2 * N_EPI_WARPS); mbar_init(bar_aready(t, 1), 2 * N_EPI_WARPS); mbar_init(bar_accfull(t), 1);
+      // operand-ready: 16 arrivals per phase -- one per hidden-epilogue warp of the pair, or two per hand-over warp
+      mbar_init(bar_aready(t, 0), 2 * N_EPI_WARPS); mbar_init(bar_aready(t, 1), 2 * N_EPI_WARPS);
+      mbar_init(bar_accfull(t), 1); mbar_init(bar_outfull(t), 1); mbar_init(bar_infull(t), 1);
     }
     fence_barrier_init();
   }
@@ -474,16 +520,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   if (threadIdx.x == 0) pdl_launch();                      // the successor's CTAs may take over SMs as this grid's CTAs exit
   if (kTimeline && p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
 
-  // Every role walks the same (slot, phase) sequence: the two slots alternate, slot 1 running `shift` phases (half a
-  // network) behind slot 0, so that one slot's narrow first/last layers and tile hand-over overlap the other slot's
-  // full-width layers and the tensor pipe always has a 2048-cycle block of MMAs queued.
+  // The single-thread roles walk the same (slot, phase) sequence: the two slots alternate phase by phase.  With `reorder`, slot
+  // 0's FIRST layer of its next tile goes before slot 1's OUTPUT layer: slot 0's new operand is published by the hand-over warps
+  // a few hundred cycles after its output layer, while slot 1's output layer still waits for a whole hidden epilogue -- in the
+  // plain order the ready first layer would sit behind it in the in-order MMA stream (head-of-line).
   struct Cursor {
     long long n_pairs, stride, tile0, tile1;
-    int np, delay, ph0, ph1;
+    int np, ph0, ph1;
     __device__ __forceinline__ long long tile(int t) const { return t ? tile1 : tile0; }
     __device__ __forceinline__ int ph(int t) const { return t ? ph1 : ph0; }
     __device__ __forceinline__ bool live(int t) const { return tile(t) < n_pairs; }
-    __device__ __forceinline__ bool has_next(int t) const { return tile(t) + stride < n_pairs; }
     __device__ __forceinline__ void advance(int t) {
       if (t) { if (++ph1 == np) { ph1 = 0; tile1 += stride; } }
       else   { if (++ph0 == np) { ph0 = 0; tile0 += stride; } }
@@ -493,24 +539,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   cur.n_pairs = n_pairs; cur.stride = 2 * n_clusters; cur.np = p.n_phases;
   cur.ph0 = cur.ph1 = 0;
   cur.tile0 = 2 * cluster_id; cur.tile1 = 2 * cluster_id + 1;
-  cur.delay = cur.live(1) ? p.shift : 0;
+  const bool walk_reorder = p.reorder != 0;
   const long long tl_tile0 = 2 * cluster_id + cur.stride;           // timeline: the second tile of slot 0 / slot 1
   // run body(0), body(1) alternately until both slots are out of tiles.  ONE copy of the body (the slot index is a
-  // run-time value): two inlined copies of the epilogue overflow the instruction cache.
-#define PN_WALK(body)                                                        \
-  for (;;) {                                                                 \
-    bool any = false;                                                        \
-    _Pragma("unroll 1")                                                      \
-    for (int t_ = 0; t_ < 2; ++t_) {                                         \
-      if (t_ == 1 && cur.delay > 0) { --cur.delay; any = true; continue; }   \
-      if (!cur.live(t_)) continue;                                           \
-      any = true;                                                            \
-      body(t_);                                                              \
-      cur.advance(t_);                                                       \
-    }                                                                        \
-    if (!any) break;                                                         \
+  // run-time value): two inlined copies overflow the instruction cache.
+#define PN_WALK(body)                                                                    \
+  {                                                                                      \
+    bool skip0 = false;                                                                  \
+    for (;;) {                                                                           \
+      bool any = false;                                                                  \
+      _Pragma("unroll 1")                                                                \
+      for (int t_ = 0; t_ < 2; ++t_) {                                                   \
+        int tt = t_;                                                                     \
+        if (!cur.live(tt)) continue;                                                     \
+        any = true;                                                                      \
+        if (tt == 0 && skip0) { skip0 = false; continue; }                               \
+        if (tt == 1 && walk_reorder && cur.ph1 == cur.np - 1 && cur.ph0 == 0 && cur.live(0)) { \
+          skip0 = true;                                                                  \
+          tt = 0;                                                                        \
+          --t_;                      /* slot 0 first, then come back for slot 1 */       \
+        }                                                                                \
+        body(tt);                                                                        \
+        cur.advance(tt);                                                                 \
+      }                                                                                  \
+      if (!any) break;                                                                   \
+    }                                                                                    \
   }
 
+  // Register hand-over between the warpgroups (one static instruction per warpgroup, warpgroup-aligned): the role warpgroup and
+  // the hand-over warps release, the hidden-epilogue warpgroups take (setmaxnreg.inc waits until the registers are free).  Each
+  // instruction sits at the top of the code it governs: ptxas budgets a region by the setmaxnreg that DOMINATES it (after a join
+  // of differently budgeted paths it assumes the smallest).
+  constexpr bool kNerfRegs = (MODE == IN_ENCODE || MODE == IN_LOAD2);
+  constexpr int kRoleRegs = role_regs(kNerfRegs), kOutRegs = out_regs(kNerfRegs);
+  if (warp >= W_PRODUCER) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRoleRegs));
   if (warp == W_PRODUCER) {
     // =============================== weight producer (both CTAs) ===============================
     if (lane == 0) {
@@ -575,6 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         const uint32_t par0 = (ar_par >> (2 * t)) & 1u, par1 = (ar_par >> (2 * t + 1)) & 1u;
         ar_par ^= 3u << (2 * t);
         const uint32_t d_tmem = tmem_base + (uint32_t)t * kHidden;
+        const uint32_t bar_done = p.ph[ph].epi == EPI_OUT ? bar_outfull(t) : bar_accfull(t);   // who drains this accumulator
         const uint32_t a_lo_t = a_lo0 + (uint32_t)t * (A_SLOT_BYTES >> 4);
         constexpr uint32_t kBlk = A_BLOCK_BYTES >> 4, kRing = RING_SLOT_BYTES >> 4;
         // operand halves: [0] = K blocks {0,1} written and the accumulator drained, [1] = K blocks {2,3} written
@@ -604,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           if (elect_one()) {
             issue_block(d_tmem, a_lo_t + 3 * kBlk, b_lo0 + slot * kRing, idesc, 1u);
             umma_commit_pair(bar_empty(slot));
-            umma_commit_pair(bar_accfull(t));
+            umma_commit_pair(bar_done);
           }
           __syncwarp();
           ring_next();
@@ -646,34 +709,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
               ring_next();
             }
           }
-          if (elect_one()) umma_commit_pair(bar_accfull(t));
+          if (elect_one()) umma_commit_pair(bar_done);
           __syncwarp();
         }
         tl_mark(p.timeline, tl_on, TL_MMA1 + ph * 2 + t);
       };
       PN_WALK(body)
     }
-  } else {
-    // =============================== epilogue / operand producers (both CTAs) ===============================
+  } else if (warp < W_PRODUCER) {
+    // =============================== hidden-epilogue warps (0-7) and hand-over warps (8-11), both CTAs ===============================
+    const bool is_out = warp >= W_OUT0;
     const int ew = warp;
-    const int ch = ew >> 2;                                // column interleave: this warp drains columns [64ch,+64) and [128+64ch,+64)
+    const int ch = (ew >> 2) & 1;                          // hidden epilogues: this warp drains columns [64ch,+64) and [128+64ch,+64)
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                           // row of the tile owned by this thread
     const uint32_t a_base = base + OFF_A;
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), xr = (uint32_t)(r & 7) << 4;
-    uint32_t acc_par = 0;
     constexpr bool kClassic = (MODE == IN_CLASSIC);          // classic NeRF: extra phase kinds, see DESIGN.md 4.3
     constexpr bool kCompute = (MODE == IN_ENCODE || MODE == IN_PLUECKER || kClassic);
     constexpr bool kNerf = (MODE == IN_ENCODE || MODE == IN_LOAD2);
     constexpr int kXin = (MODE == IN_ENCODE || kClassic) ? 3 : 6;
     const int kb_first = p.ph[0].nkb;                      // K blocks of the first phase (<= 4)
+    const int np = p.n_phases;
+    const long long stride = cur.stride;
 
     // global row of this thread in pair tile `tile`
     auto row_of = [&](long long tile) { return tile * PAIR_M + (long long)rank * TILE_M + r; };
 
-    // --- first-layer operand, "compute" modes.  The raw inputs of the NEXT tile are fetched one phase early into
-    //     registers (xin), turned into 32 packed operand elements (pre) while waiting for the output layer, and stored
-    //     as soon as the slot's operand buffer is free. ---
+    // --- first-layer operand, "compute" modes: 64 operand elements per row as two halves of 32 (16 packed words) ---
     auto fetch_input = [&](long long row, float* xin) {
 #pragma unroll
       for (int i = 0; i < kXin; ++i) xin[i] = 0.f;
@@ -683,37 +746,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         for (int i = 0; i < kXin; ++i) xin[i] = __ldg(src + i);
       }
     };
-    auto precompute_input = [&](const float* xin, bool row_live, uint32_t* pre) {
+    auto precompute_half = [&](const float* xin, bool row_live, uint32_t* pre, int half) {
       if (MODE == IN_ENCODE || kClassic) {
-        if (ch == 0) encode32<0>(xin, pre);
+        if (half == 0) encode32<0>(xin, pre);
         else encode32<1>(xin, pre);
       } else if (MODE == IN_PLUECKER) {
         // the 6 Pluecker features of the ray; the sampler's P replicated copies are folded into the weights
-        // (W_eff = sum over copies, tc_load_net), so the operand is 6 wide: one K = 16 step, written by the ch = 0 warps
+        // (W_eff = sum over copies, tc_load_net), so the operand is 6 wide: one K = 16 step, all of it in half 0
 #pragma unroll
         for (int i = 0; i < 16; ++i) pre[i] = 0u;
-        if (ch == 0 && row_live) {
+        if (half == 0 && row_live) {
           float f6[6];
           pluecker6(xin[0], xin[1], xin[2], xin[3], xin[4], xin[5], f6);
           pre[0] = pack_h2(f6[0], f6[1]); pre[1] = pack_h2(f6[2], f6[3]); pre[2] = pack_h2(f6[4], f6[5]);
         }
       }
     };
-    auto store_pre = [&](int t, const uint32_t* pre) {
+    auto store_half = [&](int t, const uint32_t* pre, int half) {
       const uint32_t dst = a_base + t * A_SLOT_BYTES + row_off;      // block 0
       if (MODE == IN_PLUECKER) {
-        if (ch == 0) {
+        if (half == 0) {
           st_shared_v4(dst + (0u ^ xr), pre[0], pre[1], pre[2], pre[3]);
           st_shared_v4(dst + (16u ^ xr), 0u, 0u, 0u, 0u);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          st_shared_v4(dst + ((uint32_t)((4 * ch + c) << 4) ^ xr), pre[4 * c], pre[4 * c + 1], pre[4 * c + 2], pre[4 * c + 3]);
+          st_shared_v4(dst + ((uint32_t)((4 * half + c) << 4) ^ xr), pre[4 * c], pre[4 * c + 1], pre[4 * c + 2], pre[4 * c + 3]);
       }
     };
-    // --- first-layer operand, "load" modes: warp (q, ch) loads rows q*32 + ch*16 .. +15 of K blocks [kb_lo, kb_lo+nblk) ---
-    auto load_input = [&](long long tile, int t, int kb_lo, int nblk) {
+    // --- first-layer operand, "load" modes (fp32 rows): the calling warp loads rows trow0 .. trow0 + 15 of K blocks [kb_lo, kb_lo+nblk) ---
+    auto load_input = [&](long long tile, int t, int kb_lo, int nblk, int trow0) {
       const long long row_base = tile * PAIR_M + (long long)rank * TILE_M;
       const int k0 = p.k0;
       for (int kb = 0; kb < nblk; ++kb) {
@@ -721,7 +784,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         const int k = (kb_lo + kb) * 64 + 2 * lane;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int trow = q * 32 + ch * 16 + i;
+          const int trow = trow0 + i;
           const long long grow = row_base + trow;
           float v0 = 0.f, v1 = 0.f;
           if (grow < p.M) {
@@ -734,9 +797,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
       }
     };
     // --- first-layer operand, fp16 "load" mode: the tile's rows are one contiguous range of 16-byte chunks (8 halves);
-    //     chunk g of the range -> (row, chunk-in-row) -> the swizzled operand position.  Up to kPf chunks per thread are
-    //     fetched into registers BEFORE the accumulator wait of the output phase (the loads do not depend on it) and
-    //     stored once the slot's operand buffer is free. ---
+    //     chunk g of the range -> (row, chunk-in-row) -> the swizzled operand position.  `tid` of `nt` threads share a range. ---
     const int cpr = p.k0 >> 3;                             // real chunks per row
     struct Range16 { int c_lo, w, total; uint32_t magic; };   // g / w == (g * magic) >> 20 for g < 128 * w, 2 <= w <= 32
     auto range16 = [&](int kb_lo, int nblk) {
@@ -772,44 +833,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         st_shared_v4(a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7), v.x, v.y, v.z, v.w);
       }
     };
-    // The same range as asynchronous copies (cp.async, 16 bytes each, zero-filled outside the tile): no staging registers
-    // -- nine 16-byte register prefetches per thread spilled at the 168-register ceiling, and a spilled load is a
-    // synchronous one (two exposed L2 round trips per tile).  Issued once the slot's operand buffer is free; the caller
-    // overlaps the latency with the head activations and calls cp_async_wait() before publishing.
-    auto cp_input16 = [&](long long tile, int t, int kb_lo, int nblk) {
-      const Range16 R = range16(kb_lo, nblk);
-      const Tile16 T = tile16(tile);
-#pragma unroll 3
-      for (int g = (int)threadIdx.x; g < R.total; g += N_EPI_WARPS * 32) {
-        const int row = (int)(((uint32_t)g * R.magic) >> 20), cc = g - row * R.w, c = R.c_lo + cc;
-        const bool ok = row < T.rows && c < cpr;
-        const uint4* src = ok ? T.src + (row * cpr + c) : reinterpret_cast<const uint4*>(p.in0);
-        const uint32_t dst = a_base + t * A_SLOT_BYTES + (cc >> 3) * A_BLOCK_BYTES + a_chunk_off(row, cc & 7);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto cp_async_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
     // synchronous form (prologue, and the second part of a first layer wider than 256): load 4 chunks, store 4 chunks
-    auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk) {
+    auto load_input16 = [&](long long tile, int t, int kb_lo, int nblk, int tid, int nt) {
       const Range16 R = range16(kb_lo, nblk);
-      constexpr int NT = N_EPI_WARPS * 32;
       const Tile16 T = tile16(tile);
-      for (int g0 = 0; g0 < R.total; g0 += 4 * NT) {
+      for (int g0 = 0; g0 < R.total; g0 += 4 * nt) {
         uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) fetch16(T, R, g0 + (int)threadIdx.x + u * NT, v[u]);
+        for (int u = 0; u < 4; ++u) fetch16(T, R, g0 + tid + u * nt, v[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) store16(t, R, g0 + (int)threadIdx.x + u * NT, v[u]);
+        for (int u = 0; u < 4; ++u) store16(t, R, g0 + tid + u * nt, v[u]);
       }
     };
     // publish this warp's share of slot t's operand: half 0 (its first K block; also "my accumulator reads are done"),
-    // half 1 (its second K block), or both at once (first-layer operands)
-    auto publish = [&](int t, int halves) {
+    // half 1 (its second K block), or both at once (first-layer operands).  narr arrivals per warp (the barriers count 16
+    // per phase: 8 hidden-epilogue warps x 2 CTAs x 1, or 4 hand-over warps x 2 CTAs x 2).
+    auto publish = [&](int t, int halves, int narr) {
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (lane < narr) {
         if (halves & 1) mbar_arrive_cluster(bar_aready(t, 0), 0);
         if (halves & 2) mbar_arrive_cluster(bar_aready(t, 1), 0);
       }
@@ -817,7 +860,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     auto fetch_dterm = [&](long long row) {
       float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < p.M) {
-        const long long idx = (p.M < 0x7fffffffLL) ? (long long)((uint32_t)row / (uint32_t)p.dir_div) : row / p.dir_div;
+        const uint32_t idx = (uint32_t)row / (uint32_t)p.dir_div;       // M < 2^32 (checked on the host): a 64-bit division is a real call
         d = __ldg(reinterpret_cast<const float4*>(p.dirterm) + idx);
       }
       return d;
@@ -827,35 +870,265 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     // this network's static weights: with programmatic dependent launch they run while the previous kernel of the stream drains.
     // The inputs (and every output buffer) belong to the dependency chain: wait for the predecessor's completion here.
     pdl_wait();
-    // prologue: first operands of both slots
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (!cur.live(t)) continue;
-      if (kCompute) {
-        float xin[6];
-        uint32_t pre[16];
-        const long long row = row_of(cur.tile(t));
-        fetch_input(row, xin);
-        precompute_input(xin, row < p.M, pre);
-        store_pre(t, pre);
-      } else if (MODE == IN_LOAD16) {
-        load_input16(cur.tile(t), t, 0, kb_first);
-      } else {
-        load_input(cur.tile(t), t, 0, kb_first);
-      }
-      publish(t, 3);
-    }
 
-    // The epilogue warps are the busiest resource of the kernel and a lone warp retires one DEPENDENT instruction every
-    // ~5 cycles, so their control flow is spelled out as plain nested loops (iteration -> phase -> slot; the two slots run
-    // in step) with everything per-phase hoisted, instead of the generic cursor walk of the single-thread roles.
-    float xin0[kXin], xin1[kXin];                          // raw inputs of each slot's NEXT tile, fetched one phase ahead
-    float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
+    if (is_out) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kOutRegs));
+      // =============================== hand-over warps: output layer + next tile's first operand ===============================
+      // Per slot and tile: fetch what the hand-over needs (the next tile's raw inputs, this tile's view-direction term), turn the
+      // inputs into the packed first-layer operand IN REGISTERS, then wait for "output full".  From there the slot's critical path
+      // is: tcgen05.ld of the few output columns -> operand stores (or cp.async copies) -> proxy fence -> arrive; the activations
+      // of the head outputs and every global store come after the slot has been handed back to the tensor pipe.
+      const int htid = (int)threadIdx.x - W_OUT0 * 32;       // 0..127
+      constexpr int HNT = N_OUT_WARPS * 32;
+      uint32_t out_par = 0, in_par = 0;
+      // the full first-layer operand of row_of(tile) -> slot t's block(s)
+      auto build_first = [&](long long tile, int t) {
+        if (kCompute) {
+          float xin[kXin];
+          uint32_t pre[32];
+          const long long row = row_of(tile);
+          fetch_input(row, xin);
+          precompute_half(xin, row < p.M, pre, 0);
+          if (MODE != IN_PLUECKER) precompute_half(xin, row < p.M, pre + 16, 1);
+          store_half(t, pre, 0);
+          if (MODE != IN_PLUECKER) store_half(t, pre + 16, 1);
+        } else if (MODE == IN_LOAD16) {
+          load_input16(tile, t, 0, kb_first, htid, HNT);
+        } else {
+          load_input(tile, t, 0, kb_first, q * 32);
+          load_input(tile, t, 0, kb_first, q * 32 + 16);
+        }
+      };
+      // prologue: first operands of both slots
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        if (!cur.live(t)) continue;
+        build_first(cur.tile(t), t);
+        publish(t, 3, 2);
+      }
+      const int layer_out = p.ph[np - 1].layer, n_pad_out = p.ph[np - 1].n_pad;
+      const int n_out = p.n_out;
+      const uint32_t tmem_q = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* stg = reinterpret_cast<float*>(sm + OFF_STAGE) + q * STAGE_FLOATS;
+
+      // ---- the slot's critical path: "output full" -> next operand on its way -> accumulator columns [c0, c0 + 48) in registers ->
+      //      (last chunk) operand landed -> publish.  `pre` = the next tile's packed first-layer operand (compute modes). ----
+      auto wait_outfull = [&](int t) {
+        mbar_wait_polite(bar_outfull(t), (out_par >> t) & 1u, p.error_flag, 6);
+        out_par ^= 1u << t;
+        tc_fence_after();
+      };
+      auto start_next_operand = [&](long long tile, int t, const uint32_t* pre) {
+        // the slot's operand buffer is free (the output layer has read it)
+        if (kCompute) {
+          store_half(t, pre, 0);
+          if (MODE != IN_PLUECKER) store_half(t, pre + 16, 1);
+        } else if (MODE == IN_LOAD16) {
+          // three instructions instead of 2 304 16-byte copies with their address arithmetic (2 K cycles on the slot's critical path)
+          if (htid == 0) {
+            const int row0 = (int)(row_of(tile + stride) - r);
+            mbar_arrive_expect_tx(bar_infull(t), (uint32_t)kb_first * A_BLOCK_BYTES);
+            for (int kb = 0; kb < kb_first; ++kb)
+              tma_load_box(a_base + t * A_SLOT_BYTES + kb * A_BLOCK_BYTES, &p.tmap_in, kb * 64, row0, bar_infull(t));
+          }
+        } else {
+          load_input(tile + stride, t, 0, kb_first, q * 32);
+          load_input(tile + stride, t, 0, kb_first, q * 32 + 16);
+        }
+      };
+      auto hand_back = [&](int t, bool has_next) {
+        if (MODE == IN_LOAD16 && has_next) {                       // the next tile's rows have landed
+          mbar_wait_polite(bar_infull(t), (in_par >> t) & 1u, p.error_flag, 7);
+          in_par ^= 1u << t;
+        }
+        publish(t, 3, 2);
+      };
+      // what the critical path prepares before "output full": the next tile's operand in registers, an L2 prefetch of its rows
+      auto prepare_next = [&](long long tile, bool has_next, uint32_t* pre) {
+        if (kCompute && has_next) {
+          float xin[kXin];
+          const long long nrow = row_of(tile + stride);
+          fetch_input(nrow, xin);
+          precompute_half(xin, nrow < p.M, pre, 0);
+          if (MODE != IN_PLUECKER) precompute_half(xin, nrow < p.M, pre + 16, 1);
+        }
+        if (MODE == IN_LOAD16 && htid == 0 && has_next) {
+          // pull the next tile's rows (one contiguous range) towards L2
+          const long long row0 = row_of(tile + stride) - r;
+          long long nrow = p.M - row0;
+          if (nrow > TILE_M) nrow = TILE_M;
+          if (nrow > 0) {
+            const uint32_t bytes = (uint32_t)(nrow * (long long)p.k0 * 2);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const __half*>(p.in0) + row0 * p.k0), "r"(bytes) : "memory");
+          }
+        }
+      };
+      // ---- off the critical path: head activations of output columns [c0, c0 + 48) and the stores.  A warp's 32 rows x n_out
+      //      floats are ONE contiguous global range, but thread = row: direct stores would scatter 4 bytes over 32 sectors per
+      //      instruction.  Activation in registers (branch-free coefficient form), then rows_per_pass rows at a time through the
+      //      lane quadrant's staging window and out as coalesced stores. ----
+      auto emit_heads = [&](float* v, int c0, long long row) {
+        const float* bo = s_bias + layer_out * kHidden + c0;
+        // blocks of 8 columns: a block of padding / linear outputs (p.head_linear) skips the SFU form -- the SFU is the unit
+        // the hidden epilogues of these kernels saturate, and the sampler's direction outputs (16 of 27 columns) are linear
+        auto activate = [&](auto c0_tag) {
+          constexpr int C0 = decltype(c0_tag)::value;
 #pragma unroll
-    for (int i = 0; i < kXin; ++i) { xin0[i] = 0.f; xin1[i] = 0.f; }
-    const int np = p.n_phases;
+          for (int g = 0; g < 6; ++g) {
+            if (C0 + 8 * g >= n_out) continue;
+            if ((p.head_linear >> (C0 / 8 + g)) & 1u) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * g + i] += bo[8 * g + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * g + i] = head_apply_tab(v[8 * g + i] + bo[8 * g + i], p.head_tab[C0 + 8 * g + i]);
+            }
+          }
+        };
+        if (c0 == 0) activate(std::integral_constant<int, 0>());
+        else activate(std::integral_constant<int, 48>());
+        int w = n_out - c0;                                  // real columns of this chunk
+        if (w > 48) w = 48;
+        if (w <= 0) return;
+        int rpp = (STAGE_FLOATS / w) & ~3;                   // rows per staging pass (a multiple of 4: 16-byte aligned passes)
+        if (rpp > 32) rpp = 32;
+        const bool whole_rows = w == n_out;                  // the usual case: the staged rows are one contiguous global range
+        const long long grow_w = row - lane;                 // global row of the quadrant's first thread (a multiple of 32)
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += rpp) {
+          const int l = lane - r0;
+          if (l >= 0 && l < rpp) {
+            float* d = stg + l * w;
+#pragma unroll
+            for (int o = 0; o < 48; ++o)
+              if (o < w) d[o] = v[o];
+          }
+          __syncwarp();
+          const long long nl = p.M - (grow_w + r0);
+          int nrows = 32 - r0 < rpp ? 32 - r0 : rpp;
+          if (nl < nrows) nrows = nl > 0 ? (int)nl : 0;
+          const int nfl = nrows * w;
+          float* dst = p.out + (grow_w + r0) * n_out;
+          if (whole_rows && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (int i = lane * 4; i < nfl; i += 128) {
+              if (i + 4 <= nfl) {
+                *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stg + i);
+              } else {
+                for (int k = i; k < nfl; ++k) dst[k] = stg[k];
+              }
+            }
+          } else if (whole_rows) {
+            for (int i = lane; i < nfl; i += 32) dst[i] = stg[i];
+          } else {
+            for (int i = lane; i < nfl; i += 32) {
+              const int rr = i / w, cc = i - rr * w;
+              dst[(long long)rr * n_out + c0 + cc] = stg[i];
+            }
+          }
+          __syncwarp();
+        }
+      };
+      auto ld48 = [&](uint32_t taddr, int c0, float* v) {
+        tmem_ld16(taddr + c0, v);
+        if (n_pad_out > c0 + 16) tmem_ld16(taddr + c0 + 16, v + 16);
+        if (n_pad_out > c0 + 32) tmem_ld16(taddr + c0 + 32, v + 32);
+        tmem_wait_ld();
+      };
+      // NeRF outputs: one float4 per row
+      auto emit_raw = [&](const float* v, int t, long long row, const float4& dterm) {
+        if (row >= p.M) return;
+        const float* bo = s_bias + layer_out * kHidden;
+        if (kClassic) {
+          // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
+          const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
+          *reinterpret_cast<float4*>(p.out + row * 4) =
+              make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
+        } else {
+          // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
+          *reinterpret_cast<float4*>(p.out + row * 4) =
+              make_float4(v[0] + bo[0] + dterm.x, v[1] + bo[1] + dterm.y, v[2] + bo[2] + dterm.z, v[3] + bo[3] + dterm.w);
+        }
+      };
+      constexpr int kPre = (kCompute && MODE != IN_PLUECKER) ? 32 : 16;
+      constexpr int kV = (kClassic || kNerf) ? 16 : 48;
+      int it_idx = 0;
+      for (long long T0 = 2 * cluster_id; T0 < n_pairs; T0 += stride, ++it_idx) {
+        const int nslots = (T0 + 1 < n_pairs) ? 2 : 1;
+        const bool tl_o = kTimeline && blockIdx.x == 0 && it_idx == 1 && warp == W_OUT0 && lane == 0;
+        if (!(kClassic || kNerf) && n_pad_out > 48) {
+          // more than 48 head columns (16 samples per ray): the chunks of a slot go one after the other -- the slot is published once
+          // its LAST chunk is in registers, after the first one has been activated and stored
+#pragma unroll 1
+          for (int t = 0; t < nslots; ++t) {
+            const long long tile = T0 + t;
+            const bool has_next = tile + stride < n_pairs;
+            uint32_t pre[kPre];
+            prepare_next(tile, has_next, pre);
+            wait_outfull(t);
+            if (has_next) start_next_operand(tile, t, pre);
+#pragma unroll 1
+            for (int c0 = 0; c0 < n_pad_out; c0 += 48) {
+              float v[48];
+              ld48(tmem_q + (uint32_t)t * kHidden, c0, v);
+              if (c0 + 48 >= n_pad_out) hand_back(t, has_next);
+              emit_heads(v, c0, row_of(tile));
+            }
+          }
+          continue;
+        }
+        // Both slots' critical paths first, the outputs afterwards: slot 1's "output full" arrives one hidden epilogue after slot
+        // 0's, and behind slot 0's head activations (which queue at the SFU the hidden epilogues saturate: ~5 K cycles) its
+        // hand-over would come 2-3 K cycles late, with the hidden-epilogue warps waiting.
+        float v0[kV], v1[kV];
+        float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
+        {
+          const bool has_next = T0 + stride < n_pairs;
+          tl_mark(p.timeline, tl_o, TL_OUT + 0);
+          uint32_t pre[kPre];
+          prepare_next(T0, has_next, pre);
+          if (kNerf) dterm0 = fetch_dterm(row_of(T0));
+          tl_mark(p.timeline, tl_o, TL_OUT + 1);
+          wait_outfull(0);
+          if (has_next) start_next_operand(T0, 0, pre);
+          if (kV == 16) { tmem_ld16(tmem_q, v0); tmem_wait_ld(); }
+          else ld48(tmem_q, 0, v0);
+          tl_mark(p.timeline, tl_o, TL_OUT + 2);
+          hand_back(0, has_next);
+          tl_mark(p.timeline, tl_o, TL_OUT + 3);
+        }
+        if (nslots == 2) {
+          const bool has_next = T0 + 1 + stride < n_pairs;
+          tl_mark(p.timeline, tl_o, TL_OUT + 6);
+          uint32_t pre[kPre];
+          prepare_next(T0 + 1, has_next, pre);
+          if (kNerf) dterm1 = fetch_dterm(row_of(T0 + 1));
+          tl_mark(p.timeline, tl_o, TL_OUT + 7);
+          wait_outfull(1);
+          if (has_next) start_next_operand(T0 + 1, 1, pre);
+          if (kV == 16) { tmem_ld16(tmem_q + kHidden, v1); tmem_wait_ld(); }
+          else ld48(tmem_q + kHidden, 0, v1);
+          tl_mark(p.timeline, tl_o, TL_OUT + 8);
+          hand_back(1, has_next);
+          tl_mark(p.timeline, tl_o, TL_OUT + 9);
+        }
+        if (kClassic || kNerf) {
+          emit_raw(v0, 0, row_of(T0), dterm0);
+          if (nslots == 2) emit_raw(v1, 1, row_of(T0 + 1), dterm1);
+        } else {
+          emit_heads(v0, 0, row_of(T0));
+          tl_mark(p.timeline, tl_o, TL_OUT + 4);
+          if (nslots == 2) emit_heads(v1, 0, row_of(T0 + 1));
+          tl_mark(p.timeline, tl_o, TL_OUT + 10);
+        }
+      }
+    } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    // =============================== hidden-epilogue warps ===============================
+    // These are the busiest warps of the kernel and a lone warp retires one DEPENDENT instruction every ~5 cycles, so their
+    // control flow is spelled out as plain nested loops (iteration -> phase -> slot; the two slots run in step) with everything
+    // per-phase hoisted, instead of the generic cursor walk of the single-thread roles.
+    uint32_t acc_par = 0;
     const bool more = p.ph[0].epi == EPI_MORE;
-    const long long stride = cur.stride;
     const uint32_t bias_base = base + OFF_BIAS + (uint32_t)(ch * 64) * 4u;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row = a_base + row_off;
@@ -872,17 +1145,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
           acc_par ^= 1u << t;
           tc_fence_after();
-          if (MODE == IN_LOAD16) load_input16(T0 + t, t, kb_first, p.ph[1].nkb);
-          else load_input(T0 + t, t, kb_first, p.ph[1].nkb);
-          publish(t, 3);
+          if (MODE == IN_LOAD16) load_input16(T0 + t, t, kb_first, p.ph[1].nkb, (int)threadIdx.x, N_EPI_WARPS * 32);
+          else load_input(T0 + t, t, kb_first, p.ph[1].nkb, q * 32 + ch * 16);
+          publish(t, 3, 1);
         }
         ph = 1;
       }
-      // ---------------- hidden phases ----------------
 #pragma unroll 1
       for (; ph < np - 1; ++ph) {
         const uint32_t bias_addr = bias_base + (uint32_t)p.ph[ph].layer * (uint32_t)(kHidden * 4);
-        const bool last_hidden = ph == np - 2;
         if (kClassic && p.ph[ph].epi == EPI_MORE) {
           // A layer whose input is a concatenation (helpers.py:833-834, 839): the K = 256 part has just been multiplied;
           // the other part -- the encoded points (skip layer) or the encoded view direction (view layer) -- is written
@@ -902,8 +1173,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
             tc_fence_after();
             uint32_t pre[16];
             if (src == MORE_PTS) {
-              precompute_input(x3, row < p.M, pre);
-              store_pre(t, pre);
+              precompute_half(x3, row < p.M, pre, ch);
+              store_half(t, pre, ch);
             } else if (ch == 0) {
               // gamma_4(viewdir): [v, sin(2^l v), cos(2^l v)]_{l<4}, 27 values + 5 zeros = K block 0, chunks 0..3
               float e[32];
@@ -926,7 +1197,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
                 st_shared_v4(dst + ((uint32_t)(c << 4) ^ xr), pack_h2(e[8 * c], e[8 * c + 1]), pack_h2(e[8 * c + 2], e[8 * c + 3]),
                              pack_h2(e[8 * c + 4], e[8 * c + 5]), pack_h2(e[8 * c + 6], e[8 * c + 7]));
             }
-            publish(t, 3);
+            publish(t, 3, 1);
           }
           continue;
         }
@@ -937,30 +1208,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         for (int t = 0; t < nslots; ++t) {
           const bool tl_e = tl_it && ew == 0 && ph == 2 && t == 0;      // fine-grained stamps of one hidden epilogue
           tl_mark(p.timeline, tl_e, TL_EPI + 0);
-          if (last_hidden) {
-            // one phase before the output layer: start the global loads the output epilogue will need.  Each slot's
-            // registers are written directly (no select on the loaded values: that would wait for the loads here).
-            const long long tile = T0 + t;
-            const bool nxt = tile + stride < n_pairs;
-            if (kCompute && nxt) {
-              if (t == 0) fetch_input(row_of(tile + stride), xin0);
-              else fetch_input(row_of(tile + stride), xin1);
-            }
-            if (kNerf && ch == 0) {
-              if (t == 0) dterm0 = fetch_dterm(row_of(tile));
-              else dterm1 = fetch_dterm(row_of(tile));
-            }
-            if (MODE == IN_LOAD16 && threadIdx.x == 0 && nxt) {
-              // pull the next tile's rows (one contiguous range) towards L2
-              const long long row0 = row_of(tile + stride) - r;
-              long long nrow = p.M - row0;
-              if (nrow > TILE_M) nrow = TILE_M;
-              if (nrow > 0) {
-                const uint32_t bytes = (uint32_t)(nrow * (long long)p.k0 * 2);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const __half*>(p.in0) + row0 * p.k0), "r"(bytes) : "memory");
-              }
-            }
-          }
           tl_mark(p.timeline, tl_e, TL_EPI + 1);
           mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
           acc_par ^= 1u << t;
@@ -995,9 +1242,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
               else if (side) dot += epilogue_store64<0, true>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr, wa + 512u);
               else epilogue_store64<0>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
             }
-            if (side)      // this thread's half of alpha_linear(h) for its row; the output phase adds the two halves
+            if (side)      // this thread's half of alpha_linear(h) for its row; the hand-over warps add the two halves
               s_bias[(p.alpha_row + 1 + t) * kHidden + ch * TILE_M + r] = dot;
-            publish(t, 3);
+            publish(t, 3, 1);
           } else {
           tmem_ld32(taddr + 128, v + 64);
           tmem_ld32(taddr + 128 + 32, v + 96);
@@ -1005,10 +1252,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           tl_mark(p.timeline, tl_e, TL_EPI + 3);
           tmem_wait_ld();                                      // every accumulator column of this thread is in registers
           tl_mark(p.timeline, tl_e, TL_EPI + 4);
-          if (p.split) publish(t, 1);                          // K blocks {0,1} are ready: the next layer's MMAs may start
+          const bool split = (p.split & 1) || ((p.split & 2) && ph == 0);
+          if (split) publish(t, 1, 1);                         // K blocks {0,1} are ready: the next layer's MMAs may start
           epilogue_store64<ACT>(v + 64, bias_addr + 512u, row_base + 2 * A_BLOCK_BYTES, xr);
           tl_mark(p.timeline, tl_e, TL_EPI + 5);
-          publish(t, p.split ? 2 : 3);
+          publish(t, split ? 2 : 3, 1);
           }
           tl_mark(p.timeline, tl_e, TL_EPI + 6);
           tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
@@ -1016,135 +1264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
         }
       }
-      // ---------------- output phase ----------------
-      // Order matters: the accumulator is pulled into registers, the next tile's first-layer operand is written and the
-      // slot is PUBLISHED before anything goes to global memory -- the proxy fence in publish() is a CTA-wide memory
-      // barrier, and behind a global store it would wait for the store's L2 round trip.
-      const int layer_out = p.ph[np - 1].layer, n_pad_out = p.ph[np - 1].n_pad;
-#pragma unroll 1
-      for (int t = 0; t < nslots; ++t) {
-        const long long tile = T0 + t;
-        const bool has_next = tile + stride < n_pairs;
-        const bool tl_o = tl_it && ew == 0;
-        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 0);
-        uint32_t pre[16];
-        if (kCompute && has_next) {                            // overlaps the wait below
-          float xin[kXin];
-#pragma unroll
-          for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
-          precompute_input(xin, row_of(tile + stride) < p.M, pre);
-        }
-        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 1);
-        mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
-        acc_par ^= 1u << t;
-        tc_fence_after();
-        tl_mark(p.timeline, tl_it && ew == 0, TL_ACC + ph * 2 + t);
-        tl_mark(p.timeline, tl_f, TL_FACC + ph * 2 + t);
-        const uint32_t taddr = tmem_lane + (uint32_t)t * kHidden;
-        const long long row = row_of(tile);
-        const bool live = row < p.M;
-        // output columns [48 ch, 48 ch + 48): the ch = 1 warps only have work for outputs wider than 48 (S = 16)
-        float v[48];
-        const int c0 = ch * 48;
-        if (c0 < n_pad_out) {
-          tmem_ld16(taddr + c0, v);
-          if (n_pad_out > c0 + 16) tmem_ld16(taddr + c0 + 16, v + 16);
-          if (n_pad_out > c0 + 32) tmem_ld16(taddr + c0 + 32, v + 32);
-          tmem_wait_ld();
-        }
-        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 2);
-        if (has_next) {
-          if (kCompute) store_pre(t, pre);
-          else if (MODE == IN_LOAD16) cp_input16(tile + stride, t, 0, kb_first);      // lands under the head activations
-          else load_input(tile + stride, t, 0, kb_first);
-        }
-        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 3);
-        if (MODE != IN_LOAD16) {
-          publish(t, 3);
-          tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
-          tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
-          tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
-        }
-        if (kClassic) {
-          if (ch == 0 && live) {
-            // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
-            const float* bo = s_bias + layer_out * kHidden;
-            const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
-            *reinterpret_cast<float4*>(p.out + row * 4) =
-                make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
-          }
-        } else if (kNerf) {
-          if (ch == 0 && live) {
-            // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
-            const float* bo = s_bias + layer_out * kHidden;
-            const float4 d = t ? dterm1 : dterm0;
-            *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
-          }
-        } else if (MODE == IN_LOAD16 || c0 < n_pad_out) {
-          // Head outputs (sampler / refine).  A warp's 32 rows x n_out floats are ONE contiguous global range, but thread = row:
-          // direct stores would scatter 4 bytes over 32 sectors per instruction.  Activation in registers, then rows_per_pass
-          // rows at a time through the lane quadrant's staging window and out as 16-byte stores.  n_out > 48: the quadrant's
-          // two warps (columns [0,48) and [48,96)) share the window and meet at a 64-thread named barrier.
-          const int n_out = p.n_out, rpp = p.out_rpp;
-          const bool two = n_pad_out > 48, mine = MODE != IN_LOAD16 || c0 < n_pad_out;
-          const float* bo = s_bias + layer_out * kHidden + c0;
-          auto activate = [&](auto c0_tag) {
-            constexpr int C0 = decltype(c0_tag)::value;
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-              if (n_pad_out > C0 + 16 * g) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[16 * g + i] = head_apply_tab(v[16 * g + i] + bo[16 * g + i], p.head_tab[C0 + 16 * g + i]);
-              }
-            }
-          };
-          if (ch == 0) activate(std::integral_constant<int, 0>());
-          else if (mine) activate(std::integral_constant<int, 48>());
-          if (MODE == IN_LOAD16) {                               // the asynchronous operand copies have landed by now
-            cp_async_wait();
-            publish(t, 3);
-            tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
-            tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
-            tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
-          }
-          auto sync_out = [&]() {
-            if (two) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            else __syncwarp();
-          };
-          float* stg = reinterpret_cast<float*>(sm + OFF_STAGE) + q * STAGE_FLOATS;
-          const long long grow_w = row - lane;                   // global row of the quadrant's first thread (a multiple of 32)
-          const int i0 = (two ? ch * 32 + lane : lane) * 4, istep = two ? 256 : 128;
-#pragma unroll 1
-          for (int r0 = 0; mine && r0 < 32; r0 += rpp) {
-            const int l = lane - r0;
-            if (l >= 0 && l < rpp) {
-              float* d = stg + l * n_out + c0;
-#pragma unroll
-              for (int o = 0; o < 48; ++o)
-                if (c0 + o < n_out) d[o] = v[o];
-            }
-            sync_out();
-            const long long nl = p.M - (grow_w + r0);
-            int nrows = 32 - r0 < rpp ? 32 - r0 : rpp;
-            if (nl < nrows) nrows = nl > 0 ? (int)nl : 0;
-            const int nfl = nrows * n_out;
-            float* dst = p.out + (grow_w + r0) * n_out;
-            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              for (int i = i0; i < nfl; i += istep) {
-                if (i + 4 <= nfl) {
-                  *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(stg + i);
-                } else {
-                  for (int k = i; k < nfl; ++k) dst[k] = stg[k];
-                }
-              }
-            } else {
-              for (int i = i0 >> 2; i < nfl; i += istep >> 2) dst[i] = stg[i];
-            }
-            sync_out();
-          }
-        }
-        tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 4);
-      }
+    }
     }
   }
 #undef PN_WALK
@@ -1388,11 +1508,40 @@ int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, cons
 static int tc_max_clusters(const void* func, int* out);
 constexpr int kMaxDevices = 64;
 
+// The [M, K0] fp16 first-layer input as a 2-D tensor map (box = one K block of a 128-row tile, 128-byte swizzle, zero fill outside).
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up at run time so that the library needs no -lcuda.
+static int tc_encode_input_map(CUtensorMap* map, const void* base, long long M, int k0) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    PN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) { set_error("tc: the driver does not export cuTensorMapEncodeTiled"); return PN_ECUDA; }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)k0, (cuuint64_t)M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)k0 * 2};               // bytes between rows (a multiple of 16: K0 % 8 == 0)
+  const cuuint32_t box[2] = {64, (cuuint32_t)tc::TILE_M};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled failed (%d) for a [%lld, %d] fp16 input", (int)rc, M, k0); return PN_ECUDA; }
+  return PN_OK;
+}
+// schedule knob (default = the measured best; the environment override is a tuning aid): see PN_WALK
+static int tc_env_reorder() {
+  static const int v = getenv("PN_TC_REORDER") ? atoi(getenv("PN_TC_REORDER")) : 1;
+  return v != 0;
+}
+
 // run_network with the classic NeRF: pts [M,3] (M = N*S rows), per-ray view directions, both encoded in-kernel -> raw [M,4]
 int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, int viewdir_stride, int S, int64_t M, float* raw,
                            cudaStream_t stream) {
   if (!n.loaded || !n.classic) { set_error("classic NeRF weights not loaded on the tensor-core tier"); return PN_ESTATE; }
   if (M == 0) return PN_OK;
+  PN_REQUIRE(M < (1LL << 32), "tc: %lld rows in one launch (limit 2^32 - 1)", (long long)M);
   const ClassicLayout L = classic_layout();
   tc::Params p{};
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(n.blob);
@@ -1402,7 +1551,7 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   p.in0 = pts; p.in_stride = 3; p.M = M; p.out = raw;
   p.vdir = viewdirs; p.vdir_stride = viewdir_stride; p.dir_div = S > 0 ? S : 1;
   p.alpha_row = kClassicAlphaRow; p.alpha_bias = n.alpha_bias;
-  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.shift = 0;
+  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.reorder = tc_env_reorder();
   p.n_phases = 13;
   for (int i = 0; i < 13; ++i) {
     const ClassicPhase& c = kClassicPhases[i];
@@ -1454,6 +1603,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     return PN_ESTATE;
   }
   if (Lc.M == 0) return PN_OK;
+  PN_REQUIRE(Lc.M < (1LL << 32), "tc: %lld rows in one launch (limit 2^32 - 1)", (long long)Lc.M);
   TcLayout L = tc_layout(n.net_id, n.n_layers, n.in_dim, n.out_dim);
   tc::Params p{};
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(n.blob);
@@ -1465,32 +1615,32 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   p.k0 = n.in_dim[0];
   p.in0 = Lc.in0; p.in_stride = Lc.in_stride;
   p.M = Lc.M; p.out = Lc.out;
+  uint32_t nonlinear_blocks = 0;
   for (int c = 0; c < 96; ++c) {
     int kind = HEAD_NONE;
     for (int g = 0; g < 3; ++g)
       if (c >= Lc.head_lo[g] && c < Lc.head_lo[g + 1]) kind = Lc.head_act[g];
     p.head_tab[c] = tc::head_coeffs(kind);
+    if (kind != HEAD_NONE && c < p.n_out) nonlinear_blocks |= 1u << (c / 8);
   }
+  p.head_linear = ~nonlinear_blocks;
   p.error_flag = n.error_flag;
   p.timeline = g_tc_timeline;
   {
     // schedule knobs (defaults = the measured best; the environment overrides are a tuning aid)
-    static const int env_shift = getenv("PN_TC_SHIFT") ? atoi(getenv("PN_TC_SHIFT")) : -1;
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
-    p.split = env_split >= 0 ? (env_split != 0) : 0;
-    // head output staging: as many rows per pass as fit the quadrant's window, a multiple of 4 (16-byte aligned passes)
-    {
-      int rpp = (tc::STAGE_FLOATS / (p.n_out > 0 ? p.n_out : 1)) & ~3;
-      p.out_rpp = rpp > 32 ? 32 : rpp;
-    }
-    p.shift = 0;           // the two slots run in step (the epilogue warps' loops assume it)
-    (void)env_shift;
+    p.split = env_split >= 0 ? env_split : 0;            // bit 0: every hidden epilogue, bit 1: the first layer's only
+    p.reorder = tc_env_reorder();
+    p.out_rpp = 0;         // (the hand-over warps derive the rows per staging pass from the chunk width)
   }
   if (Lc.input_mode == IN_LOAD16) {
     if (p.k0 % 8 != 0 || Lc.in_stride != p.k0 || (reinterpret_cast<uintptr_t>(Lc.in0) & 15) != 0) {
       set_error("tc fp16 input: needs a dense, 16-byte aligned [M, K0] fp16 tensor with K0 %% 8 == 0 (K0 = %d, stride %d)", p.k0, Lc.in_stride);
       return PN_EINVAL;
     }
+    PN_REQUIRE(Lc.M < (1LL << 31), "tc fp16 input: %lld rows in one launch (tensor-map coordinates are 32-bit)", (long long)Lc.M);
+    const int rc = tc_encode_input_map(&p.tmap_in, Lc.in0, Lc.M, p.k0);
+    if (rc != PN_OK) return rc;
   }
   if (Lc.input_mode == IN_PLUECKER) {
     if (6 * Lc.P != n.in_dim[0] || !L.has_fold) { set_error("tc sampler: 6P != first-layer width"); return PN_EINVAL; }
@@ -1517,8 +1667,6 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   for (int l = 1; l < last; ++l) add_phase(l, 4, 4, kHidden, 0, tc::EPI_HIDDEN, L.chunk_off[l]);
   add_phase(last, 4, 4, L.n_pad[last], 0, tc::EPI_OUT, L.chunk_off[last], L.merged[last]);
   p.n_phases = np;
-  if (p.shift < 0) p.shift = 0;
-  if (p.shift > np - 1) p.shift = np - 1;
 
   // NeRF: view-direction term of the last layer, fp32, one row per ray (run_network) or per sample (forward)
   if (n.net_id == PN_NET_NERF && Lc.input_mode == IN_ENCODE && Lc.dirterm_ready) {
