@@ -288,13 +288,16 @@ def main():
     images_pinned = torch.from_numpy(np.ascontiguousarray(scene.images_ref)).pin_memory()
     graph = [None]
 
-    def step_sharded():
+    def step_launches():
         if peer is None:
-            R.render_prepared(prep)
-        elif graph[0] is not None:
+            return R.render_prepared(prep)
+        multigpu.render_views_sharded_p2p(R, prep, peer)          # frame numbers are kept on the device (graph-replayable)
+
+    def step_sharded():
+        if graph[0] is not None:
             graph[0].replay()
         else:
-            multigpu.render_views_sharded_p2p(R, prep, peer)      # frame numbers are kept on the device (graph-replayable)
+            step_launches()
 
     def barrier():
         if dist is not None:
@@ -330,14 +333,16 @@ def main():
         clocks.start()
     for _ in range(args.warmup):
         step_sharded()
+    # N = 1 stays kernel by kernel with the per-stage events inside the timed region (measured: the graph buys nothing at 3.6 ms per
+    # step -- 161.7 vs 164.3 Mrays/s, inside the run-to-run spread -- and the roofline's kernel time then comes from the timed region itself)
     use_graph = peer is not None and not args.no_graph
     if use_graph:
-        # N > 1: a rank's step is ~0.5 ms of kernels at N = 8, so the whole step (7 kernels + flag store + flag wait) is captured
-        # once and replayed; the per-stage events cannot live inside a graph, so the stage times come from a profiled leg below
+        # the whole step (7 kernels; N > 1: + flag store + flag wait, a rank's step is ~0.5 ms of kernels at N = 8) is captured once
+        # and replayed; the per-stage events cannot live inside a graph, so the stage times come from a profiled leg below
         barrier()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            multigpu.render_views_sharded_p2p(R, prep, peer)
+            graph_out = step_launches()                    # N = 1: the frame tensors live in the graph's pool
         graph[0] = g
         barrier()
         for _ in range(2):
@@ -531,7 +536,8 @@ def main():
         "precision_tier": precision + (" operands, fp32 accumulate (tcgen05)" if precision == "fp16" else " SIMT"),
         "fps_504x378": value * 1e6 / n_view, "ms_per_view": ms_per_step / V, "wall_s_timed_region": t_wall,
         "rays_per_gpu_per_step": n_rays_rank, "gathered_frame_bit_identical_to_single_gpu": check,
-        "step_launch": ("one CUDA graph per rank (7 kernels + flag store + flag wait), replayed" if use_graph else "kernel by kernel"),
+        "step_launch": (("one CUDA graph per rank (7 kernels + flag store + flag wait), replayed" if peer is not None else "one CUDA graph (7 kernels), replayed")
+                        if use_graph else "kernel by kernel"),
         "kernel_ms_per_step_by_rank": own_all,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (R.image_bytes + V * (12 + 12 * NN) * 4)),
                 "d2h_bytes_per_step": int(n_rays_step * 16), "ms_per_step": e2e_step_ms, "frame_matches_device_path": e2e_check,

@@ -12,9 +12,10 @@
 //
 //   D_slot[256 x N] (fp32, TMEM, 128 lanes per CTA) = A_slot[256 x K] (fp16, smem, K-major, 128B swizzle) * W^T
 //
-// Pipeline (per slot the layers are strictly sequential; the two slots are half a period apart, so the tensor pipe
-// runs slot Y's layer while the CUDA cores drain slot X's accumulator):
+// Pipeline (per slot the layers are strictly sequential; the two slots run in step, so the tensor pipe runs slot Y's layer
+// while the CUDA cores drain slot X's accumulator).  Two CTA shapes (use_handover()):
 //
+//   ELU kernels (sampler, refine) -- 16 warps, hand-over warps:
 //   warp 12     weight producer (both CTAs): streams its half of every K block (16 KB) of every layer, in
 //               consumption order, through a 5-slot ring with cp.async.bulk + mbarrier complete_tx; the global image
 //               is pre-swizzled into the UMMA canonical layout so a linear copy lands a ready B operand.
@@ -23,17 +24,20 @@
 //               after the last block commit "accumulator full" (hidden layers) or "output full" to both CTAs.
 //               follower: relay -- forwards "my half of the weights landed" to the leader's full barrier.
 //   warps 0-7   hidden epilogues (8 warps; warp = TMEM lane quadrant x 128-column half; thread = row):
-//               tcgen05.ld the accumulator, bias + ReLU/ELU, convert to fp16 and store straight into the slot's
+//               tcgen05.ld the accumulator, bias + ELU, convert to fp16 and store straight into the slot's
 //               A operand for the next layer (the swizzle makes row-per-thread 16-byte stores conflict free), then
 //               fence.proxy.async and arrive on the leader's "operand ready" barrier (remote arrive from the follower).
 //   warps 8-11  tile hand-over (one warp per TMEM lane quadrant; thread = row): everything that is NOT a hidden epilogue --
-//               the output layer's accumulator, head activations / view-direction term, the stores to global memory, and
-//               the NEXT tile's first-layer operand (encoded / generated / loaded), which they prepare in registers while
-//               the slot's last layers run and publish a few hundred cycles after "output full".  The hidden-epilogue
-//               warps never see a tile boundary: they go from the last hidden layer of one tile straight to the first
-//               hidden layer of the next.
+//               the output layer's accumulator, the head activations, the stores to global memory, and the NEXT tile's
+//               first-layer operand (generated in registers while the slot's last layers run, or fetched by TMA: three
+//               cp.async.bulk.tensor boxes per tile), published a few hundred cycles after "output full".  Both slots'
+//               hand-overs come first, the head outputs afterwards.  The hidden-epilogue warps never see a tile boundary:
+//               they go from the last hidden layer of one tile straight to the first hidden layer of the next.
 //   warps 14-15 exist to lend their registers (setmaxnreg works on whole warpgroups): the CTA launches with 128 registers
-//               per thread, warps 12-15 drop to 64, warps 8-11 to 112, warps 0-7 grow to 168.
+//               per thread, warps 12-15 drop to 48, warps 8-11 keep 128, warps 0-7 grow to 168.
+//
+//   ReLU kernels (DoNeRFTRT, classic NeRF) -- 10 warps at 168 registers: warps 0-7 as above plus the output phase (16 output
+//               columns, one float4 per row, the next tile's frequency encoding), warp 8 weight producer, warp 9 MMA issuer.
 //
 // The first-layer operand is generated in the kernel (frequency encoding, Pluecker features) or loaded; the NeRF
 // view-direction term (27 inputs of the last layer, identical for a ray's samples) is a per-ray fp32 pre-pass added in
@@ -80,21 +84,24 @@ static_assert(SMEM_ALLOC <= 232448, "over the 227 KB per-CTA shared-memory limit
 constexpr int N_EPI_WARPS = 8;                          // hidden epilogues: lane quadrant x column half (warpgroups 0, 1)
 constexpr int N_OUT_WARPS = 4;                          // tile hand-over: one warp per lane quadrant (warpgroup 2)
 constexpr int W_OUT0 = N_EPI_WARPS;                     // warps 8..11
-constexpr int NTHREADS = 16 * 32;                       // 512: four warpgroups
+// Two shapes of the CTA.  The ELU kernels (sampler, refine) run with HAND-OVER WARPS: 16 warps, the register split below.  The ReLU
+// kernels (DoNeRFTRT, classic NeRF) keep 10 warps at 168 registers with the output phase on the epilogue warps: their hand-over is
+// a 16-column accumulator read and one float4 per row, the kernel runs into the board's power limit (a train of launches draws
+// 990 W of 1000 and the SM clock sits at 1.45-1.5 GHz), and the 16-warp shape measured 1.5-1.9 % MORE time per launch there for 1 %
+// fewer cycles (profiles/r02_handover).
+__host__ __device__ constexpr bool use_handover(int act) { return act == 1; }
+__host__ __device__ constexpr int n_threads(int act) { return use_handover(act) ? 16 * 32 : (N_EPI_WARPS + 2) * 32; }
 // Register budget.  The register file is per SM sub-partition (16 K registers = 512 per lane), a sub-partition holds one warp of
 // every warpgroup, and setmaxnreg moves registers between warpgroups INSIDE the launch allocation (512 threads x 128 = all of
-// it): 2 x 168 (hidden epilogues: 128 live accumulator columns) + 112 / 96 (hand-over) + 64 / 80 (single-thread roles) = 512.
-// The split between the hand-over and the role warps is per instantiation (out_regs / role_regs below): ptxas' allocation around
-// the 32-register tcgen05.ld blocks is brittle, and these are the splits that compile without spills in the hot loops.
+// it): 2 x 168 (hidden epilogues: 128 live accumulator columns) + 128 (hand-over: both slots' 48 output columns live) + 48 (roles) = 512.
+// ptxas budgets a region by the setmaxnreg that dominates it, and fails outright (C7600) when a role region cannot fit.
 constexpr int kEpiRegs = 168;
-__host__ __device__ constexpr int out_regs(bool nerf) { return nerf ? 96 : 128; }
-__host__ __device__ constexpr int role_regs(bool nerf) { return nerf ? 80 : 48; }
-static_assert(2 * kEpiRegs + out_regs(true) + role_regs(true) <= 512 && 2 * kEpiRegs + out_regs(false) + role_regs(false) <= 512,
-              "register budget per SM sub-partition lane");
+constexpr int kOutRegs = 128;
+constexpr int kRoleRegs = 48;
+static_assert(2 * kEpiRegs + kOutRegs + kRoleRegs <= 512, "register budget per SM sub-partition lane");
 // The two single-thread roles get the HIGHEST active warp ids: the SM's warp arbiter favours higher ids, and a starved MMA
 // issuer (or weight producer) stalls the whole pair (measured: 2x slower issue as warp 1 behind four epilogue warps).
-constexpr int W_PRODUCER = W_OUT0 + N_OUT_WARPS;        // warp 12 (scheduler 0)
-constexpr int W_MMA = W_PRODUCER + 1;                   // warp 13 (scheduler 1)
+__host__ __device__ constexpr int w_producer(int act) { return use_handover(act) ? W_OUT0 + N_OUT_WARPS : N_EPI_WARPS; }   // warp 12 / 8 (scheduler 0)
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_PHASES = 14;
 
@@ -198,8 +205,7 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, in
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, code);
 }
-// The hand-over warps wait for most of a tile's lifetime: they poll with a back-off so that their probes do not compete with the
-// epilogue warps' shared-memory traffic (a tight try_wait loop of 128 threads slowed the MMAs and the hidden epilogues by 30 %).
+// The hand-over warps wait for most of a tile's lifetime: they poll with a back-off (32 ns; 500 ns - 4 us measured the same).
 __device__ __forceinline__ void mbar_wait_polite(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -342,6 +348,16 @@ __device__ __forceinline__ float elu_f32(float y) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(y * 1.4426950408889634f)));
   return fmaxf(y, e - 1.f);
 }
+// The form the kernel runs: the ELU networks are packed with their pre-activations scaled by log2(e) (tc_load_net: first-layer
+// weights and every hidden bias x log2 e, output-layer weights / log2 e; hidden weights unchanged because input and output scale
+// cancel), so t = y log2 e arrives straight from the accumulator and the layer hands log2(e) ELU(y) = max(t, log2 e (2^-|t| - 1))
+// to the next one: MUFU + FFMA + FMNMX, one issue slot per activation less than elu_f32 (these kernels are bound by the SFU with
+// the issue slots three quarters full).
+__device__ __forceinline__ float elu_scaled(float t) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+  return fmaxf(t, fmaf(e, 1.4426950408889634f, -1.4426950408889634f));
+}
 // packed fp32x2 add (Blackwell FADD2): {o0,o1} = {x0,x1} + {b0,b1}
 __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, float& o0, float& o1) {
   asm("{\n\t.reg .b64 a, b, c;\n\t"
@@ -453,7 +469,7 @@ __device__ __forceinline__ float epilogue_store64(const float* v, uint32_t bias_
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : (ACT == 1) ? pack_h2(elu_f32(y[2 * u]), elu_f32(y[2 * u + 1])) : pack_h2(y[2 * u], y[2 * u + 1]);
+      w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : (ACT == 1) ? pack_h2(elu_scaled(y[2 * u]), elu_scaled(y[2 * u + 1])) : pack_h2(y[2 * u], y[2 * u + 1]);
     st_shared_v4(row_base + ((uint32_t)(c << 4) ^ xr), w[0], w[1], w[2], w[3]);
   }
   return side;
@@ -470,6 +486,7 @@ constexpr int TL_FACC = 150;     // follower CTA, epilogue warp 0: accumulator-f
 constexpr int TL_FARR = 170;     // follower CTA, epilogue warp 0: arrived on operand-ready
 constexpr int TL_SYNC = 140;    // clock64() right after the setup cluster barrier: [0] leader, [1] follower (per-SM clock offset)
 constexpr int TL_OUT = 110;     // epilogue warp 0, output phase, slot t: [6t + 0] body entry, [1] before the accumulator wait, [2] accumulator in registers, [3] next operand stored, [4] outputs stored
+constexpr int TL_CLK = 200;     // CTA 0, thread 0: [0] clock64 / [1] %globaltimer (ns) after setup, [2] / [3] the same before teardown -> effective SM clock
 constexpr int TL_N = 208;
 __device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
   if (kTimeline && tl && on) tl[slot] = clock64();
@@ -477,7 +494,9 @@ __device__ __forceinline__ void tl_mark(long long* tl, bool on, int slot) {
 
 // ACT: 0 ReLU / 1 ELU.  MODE: InputMode.
 template <int ACT, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_kernel(const __grid_constant__ Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) mlp_tc_kernel(const __grid_constant__ Params p) {
+  constexpr bool kHandover = use_handover(ACT);
+  constexpr int W_PRODUCER = w_producer(ACT), W_MMA = W_PRODUCER + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;              // identical in both CTAs of the pair
@@ -519,6 +538,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   const uint32_t tmem_base = *s_tmem;
   if (threadIdx.x == 0) pdl_launch();                      // the successor's CTAs may take over SMs as this grid's CTAs exit
   if (kTimeline && p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
+  if (kTimeline && p.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.timeline[TL_CLK + 0] = clock64(); p.timeline[TL_CLK + 1] = (long long)ns;
+  }
 
   // The single-thread roles walk the same (slot, phase) sequence: the two slots alternate phase by phase.  With `reorder`, slot
   // 0's FIRST layer of its next tile goes before slot 1's OUTPUT layer: slot 0's new operand is published by the hand-over warps
@@ -570,9 +594,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   // the hand-over warps release, the hidden-epilogue warpgroups take (setmaxnreg.inc waits until the registers are free).  Each
   // instruction sits at the top of the code it governs: ptxas budgets a region by the setmaxnreg that DOMINATES it (after a join
   // of differently budgeted paths it assumes the smallest).
-  constexpr bool kNerfRegs = (MODE == IN_ENCODE || MODE == IN_LOAD2);
-  constexpr int kRoleRegs = role_regs(kNerfRegs), kOutRegs = out_regs(kNerfRegs);
-  if (warp >= W_PRODUCER) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRoleRegs));
+  if (kHandover && warp >= W_PRODUCER) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRoleRegs));
   if (warp == W_PRODUCER) {
     // =============================== weight producer (both CTAs) ===============================
     if (lane == 0) {
@@ -637,7 +659,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         const uint32_t par0 = (ar_par >> (2 * t)) & 1u, par1 = (ar_par >> (2 * t + 1)) & 1u;
         ar_par ^= 3u << (2 * t);
         const uint32_t d_tmem = tmem_base + (uint32_t)t * kHidden;
-        const uint32_t bar_done = p.ph[ph].epi == EPI_OUT ? bar_outfull(t) : bar_accfull(t);   // who drains this accumulator
+        const uint32_t bar_done = (kHandover && p.ph[ph].epi == EPI_OUT) ? bar_outfull(t) : bar_accfull(t);   // who drains this accumulator
         const uint32_t a_lo_t = a_lo0 + (uint32_t)t * (A_SLOT_BYTES >> 4);
         constexpr uint32_t kBlk = A_BLOCK_BYTES >> 4, kRing = RING_SLOT_BYTES >> 4;
         // operand halves: [0] = K blocks {0,1} written and the accumulator drained, [1] = K blocks {2,3} written
@@ -718,7 +740,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     }
   } else if (warp < W_PRODUCER) {
     // =============================== hidden-epilogue warps (0-7) and hand-over warps (8-11), both CTAs ===============================
-    const bool is_out = warp >= W_OUT0;
+    const bool is_out = kHandover && warp >= W_OUT0;
     const int ew = warp;
     const int ch = (ew >> 2) & 1;                          // hidden epilogues: this warp drains columns [64ch,+64) and [128+64ch,+64)
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
@@ -871,7 +893,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
     // The inputs (and every output buffer) belong to the dependency chain: wait for the predecessor's completion here.
     pdl_wait();
 
-    if (is_out) {
+    if (kHandover && is_out) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kOutRegs));
       // =============================== hand-over warps: output layer + next tile's first operand ===============================
       // Per slot and tile: fetch what the hand-over needs (the next tile's raw inputs, this tile's view-direction term), turn the
@@ -1122,12 +1144,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         }
       }
     } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    if (kHandover) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     // =============================== hidden-epilogue warps ===============================
     // These are the busiest warps of the kernel and a lone warp retires one DEPENDENT instruction every ~5 cycles, so their
     // control flow is spelled out as plain nested loops (iteration -> phase -> slot; the two slots run in step) with everything
     // per-phase hoisted, instead of the generic cursor walk of the single-thread roles.
     uint32_t acc_par = 0;
+    // ReLU kernels (no hand-over warps): these warps also run the output phase and build the next tile's first operand, warp
+    // (q, ch) producing half `ch` of it.  The raw inputs of each slot's NEXT tile are fetched one phase ahead.
+    float xin0[kXin], xin1[kXin];
+    float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
+    if (!kHandover) {
+#pragma unroll
+      for (int i = 0; i < kXin; ++i) { xin0[i] = 0.f; xin1[i] = 0.f; }
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        if (!cur.live(t)) continue;
+        if (kCompute) {
+          float xin[kXin];
+          uint32_t pre[16];
+          const long long row = row_of(cur.tile(t));
+          fetch_input(row, xin);
+          precompute_half(xin, row < p.M, pre, ch);
+          store_half(t, pre, ch);
+        } else {
+          load_input(cur.tile(t), t, 0, kb_first, q * 32 + ch * 16);
+        }
+        publish(t, 3, 1);
+      }
+    }
     const bool more = p.ph[0].epi == EPI_MORE;
     const uint32_t bias_base = base + OFF_BIAS + (uint32_t)(ch * 64) * 4u;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -1208,6 +1253,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
         for (int t = 0; t < nslots; ++t) {
           const bool tl_e = tl_it && ew == 0 && ph == 2 && t == 0;      // fine-grained stamps of one hidden epilogue
           tl_mark(p.timeline, tl_e, TL_EPI + 0);
+          if (!kHandover && ph == np - 2) {
+            // one phase before the output layer: start the global loads the output epilogue will need.  Each slot's
+            // registers are written directly (no select on the loaded values: that would wait for the loads here).
+            const long long tile = T0 + t;
+            if (kCompute && tile + stride < n_pairs) {
+              if (t == 0) fetch_input(row_of(tile + stride), xin0);
+              else fetch_input(row_of(tile + stride), xin1);
+            }
+            if (kNerf && ch == 0) {
+              if (t == 0) dterm0 = fetch_dterm(row_of(tile));
+              else dterm1 = fetch_dterm(row_of(tile));
+            }
+          }
           tl_mark(p.timeline, tl_e, TL_EPI + 1);
           mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
           acc_par ^= 1u << t;
@@ -1264,6 +1322,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
           tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
         }
       }
+      if (!kHandover) {
+        // ---------------- output phase (ReLU kernels) ----------------
+        // Order matters: the accumulator is pulled into registers, the next tile's first-layer operand is written and the
+        // slot is PUBLISHED before anything goes to global memory -- the proxy fence in publish() is a CTA-wide memory
+        // barrier, and behind a global store it would wait for the store's L2 round trip.
+        const int layer_out = p.ph[np - 1].layer;
+#pragma unroll 1
+        for (int t = 0; t < nslots; ++t) {
+          const long long tile = T0 + t;
+          const bool has_next = tile + stride < n_pairs;
+          const bool tl_o = tl_it && ew == 0;
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 0);
+          uint32_t pre[16];
+          if (kCompute && has_next) {                            // overlaps the wait below
+            float xin[kXin];
+#pragma unroll
+            for (int i = 0; i < kXin; ++i) xin[i] = t ? xin1[i] : xin0[i];
+            precompute_half(xin, row_of(tile + stride) < p.M, pre, ch);
+          }
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 1);
+          mbar_wait(bar_accfull(t), (acc_par >> t) & 1u, p.error_flag, 4);
+          acc_par ^= 1u << t;
+          tc_fence_after();
+          tl_mark(p.timeline, tl_it && ew == 0, TL_ACC + ph * 2 + t);
+          tl_mark(p.timeline, tl_f, TL_FACC + ph * 2 + t);
+          const long long row = row_of(tile);
+          float v[16];
+          if (ch == 0) {                                         // 4 real output columns: the ch = 1 warps have none
+            tmem_ld16(tmem_lane + (uint32_t)t * kHidden, v);
+            tmem_wait_ld();
+          }
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 2);
+          if (has_next) {
+            if (kCompute) store_half(t, pre, ch);
+            else load_input(tile + stride, t, 0, kb_first, q * 32 + ch * 16);
+          }
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 3);
+          publish(t, 3, 1);
+          tl_mark(p.timeline, tl_it && ew == 0, TL_ARR + ph * 2 + t);
+          tl_mark(p.timeline, tl_it && ew == N_EPI_WARPS - 1, TL_ARRL + ph * 2 + t);
+          tl_mark(p.timeline, tl_f, TL_FARR + ph * 2 + t);
+          if (ch == 0 && row < p.M) {
+            const float* bo = s_bias + layer_out * kHidden;
+            if (kClassic) {
+              // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
+              const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
+              *reinterpret_cast<float4*>(p.out + row * 4) =
+                  make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
+            } else {
+              // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
+              const float4 d = t ? dterm1 : dterm0;
+              *reinterpret_cast<float4*>(p.out + row * 4) = make_float4(v[0] + bo[0] + d.x, v[1] + bo[1] + d.y, v[2] + bo[2] + d.z, v[3] + bo[3] + d.w);
+            }
+          }
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 4);
+        }
+      }
     }
     }
   }
@@ -1272,6 +1387,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
   // ---- teardown: nobody may leave while the peer can still touch this CTA's shared memory or barriers ----
   tc_fence_before();
   __syncthreads();
+  if (kTimeline && p.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.timeline[TL_CLK + 2] = clock64(); p.timeline[TL_CLK + 3] = (long long)ns;
+  }
   cluster_sync_all();
   if (warp == W_PRODUCER) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -1281,7 +1401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) mlp_tc_
 // each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout (narrow output layers: one chunk per layer, see below).  fold > 1: input column k stands for the sum of
 // columns k, k + fold_stride, ... (the sampler's P replicated Pluecker blocks).
 __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int fold, int fold_stride, int n_pad,
-                               int kblocks, int merged, uint8_t* __restrict__ dst, int k_src0 = 0) {
+                               int kblocks, int merged, uint8_t* __restrict__ dst, int k_src0 = 0, float scale = 1.f) {
   const int total = kblocks * n_pad * 64;
   const int half_rows = n_pad / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -1296,13 +1416,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_
     // plain: [kb][rank][rows];  merged (narrow layers, one chunk per layer): [rank][kb][rows]
     const size_t blk = merged ? ((size_t)h * kblocks + kb) : ((size_t)kb * 2 + h);
     const size_t off = blk * half_rows * 128 + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((k >> 3) ^ (rr & 7)) << 4) + (k & 7) * 2;
-    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v * scale);
   }
 }
 
-__global__ void pack_tc_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst) {
+__global__ void pack_tc_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst, float scale = 1.f) {
   int i = threadIdx.x;
-  if (i < kHidden) dst[i] = i < out_dim ? b[i] : 0.f;
+  if (i < kHidden) dst[i] = i < out_dim ? b[i] * scale : 0.f;
 }
 
 __global__ void pack_tc_wdir_kernel(const float* __restrict__ W, int in_dim, float* __restrict__ dst) {
@@ -1409,17 +1529,24 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   PN_CUDA_OK(cudaMemsetAsync(n.error_flag, 0, sizeof(int), stream));
   n.blob_bytes = L.total;
   uint8_t* blob = reinterpret_cast<uint8_t*>(n.blob);
+  // ELU networks (sampler, refine): pre-activations scaled by log2(e), see elu_scaled()
+  const bool elu = net_id != PN_NET_NERF;
+  const float l2e = 1.4426950408889634f;
+  n.elu_scaled = elu;
   for (int l = 0; l < n_layers; ++l) {
     int total = L.kblocks[l] * L.n_pad[l] * 64;
+    const bool last_l = l == n_layers - 1;
+    const float w_scale = !elu ? 1.f : last_l ? 1.f / l2e : l == 0 ? l2e : 1.f;
+    const float b_scale = (elu && !last_l) ? l2e : 1.f;
     tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[l], out_dims[l], in_dims[l], L.k_used[l], 1, 0, L.n_pad[l], L.kblocks[l],
-                                                                 L.merged[l] ? 1 : 0, blob + L.chunk_off[l]);
+                                                                 L.merged[l] ? 1 : 0, blob + L.chunk_off[l], 0, w_scale);
     PN_LAUNCH_OK("pack_tc_kernel");
-    tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden);
+    tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden, b_scale);
     PN_LAUNCH_OK("pack_tc_bias_kernel");
   }
   if (L.has_fold) {
     tc::pack_tc_kernel<<<(kHidden * 64 + 255) / 256, 256, 0, stream>>>(W[0], out_dims[0], in_dims[0], 6, in_dims[0] / 6, 6, kHidden, 1, 0,
-                                                                        blob + L.fold_off);
+                                                                        blob + L.fold_off, 0, elu ? l2e : 1.f);
     PN_LAUNCH_OK("pack_tc_kernel(fold)");
   }
   if (net_id == PN_NET_NERF) {
@@ -1505,7 +1632,7 @@ int tc_load_nerf_classic(NetTC& n, const int* in_dims, const int* out_dims, cons
   return PN_OK;
 }
 
-static int tc_max_clusters(const void* func, int* out);
+static int tc_max_clusters(const void* func, int nthreads, int* out);
 constexpr int kMaxDevices = 64;
 
 // The [M, K0] fp16 first-layer input as a 2-D tensor map (box = one K block of a 128-row tile, 128-byte swizzle, zero fill outside).
@@ -1551,7 +1678,7 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   p.in0 = pts; p.in_stride = 3; p.M = M; p.out = raw;
   p.vdir = viewdirs; p.vdir_stride = viewdir_stride; p.dir_div = S > 0 ? S : 1;
   p.alpha_row = kClassicAlphaRow; p.alpha_bias = n.alpha_bias;
-  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.reorder = tc_env_reorder();
+  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.reorder = 0;
   p.n_phases = 13;
   for (int i = 0; i < 13; ++i) {
     const ClassicPhase& c = kClassicPhases[i];
@@ -1570,21 +1697,21 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   int& max_clusters = max_clusters_dev[dev_id];
   if (max_clusters == 0) {
     PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
-    int rc = tc_max_clusters((const void*)kern, &max_clusters);
+    int rc = tc_max_clusters((const void*)kern, tc::n_threads(0), &max_clusters);
     if (rc != PN_OK) return rc;
     if (max_clusters <= 0) { set_error("tc: no co-resident CTA pair fits on this device"); return PN_ECUDA; }
   }
   const long long units = (M + tc::UNIT_M - 1) / tc::UNIT_M;
   const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);
-  PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::NTHREADS), tc::SMEM_ALLOC, stream, p));
+  PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::n_threads(0)), tc::SMEM_ALLOC, stream, p));
   PN_LAUNCH_OK("mlp_tc_kernel(classic)");
   return PN_OK;
 }
 
-static int tc_max_clusters(const void* func, int* out) {
+static int tc_max_clusters(const void* func, int nthreads, int* out) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * 148);
-  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.blockDim = dim3(nthreads);
   cfg.dynamicSmemBytes = tc::SMEM_ALLOC;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1603,6 +1730,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     return PN_ESTATE;
   }
   if (Lc.M == 0) return PN_OK;
+  PN_REQUIRE((Lc.act == 1) == n.elu_scaled, "tc: activation %d does not match how the network was packed", Lc.act);
   PN_REQUIRE(Lc.M < (1LL << 32), "tc: %lld rows in one launch (limit 2^32 - 1)", (long long)Lc.M);
   TcLayout L = tc_layout(n.net_id, n.n_layers, n.in_dim, n.out_dim);
   tc::Params p{};
@@ -1630,7 +1758,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     // schedule knobs (defaults = the measured best; the environment overrides are a tuning aid)
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
     p.split = env_split >= 0 ? env_split : 0;            // bit 0: every hidden epilogue, bit 1: the first layer's only
-    p.reorder = tc_env_reorder();
+    p.reorder = tc_env_reorder() && tc::use_handover(Lc.act);       // only the hand-over shape has a short output turn-around to exploit
     p.out_rpp = 0;         // (the hand-over warps derive the rows per staging pass from the chunk width)
   }
   if (Lc.input_mode == IN_LOAD16) {
@@ -1700,12 +1828,12 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     int& max_clusters = max_clusters_dev[dev_id];                                                                          \
     if (max_clusters == 0) {                                                                                               \
       PN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));                 \
-      int rc = tc_max_clusters((const void*)kern, &max_clusters);                                                          \
+      int rc = tc_max_clusters((const void*)kern, tc::n_threads(ACT), &max_clusters);                                      \
       if (rc != PN_OK) return rc;                                                                                          \
       if (max_clusters <= 0) { set_error("tc: no co-resident CTA pair fits on this device"); return PN_ECUDA; }            \
     }                                                                                                                      \
     const unsigned clusters = (unsigned)(units < max_clusters ? units : max_clusters);                                     \
-    PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::NTHREADS), tc::SMEM_ALLOC, stream, p));                     \
+    PN_CUDA_OK(launch_chain(kern, dim3(2 * clusters), dim3(tc::n_threads(ACT)), tc::SMEM_ALLOC, stream, p));               \
   } while (0)
   if (Lc.act == 0 && Lc.input_mode == IN_ENCODE) PN_TC_LAUNCH(0, IN_ENCODE);
   else if (Lc.act == 0 && Lc.input_mode == IN_LOAD2) PN_TC_LAUNCH(0, IN_LOAD2);

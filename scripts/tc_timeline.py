@@ -10,7 +10,8 @@ nerf, samp, refn = make_modules(sd, dev)
 M = 190512
 which = sys.argv[1] if len(sys.argv) > 1 else "nerf"
 buf = torch.zeros(208, dtype=torch.int64, device=dev)
-if which == "nerf":
+if which in ("nerf", "nerf3"):
+    if which == "nerf3": M = 571536
     pts = (torch.rand(M, 8, 3, device=dev) * 2 - 1); vd = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
     ctx = nerf._ctx(); run = lambda: ctx.run_network(pts, vd, "bf16"); nph = 8
 elif which == "refine":
@@ -29,9 +30,13 @@ else:
     ctx = samp._ctx(); run = lambda: ctx.sampler_forward(x, 8, "bf16"); nph = 8
 run(); torch.cuda.synchronize()
 _abi.lib().pn_debug_tc_timeline(buf.data_ptr())
-run(); torch.cuda.synchronize()
+for _ in range(int(os.environ.get("REPEAT", "1"))): run()      # REPEAT > 1: the stamps of the LAST of a train of launches (sustained clocks)
+torch.cuda.synchronize()
 _abi.lib().pn_debug_tc_timeline(None)
 t = buf.cpu().tolist()
+if t[200] and t[202] and t[203] > t[201]:
+    print(f"[{which}] CTA 0: {t[202] - t[200]} SM cycles in {(t[203] - t[201]) / 1e3:.1f} us -> effective SM clock {(t[202] - t[200]) / (t[203] - t[201]) * 1e3:.0f} MHz")
+for k in (200, 201, 202, 203): t[k] = 0
 t0 = min(x for x in t if x > 0)
 rel = lambda i: (t[i] - t0) if t[i] else None
 print(f"[{which}] phase slot: mma_start mma_issued | acc_seen(w2) arrive(w2) arrive(w17)   (cycles, relative)")
