@@ -348,16 +348,6 @@ __device__ __forceinline__ float elu_f32(float y) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(y * 1.4426950408889634f)));
   return fmaxf(y, e - 1.f);
 }
-// The form the kernel runs: the ELU networks are packed with their pre-activations scaled by log2(e) (tc_load_net: first-layer
-// weights and every hidden bias x log2 e, output-layer weights / log2 e; hidden weights unchanged because input and output scale
-// cancel), so t = y log2 e arrives straight from the accumulator and the layer hands log2(e) ELU(y) = max(t, log2 e (2^-|t| - 1))
-// to the next one: MUFU + FFMA + FMNMX, one issue slot per activation less than elu_f32 (these kernels are bound by the SFU with
-// the issue slots three quarters full).
-__device__ __forceinline__ float elu_scaled(float t) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
-  return fmaxf(t, fmaf(e, 1.4426950408889634f, -1.4426950408889634f));
-}
 // packed fp32x2 add (Blackwell FADD2): {o0,o1} = {x0,x1} + {b0,b1}
 __device__ __forceinline__ void add2(float x0, float x1, float b0, float b1, float& o0, float& o1) {
   asm("{\n\t.reg .b64 a, b, c;\n\t"
@@ -469,7 +459,7 @@ __device__ __forceinline__ float epilogue_store64(const float* v, uint32_t bias_
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : (ACT == 1) ? pack_h2(elu_scaled(y[2 * u]), elu_scaled(y[2 * u + 1])) : pack_h2(y[2 * u], y[2 * u + 1]);
+      w[u] = (ACT == 0) ? pack_h2_relu(y[2 * u], y[2 * u + 1]) : (ACT == 1) ? pack_h2(elu_f32(y[2 * u]), elu_f32(y[2 * u + 1])) : pack_h2(y[2 * u], y[2 * u + 1]);
     st_shared_v4(row_base + ((uint32_t)(c << 4) ^ xr), w[0], w[1], w[2], w[3]);
   }
   return side;
@@ -901,32 +891,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
       // is: tcgen05.ld of the few output columns -> operand stores (or cp.async copies) -> proxy fence -> arrive; the activations
       // of the head outputs and every global store come after the slot has been handed back to the tensor pipe.
       const int htid = (int)threadIdx.x - W_OUT0 * 32;       // 0..127
-      constexpr int HNT = N_OUT_WARPS * 32;
       uint32_t out_par = 0, in_par = 0;
-      // the full first-layer operand of row_of(tile) -> slot t's block(s)
-      auto build_first = [&](long long tile, int t) {
-        if (kCompute) {
-          float xin[kXin];
+      // prologue: first operands of both slots.  The kernel starts cold (the rows come from HBM, ~1.5 us per dependent round trip), so
+      // both slots' loads are in flight before either is waited for: at 8 GPUs a rank's whole kernel is two iterations, ~70 us.
+      if (MODE == IN_LOAD16) {
+        if (htid == 0) {
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            if (!cur.live(t)) continue;
+            const int row0 = (int)(row_of(cur.tile(t)) - r);
+            mbar_arrive_expect_tx(bar_infull(t), (uint32_t)kb_first * A_BLOCK_BYTES);
+            for (int kb = 0; kb < kb_first; ++kb)
+              tma_load_box(a_base + t * A_SLOT_BYTES + kb * A_BLOCK_BYTES, &p.tmap_in, kb * 64, row0, bar_infull(t));
+          }
+        }
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          if (!cur.live(t)) continue;
+          mbar_wait_polite(bar_infull(t), 0u, p.error_flag, 7);
+          in_par ^= 1u << t;
+          publish(t, 3, 2);
+        }
+      } else if (kCompute) {
+        float xa[kXin], xb[kXin];
+        const long long rowa = row_of(cur.tile(0)), rowb = row_of(cur.tile(1));
+        fetch_input(rowa, xa);
+        fetch_input(cur.live(1) ? rowb : p.M, xb);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (!cur.live(t)) continue;
           uint32_t pre[32];
-          const long long row = row_of(tile);
-          fetch_input(row, xin);
-          precompute_half(xin, row < p.M, pre, 0);
-          if (MODE != IN_PLUECKER) precompute_half(xin, row < p.M, pre + 16, 1);
+          const bool row_live = (t ? rowb : rowa) < p.M;
+          precompute_half(t ? xb : xa, row_live, pre, 0);
+          if (MODE != IN_PLUECKER) precompute_half(t ? xb : xa, row_live, pre + 16, 1);
           store_half(t, pre, 0);
           if (MODE != IN_PLUECKER) store_half(t, pre + 16, 1);
-        } else if (MODE == IN_LOAD16) {
-          load_input16(tile, t, 0, kb_first, htid, HNT);
-        } else {
-          load_input(tile, t, 0, kb_first, q * 32);
-          load_input(tile, t, 0, kb_first, q * 32 + 16);
+          publish(t, 3, 2);
         }
-      };
-      // prologue: first operands of both slots
+      } else {
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        if (!cur.live(t)) continue;
-        build_first(cur.tile(t), t);
-        publish(t, 3, 2);
+        for (int t = 0; t < 2; ++t) {
+          if (!cur.live(t)) continue;
+          load_input(cur.tile(t), t, 0, kb_first, q * 32);
+          load_input(cur.tile(t), t, 0, kb_first, q * 32 + 16);
+          publish(t, 3, 2);
+        }
       }
       const int layer_out = p.ph[np - 1].layer, n_pad_out = p.ph[np - 1].n_pad;
       const int n_out = p.n_out;
@@ -1401,7 +1410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
 // each half (n_pad/2 rows) in the UMMA K-major 128B-swizzle layout (narrow output layers: one chunk per layer, see below).  fold > 1: input column k stands for the sum of
 // columns k, k + fold_stride, ... (the sampler's P replicated Pluecker blocks).
 __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_dim, int k_used, int fold, int fold_stride, int n_pad,
-                               int kblocks, int merged, uint8_t* __restrict__ dst, int k_src0 = 0, float scale = 1.f) {
+                               int kblocks, int merged, uint8_t* __restrict__ dst, int k_src0 = 0) {
   const int total = kblocks * n_pad * 64;
   const int half_rows = n_pad / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -1416,13 +1425,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ W, int out_dim, int in_
     // plain: [kb][rank][rows];  merged (narrow layers, one chunk per layer): [rank][kb][rows]
     const size_t blk = merged ? ((size_t)h * kblocks + kb) : ((size_t)kb * 2 + h);
     const size_t off = blk * half_rows * 128 + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((k >> 3) ^ (rr & 7)) << 4) + (k & 7) * 2;
-    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v * scale);
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
   }
 }
 
-__global__ void pack_tc_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst, float scale = 1.f) {
+__global__ void pack_tc_bias_kernel(const float* __restrict__ b, int out_dim, float* __restrict__ dst) {
   int i = threadIdx.x;
-  if (i < kHidden) dst[i] = i < out_dim ? b[i] * scale : 0.f;
+  if (i < kHidden) dst[i] = i < out_dim ? b[i] : 0.f;
 }
 
 __global__ void pack_tc_wdir_kernel(const float* __restrict__ W, int in_dim, float* __restrict__ dst) {
@@ -1529,24 +1538,17 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
   PN_CUDA_OK(cudaMemsetAsync(n.error_flag, 0, sizeof(int), stream));
   n.blob_bytes = L.total;
   uint8_t* blob = reinterpret_cast<uint8_t*>(n.blob);
-  // ELU networks (sampler, refine): pre-activations scaled by log2(e), see elu_scaled()
-  const bool elu = net_id != PN_NET_NERF;
-  const float l2e = 1.4426950408889634f;
-  n.elu_scaled = elu;
   for (int l = 0; l < n_layers; ++l) {
     int total = L.kblocks[l] * L.n_pad[l] * 64;
-    const bool last_l = l == n_layers - 1;
-    const float w_scale = !elu ? 1.f : last_l ? 1.f / l2e : l == 0 ? l2e : 1.f;
-    const float b_scale = (elu && !last_l) ? l2e : 1.f;
     tc::pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(W[l], out_dims[l], in_dims[l], L.k_used[l], 1, 0, L.n_pad[l], L.kblocks[l],
-                                                                 L.merged[l] ? 1 : 0, blob + L.chunk_off[l], 0, w_scale);
+                                                                 L.merged[l] ? 1 : 0, blob + L.chunk_off[l]);
     PN_LAUNCH_OK("pack_tc_kernel");
-    tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden, b_scale);
+    tc::pack_tc_bias_kernel<<<1, kHidden, 0, stream>>>(b[l], out_dims[l], reinterpret_cast<float*>(blob + L.bias_off) + (size_t)l * kHidden);
     PN_LAUNCH_OK("pack_tc_bias_kernel");
   }
   if (L.has_fold) {
     tc::pack_tc_kernel<<<(kHidden * 64 + 255) / 256, 256, 0, stream>>>(W[0], out_dims[0], in_dims[0], 6, in_dims[0] / 6, 6, kHidden, 1, 0,
-                                                                        blob + L.fold_off, 0, elu ? l2e : 1.f);
+                                                                        blob + L.fold_off);
     PN_LAUNCH_OK("pack_tc_kernel(fold)");
   }
   if (net_id == PN_NET_NERF) {
@@ -1730,7 +1732,6 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     return PN_ESTATE;
   }
   if (Lc.M == 0) return PN_OK;
-  PN_REQUIRE((Lc.act == 1) == n.elu_scaled, "tc: activation %d does not match how the network was packed", Lc.act);
   PN_REQUIRE(Lc.M < (1LL << 32), "tc: %lld rows in one launch (limit 2^32 - 1)", (long long)Lc.M);
   TcLayout L = tc_layout(n.net_id, n.n_layers, n.in_dim, n.out_dim);
   tc::Params p{};

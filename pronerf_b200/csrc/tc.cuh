@@ -15,7 +15,6 @@ struct NetTC {
   float* dirterm = nullptr;      // device scratch (NeRF): per-ray view-direction term of the last layer, grown on demand
   size_t dirterm_rows = 0;
   bool classic = false;          // classic NeRF topology (tc_load_nerf_classic)
-  bool elu_scaled = false;       // ELU network packed with pre-activations x log2(e) (mlp_tc.cu: elu_scaled)
   float alpha_bias = 0.f;        // classic NeRF: alpha_linear.bias
   bool supported = false;        // shape within the tensor-core kernel's limits
   bool loaded = false;

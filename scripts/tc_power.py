@@ -10,7 +10,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "nerf"
 secs = float(sys.argv[2]) if len(sys.argv) > 2 else 5.0
 sd = synth.make_weights(seed=0)
 nerf, samp, refn = make_modules(sd, dev)
-M = 571536
+M = int(os.environ.get("PN_M", 571536))      # rays per launch (8-GPU shard of the bench step: 71442)
 if which == "nerf":
     pts = (torch.rand(M, 8, 3, device=dev) * 2 - 1); vd = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
     ctx = nerf._ctx(); run = lambda: ctx.run_network(pts, vd, "bf16")
