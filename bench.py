@@ -25,6 +25,10 @@ over NVLink and rank 0's stream waits for all flags on the device (``multigpu.Pe
 * ``roofline``  the dominant kernel (encode + NeRF MLP) timed live with CUDA events around that stage inside the timed
               region (``pn_ctx_profile``), against MEASURED_PEAKS.json; ``traffic`` from this round's ncu capture.
 * ``cpu_baseline`` / ``--impl reference``  the CPU oracle port (PyTorch fp32 ops in the reference's order) on the host cores.
+* extra keys at N = 1: ``effective_sm_clock`` (SM cycles against wall time inside each MLP launch: the clock the kernels really run
+  at, 1.45-1.8 GHz under the 1000 W board limit while ``clocks.sm_mhz`` -- nvidia-smi's averaged reading over the 0.1 s timed region --
+  still says 1965), ``sustained`` (the same step back to back for 2 s: steady-state rate, board power, reported clock), ``fp32_tier``,
+  ``config4``, ``torch_eager_gpu``.
 """
 from __future__ import annotations
 
@@ -133,7 +137,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_median": statistics.median(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU oracle legs
@@ -435,6 +439,45 @@ def main():
             extras["view_parallel"] = {"value": world * n_rays_step / ms / 1e3, "unit": UNIT, "ms_per_step": ms, "scaling": "weak",
                                        "what": "every rank renders the whole 3-view batch (replica serving, no exchange)"}
             del full, dense
+        if precision == "fp16" and world == 1:
+            # (1) the clock the MLP kernels really run at: SM cycles (clock64) against wall time (%globaltimer) inside CTA 0 of each
+            #     launch (pn_debug_tc_clock) -- nvidia-smi's reading above is a slow average and still says 1965 MHz;
+            # (2) the same step back to back for ~2 s, no flush: steady-state rate, board power and the clock nvidia-smi reports then
+            try:
+                from pronerf_b200 import _abi
+                clk = torch.zeros(12, dtype=torch.int64, device=dev)
+                _abi.lib().pn_debug_tc_clock(clk.data_ptr())
+                for _ in range(3):
+                    step_launches()
+                torch.cuda.synchronize(dev)
+                _abi.lib().pn_debug_tc_clock(None)
+                c = clk.cpu().tolist()
+                eff = {}
+                for i, name in enumerate(("sampler_mlp", "refine_mlp", "nerf_mlp")):
+                    cyc, ns = c[4 * i + 2] - c[4 * i], c[4 * i + 3] - c[4 * i + 1]
+                    if ns > 0:
+                        eff[name] = {"sm_cycles": cyc, "us": ns / 1e3, "mhz": cyc / ns * 1e3}
+                extras["effective_sm_clock"] = dict(eff, how="clock64() against %globaltimer in CTA 0 of the launch (third of three back-to-back steps)")
+                sus = ClockSampler(local_rank)
+                sus.start()
+                t0 = time.perf_counter()
+                n_sus = 0
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                while time.perf_counter() - t0 < 2.0:
+                    for _ in range(20):
+                        step_launches()
+                    n_sus += 20
+                    torch.cuda.synchronize(dev)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                info = sus.stop()
+                ms = e0.elapsed_time(e1) / n_sus
+                extras["sustained"] = {"value": n_rays_step / ms / 1e3, "unit": UNIT, "ms_per_step": ms, "steps": n_sus, "clocks": info,
+                                       "what": "the same step back to back for 2 s without the L2 flush: steady-state rate with the board at its "
+                                               "power limit (nvidia-smi sampled every 20 ms meanwhile)"}
+            except Exception as e:                          # an extra leg must not take the headline down
+                extras["sustained"] = {"error": repr(e)[:300]}
         if precision == "fp16":
             # the <=1e-3 parity tier on one view (fp32 SIMT kernels), device-timed
             R32 = Renderer(weights, scene.images_ref, scene.poses_ref, scene.K, H, W, S=S, P=P, num_neighbor=NN, precision="fp32", device=dev)

@@ -54,6 +54,11 @@ int         pn_has_bf16_tier(void);
 /* Debug aid (not part of the render path): when set to a device buffer of 208 int64, CTA 0 of every subsequent
  * bf16 MLP launch records clock64() stamps of its second tile's pipeline events; NULL switches it off. */
 int         pn_debug_tc_timeline(void* dev_buf_208_i64);
+/* Measurement aid (not part of the render path): when set to a device buffer of 12 int64, CTA 0 of every subsequent tensor-core
+ * MLP launch writes {clock64(), %globaltimer [ns]} after its setup and before its teardown into slots [4 net .. 4 net + 3]
+ * (net: 0 sampler, 1 refine, 2 NeRF): SM cycles / wall time = the clock the launch really ran at (the board's power limit
+ * holds these kernels at 1.45-1.8 GHz while nvidia-smi's averaged reading still says 1965 MHz).  NULL switches it off. */
+int         pn_debug_tc_clock(void* dev_buf_12_i64);
 
 /* ---- context: packed weights + scratch ------------------------------------------------------- */
 int  pn_ctx_create(int device, pn_ctx_t** out);

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pn_device_check": (_i, [_i]),
     "pn_has_bf16_tier": (_i, []),
     "pn_debug_tc_timeline": (_i, [_p]),
+    "pn_debug_tc_clock": (_i, [_p]),
     "pn_ctx_create": (_i, [_i, C.POINTER(_p)]),
     "pn_ctx_destroy": (None, [_p]),
     "pn_ctx_profile": (_i, [_p, _i]),

@@ -89,6 +89,7 @@ int pn_version(void) { return PN_VERSION; }
 const char* pn_last_error(void) { return g_err; }
 int pn_has_bf16_tier(void) { return tc_available() ? 1 : 0; }
 int pn_debug_tc_timeline(void* dev_buf_208_i64) { tc_set_timeline(reinterpret_cast<long long*>(dev_buf_208_i64)); return PN_OK; }
+int pn_debug_tc_clock(void* dev_buf_12_i64) { tc_set_clock(reinterpret_cast<long long*>(dev_buf_12_i64)); return PN_OK; }
 
 int pn_device_check(int device) {
   int count = 0;

@@ -150,6 +150,7 @@ struct Params {
   int out_rpp;                  // rows per staging pass of the head output (multiple of 4)
   int* error_flag;
   long long* timeline;          // debug: leader CTA of cluster 0 stamps clock64() of its second iteration
+  long long* clk;               // measurement aid (pn_debug_tc_clock): CTA 0 writes {clock64, %globaltimer ns} after setup and before teardown
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -527,6 +528,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   if (threadIdx.x == 0) pdl_launch();                      // the successor's CTAs may take over SMs as this grid's CTAs exit
+  if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {           // SM cycles against wall time: the clock this launch really runs at
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.clk[0] = clock64(); p.clk[1] = (long long)ns;
+  }
   if (kTimeline && p.timeline && blockIdx.x < 2 && threadIdx.x == 0) p.timeline[TL_SYNC + blockIdx.x] = clock64();
   if (kTimeline && p.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;
@@ -886,10 +892,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
     if (kHandover && is_out) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kOutRegs));
       // =============================== hand-over warps: output layer + next tile's first operand ===============================
-      // Per slot and tile: fetch what the hand-over needs (the next tile's raw inputs, this tile's view-direction term), turn the
-      // inputs into the packed first-layer operand IN REGISTERS, then wait for "output full".  From there the slot's critical path
-      // is: tcgen05.ld of the few output columns -> operand stores (or cp.async copies) -> proxy fence -> arrive; the activations
-      // of the head outputs and every global store come after the slot has been handed back to the tensor pipe.
+      // Per slot and tile: fetch the next tile's raw inputs and turn them into the packed first-layer operand IN REGISTERS (or
+      // prefetch its rows towards L2), then wait for "output full".  From there the slot's critical path is: operand stores (or
+      // three TMA boxes) -> tcgen05.ld of the output columns -> operand landed -> proxy fence -> arrive; the activations of the
+      // head outputs and every global store come after BOTH slots have been handed back to the tensor pipe.
       const int htid = (int)threadIdx.x - W_OUT0 * 32;       // 0..127
       uint32_t out_par = 0, in_par = 0;
       // prologue: first operands of both slots.  The kernel starts cold (the rows come from HBM, ~1.5 us per dependent round trip), so
@@ -1065,91 +1071,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
         if (n_pad_out > c0 + 32) tmem_ld16(taddr + c0 + 32, v + 32);
         tmem_wait_ld();
       };
-      // NeRF outputs: one float4 per row
-      auto emit_raw = [&](const float* v, int t, long long row, const float4& dterm) {
-        if (row >= p.M) return;
-        const float* bo = s_bias + layer_out * kHidden;
-        if (kClassic) {
-          // [rgb_linear(h), alpha_linear(h7)] (helpers.py:843-844): alpha = the two half dot products of the pts_linears.7 epilogue
-          const float* ap = s_bias + (p.alpha_row + 1 + t) * kHidden;
-          *reinterpret_cast<float4*>(p.out + row * 4) =
-              make_float4(v[0] + bo[0], v[1] + bo[1], v[2] + bo[2], ap[r] + ap[TILE_M + r] + p.alpha_bias);
-        } else {
-          // DoNeRFTRT's last layer: hidden part from the tensor cores + W7[:, 256:283] . gamma_4(viewdir) (pre-pass)
-          *reinterpret_cast<float4*>(p.out + row * 4) =
-              make_float4(v[0] + bo[0] + dterm.x, v[1] + bo[1] + dterm.y, v[2] + bo[2] + dterm.z, v[3] + bo[3] + dterm.w);
-        }
-      };
+      // One shape for any number of head columns: first the critical paths of both slots (each slot's accumulator chunks are
+      // drained into a per-thread scratch array -- local memory on purpose: two slots x up to two 48-column chunks do not fit the
+      // hand-over warps' registers next to the activation temporaries, and an indexed array keeps ONE copy of the output code), then
+      // the head activations and stores of everything.  Slot 1's "output full" arrives one hidden epilogue after slot 0's, and
+      // behind slot 0's head activations (which queue at the SFU the hidden epilogues saturate: ~5 K cycles) its hand-over would
+      // come 2-3 K cycles late, with the hidden-epilogue warps waiting.
       constexpr int kPre = (kCompute && MODE != IN_PLUECKER) ? 32 : 16;
-      constexpr int kV = (kClassic || kNerf) ? 16 : 48;
+      float vbuf[2][2][48];
       int it_idx = 0;
       for (long long T0 = 2 * cluster_id; T0 < n_pairs; T0 += stride, ++it_idx) {
         const int nslots = (T0 + 1 < n_pairs) ? 2 : 1;
         const bool tl_o = kTimeline && blockIdx.x == 0 && it_idx == 1 && warp == W_OUT0 && lane == 0;
-        if (!(kClassic || kNerf) && n_pad_out > 48) {
-          // more than 48 head columns (16 samples per ray): the chunks of a slot go one after the other -- the slot is published once
-          // its LAST chunk is in registers, after the first one has been activated and stored
 #pragma unroll 1
-          for (int t = 0; t < nslots; ++t) {
-            const long long tile = T0 + t;
-            const bool has_next = tile + stride < n_pairs;
-            uint32_t pre[kPre];
-            prepare_next(tile, has_next, pre);
-            wait_outfull(t);
-            if (has_next) start_next_operand(tile, t, pre);
+        for (int t = 0; t < nslots; ++t) {
+          const long long tile = T0 + t;
+          const bool has_next = tile + stride < n_pairs;
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 0);
+          uint32_t pre[kPre];
+          prepare_next(tile, has_next, pre);
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 1);
+          wait_outfull(t);
+          if (has_next) start_next_operand(tile, t, pre);
 #pragma unroll 1
-            for (int c0 = 0; c0 < n_pad_out; c0 += 48) {
-              float v[48];
-              ld48(tmem_q + (uint32_t)t * kHidden, c0, v);
-              if (c0 + 48 >= n_pad_out) hand_back(t, has_next);
-              emit_heads(v, c0, row_of(tile));
+          for (int c0 = 0, ci = 0; c0 < n_pad_out; c0 += 48, ++ci) {
+            float v[48];
+            ld48(tmem_q + (uint32_t)t * kHidden, c0, v);
+            if (c0 + 48 >= n_pad_out) {                            // the slot's last chunk is in registers: hand the slot back
+              tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 2);
+              hand_back(t, has_next);
+              tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 3);
             }
+#pragma unroll
+            for (int o = 0; o < 48; ++o)
+              if (o < 16 || n_pad_out > c0 + (o & ~15)) vbuf[t][ci][o] = v[o];
           }
-          continue;
         }
-        // Both slots' critical paths first, the outputs afterwards: slot 1's "output full" arrives one hidden epilogue after slot
-        // 0's, and behind slot 0's head activations (which queue at the SFU the hidden epilogues saturate: ~5 K cycles) its
-        // hand-over would come 2-3 K cycles late, with the hidden-epilogue warps waiting.
-        float v0[kV], v1[kV];
-        float4 dterm0 = make_float4(0.f, 0.f, 0.f, 0.f), dterm1 = dterm0;
-        {
-          const bool has_next = T0 + stride < n_pairs;
-          tl_mark(p.timeline, tl_o, TL_OUT + 0);
-          uint32_t pre[kPre];
-          prepare_next(T0, has_next, pre);
-          if (kNerf) dterm0 = fetch_dterm(row_of(T0));
-          tl_mark(p.timeline, tl_o, TL_OUT + 1);
-          wait_outfull(0);
-          if (has_next) start_next_operand(T0, 0, pre);
-          if (kV == 16) { tmem_ld16(tmem_q, v0); tmem_wait_ld(); }
-          else ld48(tmem_q, 0, v0);
-          tl_mark(p.timeline, tl_o, TL_OUT + 2);
-          hand_back(0, has_next);
-          tl_mark(p.timeline, tl_o, TL_OUT + 3);
-        }
-        if (nslots == 2) {
-          const bool has_next = T0 + 1 + stride < n_pairs;
-          tl_mark(p.timeline, tl_o, TL_OUT + 6);
-          uint32_t pre[kPre];
-          prepare_next(T0 + 1, has_next, pre);
-          if (kNerf) dterm1 = fetch_dterm(row_of(T0 + 1));
-          tl_mark(p.timeline, tl_o, TL_OUT + 7);
-          wait_outfull(1);
-          if (has_next) start_next_operand(T0 + 1, 1, pre);
-          if (kV == 16) { tmem_ld16(tmem_q + kHidden, v1); tmem_wait_ld(); }
-          else ld48(tmem_q + kHidden, 0, v1);
-          tl_mark(p.timeline, tl_o, TL_OUT + 8);
-          hand_back(1, has_next);
-          tl_mark(p.timeline, tl_o, TL_OUT + 9);
-        }
-        if (kClassic || kNerf) {
-          emit_raw(v0, 0, row_of(T0), dterm0);
-          if (nslots == 2) emit_raw(v1, 1, row_of(T0 + 1), dterm1);
-        } else {
-          emit_heads(v0, 0, row_of(T0));
-          tl_mark(p.timeline, tl_o, TL_OUT + 4);
-          if (nslots == 2) emit_heads(v1, 0, row_of(T0 + 1));
-          tl_mark(p.timeline, tl_o, TL_OUT + 10);
+#pragma unroll 1
+        for (int t = 0; t < nslots; ++t) {
+#pragma unroll 1
+          for (int c0 = 0, ci = 0; c0 < n_pad_out; c0 += 48, ++ci) {
+            float v[48];
+#pragma unroll
+            for (int o = 0; o < 48; ++o) v[o] = (o < 16 || n_pad_out > c0 + (o & ~15)) ? vbuf[t][ci][o] : 0.f;
+            emit_heads(v, c0, row_of(T0 + t));
+          }
+          tl_mark(p.timeline, tl_o, TL_OUT + t * 6 + 4);
         }
       }
     } else {
@@ -1396,6 +1363,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
   // ---- teardown: nobody may leave while the peer can still touch this CTA's shared memory or barriers ----
   tc_fence_before();
   __syncthreads();
+  if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.clk[2] = clock64(); p.clk[3] = (long long)ns;
+  }
   if (kTimeline && p.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -1473,6 +1445,8 @@ __global__ void dirterm_kernel(const float* __restrict__ in, int stride, int mod
 // ------------------------------------------------------------------------------------------------ host side
 static long long* g_tc_timeline = nullptr;
 void tc_set_timeline(long long* dev_buf) { g_tc_timeline = dev_buf; }
+static long long* g_tc_clock = nullptr;                  // [3 networks][4] int64 (pn_debug_tc_clock)
+void tc_set_clock(long long* dev_buf) { g_tc_clock = dev_buf; }
 
 struct TcLayout {
   int kblocks[kMaxLayers];
@@ -1680,7 +1654,7 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   p.in0 = pts; p.in_stride = 3; p.M = M; p.out = raw;
   p.vdir = viewdirs; p.vdir_stride = viewdir_stride; p.dir_div = S > 0 ? S : 1;
   p.alpha_row = kClassicAlphaRow; p.alpha_bias = n.alpha_bias;
-  p.error_flag = n.error_flag; p.timeline = nullptr; p.split = 0; p.reorder = 0;
+  p.error_flag = n.error_flag; p.timeline = nullptr; p.clk = g_tc_clock ? g_tc_clock + 8 : nullptr; p.split = 0; p.reorder = 0;
   p.n_phases = 13;
   for (int i = 0; i < 13; ++i) {
     const ClassicPhase& c = kClassicPhases[i];
@@ -1755,6 +1729,7 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
   p.head_linear = ~nonlinear_blocks;
   p.error_flag = n.error_flag;
   p.timeline = g_tc_timeline;
+  p.clk = g_tc_clock ? g_tc_clock + 4 * (n.net_id == PN_NET_SAMPLER ? 0 : n.net_id == PN_NET_REFINE ? 1 : 2) : nullptr;
   {
     // schedule knobs (defaults = the measured best; the environment overrides are a tuning aid)
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;

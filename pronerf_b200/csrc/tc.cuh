@@ -25,6 +25,7 @@ int tc_load_net(NetTC& n, int net_id, int n_layers, const int* in_dims, const in
                 const float* const* b, cudaStream_t stream);
 bool tc_available();
 void tc_set_timeline(long long* dev_buf);   // debug: clock64 stamps of CTA 0's second tile (208 slots)
+void tc_set_clock(long long* dev_buf);      // measurement aid: per network {clock64, globaltimer} at the start and end of CTA 0 (12 slots)
 int tc_launch_mlp(NetTC& n, const MlpLaunch& L, cudaStream_t stream);
 // device pointer to the 4 x 27 fp32 view-direction weights of a loaded DoNeRFTRT (NULL: not loaded / classic topology)
 const float* tc_wdir(const NetTC& n);
