@@ -145,7 +145,7 @@ struct Params {
   float4 head_tab[96];          // output column c: y = x * .w + (.y / (1 + 2^(x * .x)) + .z), x = accumulator + bias (head_coeffs)
   uint32_t head_linear;         // bit b: output columns [8b, 8b + 8) are all linear (or padding): y = x
   alignas(64) CUtensorMap tmap_in;   // IN_LOAD16: the [M, K0] fp16 input as a 2-D tensor, box = 64 columns x 128 rows, 128-byte swizzle
-  int reorder;                  // 1: slot 0's first layer of its next tile is issued BEFORE slot 1's output layer (see PN_WALK)
+  int share;                    // 1: a layer's weight blocks are streamed ONCE per unit and multiplied into both slots (see "weight sharing" below)
   int split;                    // hidden epilogues publish their first two K blocks early (two-step operand hand-over): bit 0 = all, bit 1 = first layer only
   int out_rpp;                  // rows per staging pass of the head output (multiple of 4)
   int* error_flag;
@@ -540,10 +540,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
     p.timeline[TL_CLK + 0] = clock64(); p.timeline[TL_CLK + 1] = (long long)ns;
   }
 
-  // The single-thread roles walk the same (slot, phase) sequence: the two slots alternate phase by phase.  With `reorder`, slot
-  // 0's FIRST layer of its next tile goes before slot 1's OUTPUT layer: slot 0's new operand is published by the hand-over warps
-  // a few hundred cycles after its output layer, while slot 1's output layer still waits for a whole hidden epilogue -- in the
-  // plain order the ready first layer would sit behind it in the in-order MMA stream (head-of-line).
+  // The single-thread roles walk the same (slot, phase) sequence: the two slots alternate phase by phase.  (Round 2 also measured
+  // slot 0's first layer of its next tile issued BEFORE slot 1's output layer, which the hand-over warps make possible: +-0 in a
+  // train of launches, and it breaks the adjacency the weight sharing below needs.)
   struct Cursor {
     long long n_pairs, stride, tile0, tile1;
     int np, ph0, ph1;
@@ -559,31 +558,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
   cur.n_pairs = n_pairs; cur.stride = 2 * n_clusters; cur.np = p.n_phases;
   cur.ph0 = cur.ph1 = 0;
   cur.tile0 = 2 * cluster_id; cur.tile1 = 2 * cluster_id + 1;
-  const bool walk_reorder = p.reorder != 0;
+  // Weight sharing: in the plain alternating order slot 1's phase follows slot 0's SAME phase, so the layer's blocks need to come
+  // through the ring only once per unit: slot 0 multiplies them without releasing the ring slots, slot 1 multiplies them again
+  // and releases.  A layer's blocks (<= 4) fit the 5-slot ring, and the prefetch distance stays what it was (a block's slot is
+  // refilled 2.2 K cycles before the next layer needs it).  Halves the L2 -> shared-memory weight traffic (7 GB per 571 536-ray
+  // NeRF launch, 4.5 % of that kernel's energy: profiles/r02_handover/sustained_power_nerf_without_weight_stream.txt).
+  // shared_step(): called in body(0) BEFORE the cursor advances -- both slots live and at the same phase.
+  const bool walk_share = p.share != 0;
+  auto shared_step = [&]() { return walk_share && cur.live(1) && cur.ph0 == cur.ph1; };
   const long long tl_tile0 = 2 * cluster_id + cur.stride;           // timeline: the second tile of slot 0 / slot 1
   // run body(0), body(1) alternately until both slots are out of tiles.  ONE copy of the body (the slot index is a
   // run-time value): two inlined copies overflow the instruction cache.
-#define PN_WALK(body)                                                                    \
-  {                                                                                      \
-    bool skip0 = false;                                                                  \
-    for (;;) {                                                                           \
-      bool any = false;                                                                  \
-      _Pragma("unroll 1")                                                                \
-      for (int t_ = 0; t_ < 2; ++t_) {                                                   \
-        int tt = t_;                                                                     \
-        if (!cur.live(tt)) continue;                                                     \
-        any = true;                                                                      \
-        if (tt == 0 && skip0) { skip0 = false; continue; }                               \
-        if (tt == 1 && walk_reorder && cur.ph1 == cur.np - 1 && cur.ph0 == 0 && cur.live(0)) { \
-          skip0 = true;                                                                  \
-          tt = 0;                                                                        \
-          --t_;                      /* slot 0 first, then come back for slot 1 */       \
-        }                                                                                \
-        body(tt);                                                                        \
-        cur.advance(tt);                                                                 \
-      }                                                                                  \
-      if (!any) break;                                                                   \
-    }                                                                                    \
+#define PN_WALK(body)                                                        \
+  for (;;) {                                                                 \
+    bool any = false;                                                        \
+    _Pragma("unroll 1")                                                      \
+    for (int t_ = 0; t_ < 2; ++t_) {                                         \
+      if (!cur.live(t_)) continue;                                           \
+      any = true;                                                            \
+      body(t_);                                                              \
+      cur.advance(t_);                                                       \
+    }                                                                        \
+    if (!any) break;                                                         \
   }
 
   // Register hand-over between the warpgroups (one static instruction per warpgroup, warpgroup-aligned): the role warpgroup and
@@ -595,7 +591,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
     // =============================== weight producer (both CTAs) ===============================
     if (lane == 0) {
       uint32_t slot = 0, ring_par = 1;                       // empty barriers: the first pass over the ring is free
+      bool shared = false;
       auto body = [&](int t) {
+        if (t == 0) shared = shared_step();
+        else if (shared) return;                             // slot 1 multiplies the blocks slot 0's step has brought
         const int ph = cur.ph(t);
         const bool merged = p.ph[ph].merged != 0;
         const int nchunks = merged ? 1 : p.ph[ph].nkb;
@@ -615,7 +614,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
     if (lane == 0 && rank != 0) {
       // =============================== follower: weights-landed relay ===============================
       uint32_t slot = 0, ring_par = 0;
+      bool shared = false;
       auto body = [&](int t) {
+        if (t == 0) shared = shared_step();
+        else if (shared) return;
         const int ph = cur.ph(t);
         const int n = p.ph[ph].merged ? 1 : p.ph[ph].nkb;
         for (int i = 0; i < n; ++i) {
@@ -645,8 +647,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
         umma_f16_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
       };
       auto ring_next = [&]() { if (++slot == N_RING) { slot = 0; ring_par ^= 1u; } };
+      bool shared = false;
+      uint32_t shared_slot = 0, shared_par = 0;
       auto body = [&](int t) {
         const int ph = cur.ph(t);
+        // weight sharing: slot 0's step leaves the layer's blocks in the ring, slot 1's step revisits them and releases
+        bool do_wait = true, do_release = true;
+        if (t == 0) {
+          shared = shared_step();
+          if (shared) { do_release = false; shared_slot = slot; shared_par = ring_par; }
+        } else if (shared) {
+          do_wait = false; slot = shared_slot; ring_par = shared_par;
+        }
         const bool tl_on = kTimeline && blockIdx.x == 0 && cur.tile(t) == tl_tile0 + t && lane == 0;
         const int nkb = p.ph[ph].nkb, k16_last = p.ph[ph].k16_last;
         const uint32_t acc0 = (uint32_t)p.ph[ph].acc;
@@ -664,27 +676,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
         tl_mark(p.timeline, tl_on, TL_MMA0 + ph * 2 + t);
         if (nkb == 4 && k16_last == 4 && !merged) {
           // the standard full-width layer: straight-line issue, 2 K blocks per operand half
-          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
           tc_fence_after();
-          if (elect_one()) { issue_block(d_tmem, a_lo_t, b_lo0 + slot * kRing, idesc, acc0); umma_commit_pair(bar_empty(slot)); }
+          if (elect_one()) { issue_block(d_tmem, a_lo_t, b_lo0 + slot * kRing, idesc, acc0); if (do_release) umma_commit_pair(bar_empty(slot)); }
           __syncwarp();
           ring_next();
-          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
           tc_fence_after();
-          if (elect_one()) { issue_block(d_tmem, a_lo_t + kBlk, b_lo0 + slot * kRing, idesc, 1u); umma_commit_pair(bar_empty(slot)); }
+          if (elect_one()) { issue_block(d_tmem, a_lo_t + kBlk, b_lo0 + slot * kRing, idesc, 1u); if (do_release) umma_commit_pair(bar_empty(slot)); }
           __syncwarp();
           ring_next();
           mbar_wait(bar_aready(t, 1), par1, p.error_flag, 2);
-          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
           tc_fence_after();
-          if (elect_one()) { issue_block(d_tmem, a_lo_t + 2 * kBlk, b_lo0 + slot * kRing, idesc, 1u); umma_commit_pair(bar_empty(slot)); }
+          if (elect_one()) { issue_block(d_tmem, a_lo_t + 2 * kBlk, b_lo0 + slot * kRing, idesc, 1u); if (do_release) umma_commit_pair(bar_empty(slot)); }
           __syncwarp();
           ring_next();
-          mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+          if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
           tc_fence_after();
           if (elect_one()) {
             issue_block(d_tmem, a_lo_t + 3 * kBlk, b_lo0 + slot * kRing, idesc, 1u);
-            umma_commit_pair(bar_empty(slot));
+            if (do_release) umma_commit_pair(bar_empty(slot));
             umma_commit_pair(bar_done);
           }
           __syncwarp();
@@ -695,7 +707,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
           const uint32_t half16 = (uint32_t)p.ph[ph].n_pad * 4u;      // one K block of this CTA's weight half, in 16-byte units
           uint32_t a_lo = a_lo_t;
           if (merged) {
-            mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+            if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
             tc_fence_after();
             if (elect_one()) {
               uint32_t b_lo = b_lo0 + slot * kRing;
@@ -704,13 +716,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
                 a_lo += kBlk;
                 b_lo += half16;
               }
-              umma_commit_pair(bar_empty(slot));
+              if (do_release) umma_commit_pair(bar_empty(slot));
             }
             __syncwarp();
             ring_next();
           } else {
             for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
+              if (do_wait) mbar_wait(bar_full(slot), ring_par, p.error_flag, 3);
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t b_lo = b_lo0 + slot * kRing;
@@ -720,7 +732,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(ACT), 1) m
                   const uint64_t a_desc = ((uint64_t)kDescHi << 32) | a_lo, b_desc = ((uint64_t)kDescHi << 32) | b_lo;
                   for (int s2 = 0; s2 < k16_last; ++s2) umma_f16_pair(d_tmem, a_desc + 2u * s2, b_desc + 2u * s2, idesc, acc0 | (uint32_t)(kb | s2));
                 }
-                umma_commit_pair(bar_empty(slot));           // ring slot is free (in both CTAs) once these MMAs have read it
+                if (do_release) umma_commit_pair(bar_empty(slot));           // ring slot is free (in both CTAs) once these MMAs have read it
               }
               __syncwarp();
               a_lo += kBlk;
@@ -1633,11 +1645,6 @@ static int tc_encode_input_map(CUtensorMap* map, const void* base, long long M, 
   if (rc != CUDA_SUCCESS) { set_error("tc: cuTensorMapEncodeTiled failed (%d) for a [%lld, %d] fp16 input", (int)rc, M, k0); return PN_ECUDA; }
   return PN_OK;
 }
-// schedule knob (default = the measured best; the environment override is a tuning aid): see PN_WALK
-static int tc_env_reorder() {
-  static const int v = getenv("PN_TC_REORDER") ? atoi(getenv("PN_TC_REORDER")) : 1;
-  return v != 0;
-}
 
 // run_network with the classic NeRF: pts [M,3] (M = N*S rows), per-ray view directions, both encoded in-kernel -> raw [M,4]
 int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, int viewdir_stride, int S, int64_t M, float* raw,
@@ -1654,7 +1661,7 @@ int tc_launch_nerf_classic(NetTC& n, const float* pts, const float* viewdirs, in
   p.in0 = pts; p.in_stride = 3; p.M = M; p.out = raw;
   p.vdir = viewdirs; p.vdir_stride = viewdir_stride; p.dir_div = S > 0 ? S : 1;
   p.alpha_row = kClassicAlphaRow; p.alpha_bias = n.alpha_bias;
-  p.error_flag = n.error_flag; p.timeline = nullptr; p.clk = g_tc_clock ? g_tc_clock + 8 : nullptr; p.split = 0; p.reorder = 0;
+  p.error_flag = n.error_flag; p.timeline = nullptr; p.clk = g_tc_clock ? g_tc_clock + 8 : nullptr; p.split = 0; p.share = 1;
   p.n_phases = 13;
   for (int i = 0; i < 13; ++i) {
     const ClassicPhase& c = kClassicPhases[i];
@@ -1734,7 +1741,8 @@ int tc_launch_mlp(NetTC& n, const MlpLaunch& Lc, cudaStream_t stream) {
     // schedule knobs (defaults = the measured best; the environment overrides are a tuning aid)
     static const int env_split = getenv("PN_TC_SPLIT") ? atoi(getenv("PN_TC_SPLIT")) : -1;
     p.split = env_split >= 0 ? env_split : 0;            // bit 0: every hidden epilogue, bit 1: the first layer's only
-    p.reorder = tc_env_reorder() && tc::use_handover(Lc.act);       // only the hand-over shape has a short output turn-around to exploit
+    static const int env_share = getenv("PN_TC_SHARE") ? atoi(getenv("PN_TC_SHARE")) : 1;
+    p.share = env_share != 0;
     p.out_rpp = 0;         // (the hand-over warps derive the rows per staging pass from the chunk width)
   }
   if (Lc.input_mode == IN_LOAD16) {
