@@ -863,6 +863,47 @@ def test_cuda_graph_replay(ops):
         assert torch.equal(batch["rgb"], rgb_e) and torch.equal(batch["depth"], depth_e)
 
 
+def test_tc_clock_stamps_and_weight_sharing_odd_tiles(ops):
+    """(i) pn_debug_tc_clock: CTA 0 of every tensor-core MLP launch stamps {clock64, %globaltimer} at its start and end -- SM cycles
+    over wall time must be a plausible SM clock and the render must not change; (ii) the weight blocks are streamed once per unit
+    and multiplied into both slots: row counts that leave slot 1 without a tile in the last unit (an odd number of 256-row pair
+    tiles, a single tile) must give the same rows as the full batch."""
+    _bf16_ready(ops)
+    from pronerf_b200 import _abi
+    from pronerf_b200.engine import Renderer
+    scene = synth.make_small_scene(H=40, W=52)                    # 2080 rays/view: 16 640 NeRF rows = 65 pair tiles (odd)
+    sd = synth.make_weights(seed=4, calibrated=True)
+    R = Renderer(sd, scene.images_ref, scene.poses_ref, scene.K, scene.H, scene.W, precision="bf16", device=DEV)
+    batch = R.prepare_views([scene.poses[0]])
+    rgb0, depth0 = R.render_prepared(batch)
+    rgb0, depth0 = rgb0.clone(), depth0.clone()
+    clk = torch.zeros(12, dtype=torch.int64, device=DEV)
+    assert _abi.lib().pn_debug_tc_clock(clk.data_ptr()) == 0
+    try:
+        rgb1, depth1 = R.render_prepared(batch)
+        torch.cuda.synchronize()
+    finally:
+        _abi.lib().pn_debug_tc_clock(None)
+    assert torch.equal(rgb1, rgb0) and torch.equal(depth1, depth0)
+    c = clk.cpu().tolist()
+    for i, name in enumerate(("sampler", "refine", "nerf")):
+        cyc, ns = c[4 * i + 2] - c[4 * i], c[4 * i + 3] - c[4 * i + 1]
+        assert cyc > 0 and ns > 0, (name, c)
+        assert 0.5 < cyc / ns < 2.3, (name, cyc / ns)            # GHz
+    # ragged prefixes through the public render(): 1 pair tile, 3 pair tiles (slot 1 idle in the last unit), 2 full units + 1 row
+    sd2 = synth.make_weights(seed=1, calibrated=True)
+    nets = make_modules(sd2, DEV, precision="bf16")
+    kw = make_kwargs(nets, scene, DEV, precision="bf16")
+    from pronerf_b200.render import prepare_view, render
+    with torch.no_grad():
+        rays, or_rays, sh = prepare_view(scene.poses[0], scene.hwf, scene.K, kw)
+        ck = call_kwargs(kw)
+        full, _, dfull, _ = render(rays, or_rays, sh, **ck)
+        for n in (32, 96, 129, 256, 257, 1025):                  # x 8 samples = NeRF rows; sampler / refine rows = n
+            r, _, d, _ = render(rays[:n], or_rays[:n], (n, 3), **ck)
+            assert torch.equal(r, full.reshape(-1, 3)[:n]) and torch.equal(d, dfull.reshape(-1)[:n]), n
+
+
 def test_bf16_edge_cases(ops):
     _bf16_ready(ops)
     scene = synth.make_small_scene(H=16, W=20)
