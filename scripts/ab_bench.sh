@@ -10,6 +10,8 @@
 #   (cd /tmp/prev/x/y/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared \
 #        -o $OLDPWD/build_ab/libprev.so api.cu elementwise.cu gather.cu mlp_f32.cu mlp_prog.cu mlp_tc.cu)
 #   gpurun --timeout 400 -- 'bash scripts/ab_bench.sh'
+# (the loader binds every symbol of include/pronerf_b200.h: <rev> must not be older than the newest entry point, pn_debug_tc_clock;
+#  scripts/tc_power.py does the same A/B as trains of launches at the board's power limit, scripts/tc_timeline.py in cycles)
 for i in 1 2; do
 for L in "" build_ab/libprev.so; do
   if [ -n "$L" ]; then export PN_B200_LIB=$PWD/$L; else unset PN_B200_LIB; fi
