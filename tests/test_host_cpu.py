@@ -310,3 +310,88 @@ def test_host_pass_chunk_rule():
             for rpu in (512, 64):               # sampler / refine units, NeRF units at S = 8
                 assert waves(n_a, rpu) + waves(n - n_a, rpu) == waves(n, rpu)
     assert split(571536) == 13 * 37888 and split(1000) == 0
+
+
+def test_weight_ring_protocol_with_sharing():
+    """The tensor-core MLP kernel's weight ring (mlp_tc.cu: producer / MMA issuer, `shared_step()`): each layer's K-block chunks are
+    streamed ONCE per 512-row unit and multiplied into both row tiles ("slots") -- slot 0's pass over a phase reads the chunks without
+    releasing their ring slots, slot 1's pass revisits the same ring slots and releases them.  Restated as a discrete simulation of the
+    two roles over the phase tables of every network (5 ring slots): the walk never deadlocks, every chunk lands before it is read,
+    no ring slot is refilled while a pass still has to read it, every loaded chunk is read by exactly as many passes as there are live
+    slots in that unit, and the stream is half of the unshared one when both slots are live."""
+    N_RING = 5
+    tables = {                                    # chunks per phase (merged narrow output layers = one chunk)
+        "sampler (in-kernel Pluecker)": [1] + [4] * 5 + [1],
+        "sampler (288 loaded inputs)": [4, 1] + [4] * 5 + [1],
+        "refine S=8": [3] + [4] * 5 + [1],
+        "refine S=16": [4, 1] + [4] * 5 + [4],     # 288-wide rows: two operand phases; 80-wide output layer: not merged
+        "DoNeRFTRT": [1] + [4] * 6 + [1],
+        "classic NeRF": [1, 4, 4, 4, 4, 4, 1, 4, 4, 4, 4, 1, 1],
+    }
+
+    def run(phases, tiles0, tiles1, share):
+        np_ = len(phases)
+
+        def walk():                               # PN_WALK: (slot, phase, shared) steps, slots alternating phase by phase
+            t = [0, 0]; ph = [0, 0]; left = [tiles0, tiles1]
+            while left[0] > 0 or left[1] > 0:
+                shared = False
+                for s in (0, 1):
+                    if left[s] <= 0:
+                        continue
+                    if s == 0:
+                        shared = share and left[1] > 0 and ph[0] == ph[1]
+                    yield s, ph[s], shared
+                    ph[s] += 1
+                    if ph[s] == np_:
+                        ph[s] = 0; left[s] -= 1
+        steps = list(walk())
+        # producer program: (ring uses) in order; MMA program: per step the list of (use index, wait?, release?)
+        loads, mma = [], []
+        start_of_shared = None
+        for s, p_, shared in steps:
+            if s == 1 and shared:
+                mma.append([(u, False, True) for u in start_of_shared])
+                continue
+            uses = list(range(len(loads), len(loads) + phases[p_]))
+            loads.extend(uses)
+            if s == 0 and shared:
+                start_of_shared = uses
+                mma.append([(u, True, False) for u in uses])
+            else:
+                mma.append([(u, True, True) for u in uses])
+        n_uses = len(loads)
+        landed = [False] * n_uses; released = [False] * n_uses; reads = [0] * n_uses
+        pi = 0; mi = 0; mj = 0
+        while pi < n_uses or mi < len(mma):
+            progressed = False
+            while pi < n_uses and (pi < N_RING or released[pi - N_RING]):      # the slot's previous occupant has been released
+                if pi >= N_RING:
+                    assert reads[pi - N_RING] >= 1
+                landed[pi] = True; pi += 1; progressed = True
+            while mi < len(mma):
+                if mj == len(mma[mi]):
+                    mi += 1; mj = 0; progressed = True
+                    continue
+                u, wait, release = mma[mi][mj]
+                if not landed[u]:
+                    break
+                assert not released[u], "a pass reads a ring slot that was already handed back"
+                assert u + N_RING >= n_uses or not landed[u + N_RING], "ring slot refilled under a reader"
+                reads[u] += 1
+                if release:
+                    released[u] = True
+                mj += 1; progressed = True
+            assert progressed, "deadlock"
+        assert all(released)
+        return n_uses, reads
+
+    for name, phases in tables.items():
+        assert max(phases) <= N_RING - 1, name                                  # a shared layer leaves one slot for the prefetch
+        for tiles0, tiles1 in ((3, 3), (3, 2), (1, 0), (1, 1)):
+            n_shared, reads = run(phases, tiles0, tiles1, True)
+            n_plain, reads_plain = run(phases, tiles0, tiles1, False)
+            assert set(reads_plain) == {1}
+            assert n_plain == sum(phases) * (tiles0 + tiles1)
+            assert n_shared == sum(phases) * tiles0, (name, tiles0, tiles1)     # slot 1 never loads: it always has a partner pass
+            assert sum(reads) == n_plain and set(reads) <= {1, 2}
